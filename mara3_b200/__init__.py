@@ -1,0 +1,326 @@
+"""mara3_b200 -- B200-native implementation of Mara3's `binary` isothermal-2D hot path.
+
+This package is a thin ctypes view of the C ABI in ``include/mara3_b200.h``
+(``mara3_b200/libmara3_b200.so``, built from ``mara3_b200/csrc`` for sm_100a).
+The names mirror the reference's operator API for the path
+(Mara3 ``src/subprog_binary.hpp:180-208``):
+
+    solver   = mara3_b200.create_solver_data(depth=4, block_size=64, ...)   # create_run_config + create_solver_data
+    solution = solver.create_solution()                                     # binary::create_solution
+    dt       = solver.maximum_timestep(solution)                            # binary::maximum_timestep
+    s1       = solver.advance(solution, dt)                                 # binary::advance
+    solver.next_solution(solution)                                          # binary::next_solution (in place)
+
+There is no CPU compute path: without the compiled CUDA library, or without a
+GPU, every compute call raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+__all__ = ["create_solver_data", "Solver", "Solution", "NegativeDensity", "Mara3Error", "library_path", "load_library"]
+
+NUM_SCALARS = 43
+OK, NEGATIVE_DENSITY, UNBOUND_ORBIT, UNSUPPORTED = 0, 1, 2, 3
+FLAG_GENERAL_ONLY = 1   # every block through the any-tree kernels (tests)
+FLAG_HOST_ONLY = 2      # mesh / solver_data queries only; no device context
+
+SCALAR_NAMES = (
+    ["time", "iter_num", "iter_den"]
+    + [f"mass_accreted_on[{k}]" for k in range(2)]
+    + [f"angular_momentum_accreted_on[{k}]" for k in range(2)]
+    + [f"integrated_torque_on[{k}]" for k in range(2)]
+    + [f"work_done_on[{k}]" for k in range(2)]
+    + ["mass_ejected", "angular_momentum_ejected"]
+    + [f"orbital_elements_acc[{k}]" for k in range(10)]
+    + [f"orbital_elements_grav[{k}]" for k in range(10)]
+    + [f"orbital_elements[{k}]" for k in range(10)]
+)
+
+
+class Mara3Error(RuntimeError):
+    pass
+
+
+class NegativeDensity(Mara3Error):
+    """The reference's std::runtime_error("negative density in updated state")."""
+
+    def __init__(self, message, lines):
+        super().__init__(message)
+        self.lines = lines
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmara3_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load the C-ABI library; fail loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise Mara3Error(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C mara3_b200/csrc`; mara3_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.m3b_version.restype = C.c_char_p
+    L.m3b_global_error.restype = C.c_char_p
+    L.m3b_solver_create.restype = vp
+    L.m3b_solver_create.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    L.m3b_solver_destroy.argtypes = [vp]
+    L.m3b_last_error.restype = C.c_char_p
+    L.m3b_last_error.argtypes = [vp]
+    for name in ("num_blocks", "block_size", "num_regular_blocks", "num_messages"):
+        getattr(L, "m3b_" + name).argtypes = [vp]
+    L.m3b_num_cells.argtypes = [vp]
+    L.m3b_num_cells.restype = C.c_int64
+    L.m3b_tree_index.argtypes = [vp, C.POINTER(C.c_int64)]
+    for name in ("vertices", "cell_centers", "cell_areas", "buffer_rate_field", "initial_conserved_u"):
+        getattr(L, "m3b_" + name).argtypes = [vp, dp]
+    for name in ("recommended_time_step", "gst_suppr_radius", "density_floor"):
+        fn = getattr(L, "m3b_" + name)
+        fn.argtypes = [vp]
+        fn.restype = C.c_double
+    L.m3b_config_get.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.m3b_solution_create.restype = vp
+    L.m3b_solution_create.argtypes = [vp]
+    L.m3b_solution_clone.restype = vp
+    L.m3b_solution_clone.argtypes = [vp, vp]
+    L.m3b_solution_destroy.argtypes = [vp]
+    L.m3b_solution_set_conserved.argtypes = [vp, vp, dp]
+    L.m3b_solution_get_conserved.argtypes = [vp, vp, dp]
+    L.m3b_solution_set_scalars.argtypes = [vp, dp]
+    L.m3b_solution_get_scalars.argtypes = [vp, dp]
+    L.m3b_maximum_timestep.argtypes = [vp, vp, dp]
+    L.m3b_advance.argtypes = [vp, vp, C.c_double, C.c_int, vp]
+    L.m3b_solution_combine.argtypes = [vp, vp, vp, C.c_double, vp]
+    L.m3b_next_solution.argtypes = [vp, vp, dp, ip]
+    L.m3b_run_steps.argtypes = [vp, vp, C.c_int, ip]
+    L.m3b_advance_host.argtypes = [vp, dp, dp, C.c_double, C.c_int, dp, dp]
+    L.m3b_next_solution_host.argtypes = [vp, dp, dp, dp, dp, dp, ip]
+    L.m3b_message.argtypes = [vp, C.c_int]
+    L.m3b_message.restype = C.c_char_p
+    L.m3b_set_quiet.argtypes = [vp, C.c_int]
+    L.m3b_kernel_launches.argtypes = [vp]
+    L.m3b_kernel_launches.restype = C.c_uint64
+    L.m3b_stage_timing.argtypes = [vp, C.c_int]
+    L.m3b_stage_timing_read.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+    L.m3b_synchronize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _host_array(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != tuple(shape):
+        raise ValueError(f"expected an array of shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class Solution:
+    """binary::solution_t -- conserved field resident on the GPU plus host scalars."""
+
+    def __init__(self, solver, handle):
+        if not handle:
+            raise Mara3Error(solver._error())
+        self.solver = solver
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.m3b_solution_destroy(self._h)
+            self._h = None
+
+    def clone(self):
+        return Solution(self.solver, _lib.m3b_solution_clone(self.solver._h, self._h))
+
+    @property
+    def conserved_u(self):
+        """Download as [B][3][N][N] (sigma, px, py)."""
+        s = self.solver
+        a = np.empty((s.num_blocks, 3, s.block_size, s.block_size), dtype=np.float64)
+        s._check(_lib.m3b_solution_get_conserved(s._h, self._h, _dptr(a)))
+        return a
+
+    @conserved_u.setter
+    def conserved_u(self, a):
+        s = self.solver
+        a = _host_array(a, (s.num_blocks, 3, s.block_size, s.block_size))
+        s._check(_lib.m3b_solution_set_conserved(s._h, self._h, _dptr(a)))
+
+    @property
+    def scalars(self):
+        a = np.empty(NUM_SCALARS, dtype=np.float64)
+        _lib.m3b_solution_get_scalars(self._h, _dptr(a))
+        return a
+
+    @scalars.setter
+    def scalars(self, a):
+        a = _host_array(a, (NUM_SCALARS,))
+        _lib.m3b_solution_set_scalars(self._h, _dptr(a))
+
+    @property
+    def time(self):
+        return float(self.scalars[0])
+
+    @property
+    def iteration(self):
+        s = self.scalars
+        return int(s[1]), int(s[2])
+
+
+class Solver:
+    """run_config + solver_data_t + the device context (one GPU)."""
+
+    def __init__(self, config=None, device=0, general_only=False, host_only=False, quiet=True, argv=None, **keys):
+        L = load_library()
+        items = dict(config or {})
+        items.update(keys)
+        tokens = list(argv or []) + [f"{k}={_format(v)}" for k, v in items.items()]
+        arr = (C.c_char_p * max(1, len(tokens)))(*[t.encode() for t in tokens])
+        flags = (FLAG_GENERAL_ONLY if general_only else 0) | (FLAG_HOST_ONLY if host_only else 0)
+        self._h = L.m3b_solver_create(len(tokens), arr, int(device), flags)
+        if not self._h:
+            raise Mara3Error(L.m3b_global_error().decode())
+        self.host_only = host_only
+        self.num_blocks = L.m3b_num_blocks(self._h)
+        self.block_size = L.m3b_block_size(self._h)
+        self.num_cells = L.m3b_num_cells(self._h)
+        L.m3b_set_quiet(self._h, int(quiet))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.m3b_solver_destroy(self._h)
+            self._h = None
+
+    # ---- errors -------------------------------------------------------------------------------
+    def _error(self):
+        return _lib.m3b_last_error(self._h).decode()
+
+    def messages(self):
+        return [_lib.m3b_message(self._h, n).decode() for n in range(_lib.m3b_num_messages(self._h))]
+
+    def _check(self, status):
+        if status == OK:
+            return
+        if status == NEGATIVE_DENSITY:
+            raise NegativeDensity("negative density in updated state", self.messages())
+        raise Mara3Error(self._error() or f"status {status}")
+
+    # ---- solver_data --------------------------------------------------------------------------
+    def _get(self, name, shape, dtype=np.float64):
+        a = np.empty(shape, dtype=dtype)
+        ptr = a.ctypes.data_as(C.POINTER(C.c_int64 if dtype == np.int64 else C.c_double))
+        getattr(_lib, "m3b_" + name)(self._h, ptr)
+        return a
+
+    tree_index = property(lambda s: s._get("tree_index", (s.num_blocks, 3), np.int64))
+    vertices = property(lambda s: s._get("vertices", (s.num_blocks, 2, s.block_size + 1, s.block_size + 1)))
+    cell_centers = property(lambda s: s._get("cell_centers", (s.num_blocks, 2, s.block_size, s.block_size)))
+    cell_areas = property(lambda s: s._get("cell_areas", (s.num_blocks, s.block_size, s.block_size)))
+    buffer_rate_field = property(lambda s: s._get("buffer_rate_field", (s.num_blocks, s.block_size, s.block_size)))
+    initial_conserved_u = property(lambda s: s._get("initial_conserved_u", (s.num_blocks, 3, s.block_size, s.block_size)))
+    recommended_time_step = property(lambda s: _lib.m3b_recommended_time_step(s._h))
+    gst_suppr_radius = property(lambda s: _lib.m3b_gst_suppr_radius(s._h))
+    density_floor = property(lambda s: _lib.m3b_density_floor(s._h))
+    num_regular_blocks = property(lambda s: _lib.m3b_num_regular_blocks(s._h))
+    kernel_launches = property(lambda s: int(_lib.m3b_kernel_launches(s._h)))
+
+    def config(self, key):
+        buf = C.create_string_buffer(1024)
+        if _lib.m3b_config_get(self._h, key.encode(), buf, 1024):
+            raise KeyError("config has no option " + key)
+        return buf.value.decode()
+
+    # ---- the operator API ---------------------------------------------------------------------
+    def create_solution(self):
+        return Solution(self, _lib.m3b_solution_create(self._h))
+
+    def maximum_timestep(self, solution):
+        dt = C.c_double(0.0)
+        self._check(_lib.m3b_maximum_timestep(self._h, solution._h, C.byref(dt)))
+        return dt.value
+
+    def advance(self, solution, dt, safe_mode=False):
+        """binary::advance: returns the new solution; raises NegativeDensity like the reference throws."""
+        out = solution.clone()
+        status = _lib.m3b_advance(self._h, solution._h, float(dt), int(safe_mode), out._h)
+        if status == NEGATIVE_DENSITY:
+            err = NegativeDensity("negative density in updated state", self.messages())
+            err.solution = out
+            raise err
+        self._check(status)
+        return out
+
+    def combine(self, a, b, b0):
+        """a * b0 + b * (1 - b0)."""
+        out = a.clone()
+        self._check(_lib.m3b_solution_combine(self._h, a._h, b._h, float(b0), out._h))
+        return out
+
+    def next_solution(self, solution):
+        """binary::next_solution in place -> (dt used, fell back to safe mode)."""
+        dt, fb = C.c_double(0.0), C.c_int(0)
+        self._check(_lib.m3b_next_solution(self._h, solution._h, C.byref(dt), C.byref(fb)))
+        return dt.value, bool(fb.value)
+
+    def run_steps(self, solution, count):
+        fb = C.c_int(0)
+        self._check(_lib.m3b_run_steps(self._h, solution._h, int(count), C.byref(fb)))
+        return fb.value
+
+    def advance_host(self, u, scalars, dt, safe_mode=False, out=None):
+        """binary::advance on host arrays (H2D + stage + D2H inside the call)."""
+        shape = (self.num_blocks, 3, self.block_size, self.block_size)
+        u = _host_array(u, shape)
+        scalars = _host_array(scalars, (NUM_SCALARS,))
+        u_out = np.empty(shape, dtype=np.float64) if out is None else out
+        s_out = np.empty(NUM_SCALARS, dtype=np.float64)
+        self._check(_lib.m3b_advance_host(self._h, _dptr(u), _dptr(scalars), float(dt), int(safe_mode), _dptr(u_out), _dptr(s_out)))
+        return u_out, s_out
+
+    def next_solution_host(self, u, scalars, out=None):
+        """binary::next_solution on host arrays -> (u, scalars, dt, fell_back)."""
+        shape = (self.num_blocks, 3, self.block_size, self.block_size)
+        u = _host_array(u, shape)
+        scalars = _host_array(scalars, (NUM_SCALARS,))
+        u_out = np.empty(shape, dtype=np.float64) if out is None else out
+        s_out = np.empty(NUM_SCALARS, dtype=np.float64)
+        dt, fb = C.c_double(0.0), C.c_int(0)
+        self._check(_lib.m3b_next_solution_host(self._h, _dptr(u), _dptr(scalars), _dptr(u_out), _dptr(s_out), C.byref(dt), C.byref(fb)))
+        return u_out, s_out, dt.value, bool(fb.value)
+
+    # ---- measurement helpers ------------------------------------------------------------------
+    def stage_timing(self, enable):
+        _lib.m3b_stage_timing(self._h, int(enable))
+
+    def stage_timing_read(self):
+        ms, n = C.c_double(0.0), C.c_uint64(0)
+        self._check(_lib.m3b_stage_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    def synchronize(self):
+        _lib.m3b_synchronize(self._h)
+
+
+def _format(v):
+    if isinstance(v, bool):
+        return str(int(v))
+    if isinstance(v, float):
+        return repr(v)
+    return str(v)
+
+
+def create_solver_data(config=None, **kwargs):
+    """create_run_config + create_solver_data + set_scheme_globals."""
+    return Solver(config, **kwargs)

@@ -1,0 +1,275 @@
+/**
+ * capi.cpp -- the extern "C" boundary declared in include/mara3_b200.h.
+ * Thin: argument checks, exception -> status code translation, layout copies.
+ */
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/mara3_b200.h"
+#include "scheme.hpp"
+
+using namespace m3b;
+
+struct m3b_solver
+{
+    std::unique_ptr<binary_solver_t> solver;
+    std::string error;
+};
+
+struct m3b_solution
+{
+    solution_t solution;
+};
+
+namespace
+{
+    thread_local std::string global_error;
+
+    template<typename Function>
+    int guarded(m3b_solver* s, Function&& fn)
+    {
+        try {
+            return fn();
+        }
+        catch (const std::exception& e)
+        {
+            if (s) s->error = e.what();
+            return M3B_ERROR;
+        }
+    }
+
+    template<typename T>
+    void copy_out(const std::vector<T>& v, T* out)
+    {
+        std::memcpy(out, v.data(), v.size() * sizeof(T));
+    }
+}
+
+extern "C" {
+
+const char* m3b_version(void) { return "mara3_b200 0.1 (sm_100a, fp64)"; }
+
+int m3b_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+const char* m3b_global_error(void) { return global_error.c_str(); }
+
+m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, int flags)
+{
+    try {
+        auto s = std::make_unique<m3b_solver>();
+        auto config = config_t::from_argv(argc, argv);
+        if (! config.get_string("restart").empty())
+            throw std::invalid_argument("restart= is handled by the checkpoint reader, not by m3b_solver_create");
+        s->solver = std::make_unique<binary_solver_t>(config, (flags & 2) ? -1 : device, (flags & 1) != 0);
+        return s.release();
+    }
+    catch (const std::exception& e)
+    {
+        global_error = e.what();
+        return nullptr;
+    }
+}
+
+void m3b_solver_destroy(m3b_solver_t* s) { delete s; }
+
+const char* m3b_last_error(const m3b_solver_t* s)
+{
+    if (! s) return global_error.c_str();
+    return s->error.empty() ? s->solver->last_error().c_str() : s->error.c_str();
+}
+
+int m3b_num_blocks(const m3b_solver_t* s) { return s->solver->solver_data().num_blocks; }
+int m3b_block_size(const m3b_solver_t* s) { return s->solver->solver_data().block_size; }
+int64_t m3b_num_cells(const m3b_solver_t* s) { return int64_t(s->solver->solver_data().num_cells()); }
+int m3b_num_regular_blocks(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().num_regular_blocks() : -1; }
+
+void m3b_tree_index(const m3b_solver_t* s, int64_t* out)
+{
+    const auto& d = s->solver->solver_data();
+    for (int b = 0; b < d.num_blocks; ++b)
+    {
+        out[3 * b + 0] = d.tree->index(b).level;
+        out[3 * b + 1] = d.tree->index(b).i;
+        out[3 * b + 2] = d.tree->index(b).j;
+    }
+}
+
+void m3b_vertices(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().vertices(), out); }
+void m3b_cell_centers(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().cell_centers(), out); }
+void m3b_cell_areas(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().cell_areas(), out); }
+void m3b_buffer_rate_field(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().buffer_rate_field, out); }
+
+void m3b_initial_conserved_u(const m3b_solver_t* s, double* out)
+{
+    // stored field-major [3][B][NN]; the ABI layout is block-major [B][3][NN]
+    const auto& d = s->solver->solver_data();
+    const std::size_t NN = d.cells_per_block(), FS = d.num_cells();
+    for (int b = 0; b < d.num_blocks; ++b)
+        for (int q = 0; q < 3; ++q)
+            std::memcpy(out + (std::size_t(b) * 3 + q) * NN, &d.initial_conserved_u[q * FS + b * NN], NN * sizeof(double));
+}
+
+double m3b_recommended_time_step(const m3b_solver_t* s) { return s->solver->solver_data().recommended_time_step; }
+double m3b_gst_suppr_radius(const m3b_solver_t* s) { return s->solver->solver_data().gst_suppr_radius; }
+double m3b_density_floor(const m3b_solver_t* s) { return s->solver->solver_data().density_floor; }
+
+int m3b_config_get(const m3b_solver_t* s, const char* key, char* out, int out_len)
+{
+    const auto& all = s->solver->run_config().all();
+    auto it = all.find(key);
+    if (it == all.end()) return 1;
+    auto ss = std::ostringstream();
+    std::visit([&ss] (const auto& v) { ss << v; }, it->second);
+    std::strncpy(out, ss.str().c_str(), out_len > 0 ? out_len - 1 : 0);
+    if (out_len > 0) out[out_len - 1] = 0;
+    return 0;
+}
+
+m3b_solution_t* m3b_solution_create(m3b_solver_t* s)
+{
+    try {
+        auto u = std::make_unique<m3b_solution>();
+        u->solution = s->solver->create_solution();
+        return u.release();
+    }
+    catch (const std::exception& e) { s->error = e.what(); return nullptr; }
+}
+
+m3b_solution_t* m3b_solution_clone(m3b_solver_t* s, const m3b_solution_t* u)
+{
+    try {
+        auto r = std::make_unique<m3b_solution>();
+        r->solution = s->solver->clone(u->solution);
+        return r.release();
+    }
+    catch (const std::exception& e) { s->error = e.what(); return nullptr; }
+}
+
+void m3b_solution_destroy(m3b_solution_t* u) { delete u; }
+
+int m3b_solution_set_conserved(m3b_solver_t* s, m3b_solution_t* u, const double* host)
+{
+    return guarded(s, [&] { s->solver->device().upload(host, *u->solution.conserved_u); s->solver->device().sync(); return M3B_OK; });
+}
+
+int m3b_solution_get_conserved(m3b_solver_t* s, const m3b_solution_t* u, double* host)
+{
+    return guarded(s, [&] { s->solver->device().download(*u->solution.conserved_u, host); return M3B_OK; });
+}
+
+void m3b_solution_set_scalars(m3b_solution_t* u, const double* in43) { u->solution.set_scalars(in43); }
+void m3b_solution_get_scalars(const m3b_solution_t* u, double* out43) { u->solution.get_scalars(out43); }
+
+int m3b_maximum_timestep(m3b_solver_t* s, const m3b_solution_t* u, double* dt_out)
+{
+    return guarded(s, [&] { *dt_out = s->solver->maximum_timestep(u->solution); return M3B_OK; });
+}
+
+int m3b_advance(m3b_solver_t* s, const m3b_solution_t* in, double dt, int safe_mode, m3b_solution_t* out)
+{
+    return guarded(s, [&] { s->error.clear(); return int(s->solver->advance(in->solution, dt, safe_mode != 0, out->solution)); });
+}
+
+int m3b_solution_combine(m3b_solver_t* s, const m3b_solution_t* a, const m3b_solution_t* b, double b0, m3b_solution_t* out)
+{
+    return guarded(s, [&] { s->solver->combine(a->solution, b->solution, b0, out->solution); return M3B_OK; });
+}
+
+int m3b_next_solution(m3b_solver_t* s, m3b_solution_t* u, double* dt_used, int* fell_back)
+{
+    return guarded(s, [&]
+    {
+        bool fb = false;
+        s->error.clear();
+        auto st = s->solver->next_solution(u->solution, dt_used, &fb);
+        if (fell_back) *fell_back = fb;
+        return int(st);
+    });
+}
+
+int m3b_run_steps(m3b_solver_t* s, m3b_solution_t* u, int count, int* num_fallbacks)
+{
+    return guarded(s, [&]
+    {
+        int fallbacks = 0;
+        s->error.clear();
+        for (int n = 0; n < count; ++n)
+        {
+            bool fb = false;
+            auto st = s->solver->next_solution(u->solution, nullptr, &fb);
+            fallbacks += fb;
+            if (st != status_ok) { if (num_fallbacks) *num_fallbacks = fallbacks; return int(st); }
+        }
+        if (num_fallbacks) *num_fallbacks = fallbacks;
+        return M3B_OK;
+    });
+}
+
+int m3b_advance_host(m3b_solver_t* s, const double* u_in, const double* scalars_in, double dt, int safe_mode, double* u_out, double* scalars_out)
+{
+    return guarded(s, [&]
+    {
+        auto& solver = *s->solver;
+        auto in = solution_t();
+        auto out = solution_t();
+        s->error.clear();
+        in.conserved_u = solver.new_field();
+        in.set_scalars(scalars_in);
+        solver.device().upload(u_in, *in.conserved_u);
+        auto st = solver.advance(in, dt, safe_mode != 0, out);
+        if (st == status_ok || st == status_negative_density)
+        {
+            solver.device().download(*out.conserved_u, u_out);
+            out.get_scalars(scalars_out);
+        }
+        return int(st);
+    });
+}
+
+int m3b_next_solution_host(m3b_solver_t* s, const double* u_in, const double* scalars_in, double* u_out, double* scalars_out, double* dt_used, int* fell_back)
+{
+    return guarded(s, [&]
+    {
+        auto& solver = *s->solver;
+        auto u = solution_t();
+        bool fb = false;
+        s->error.clear();
+        u.conserved_u = solver.new_field();
+        u.set_scalars(scalars_in);
+        solver.device().upload(u_in, *u.conserved_u);
+        auto st = solver.next_solution(u, dt_used, &fb);
+        if (fell_back) *fell_back = fb;
+        if (st == status_ok)
+        {
+            solver.device().download(*u.conserved_u, u_out);
+            u.get_scalars(scalars_out);
+        }
+        return int(st);
+    });
+}
+
+int m3b_num_messages(const m3b_solver_t* s) { return int(s->solver->last_messages().size()); }
+const char* m3b_message(const m3b_solver_t* s, int n) { return s->solver->last_messages().at(n).c_str(); }
+void m3b_set_quiet(m3b_solver_t* s, int quiet) { s->solver->set_quiet(quiet != 0); }
+uint64_t m3b_kernel_launches(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().launch_count() : 0; }
+void m3b_stage_timing(m3b_solver_t* s, int enable) { if (s->solver->has_device()) s->solver->device().set_stage_timing(enable != 0); }
+
+int m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches)
+{
+    return guarded(s, [&]
+    {
+        s->solver->device().collect_stage_timing();
+        *total_ms = s->solver->device().stage_kernel_ms_total();
+        *launches = s->solver->device().stage_kernel_launches();
+        return M3B_OK;
+    });
+}
+
+void m3b_synchronize(m3b_solver_t* s) { try { s->solver->device().sync(); } catch (...) {} }
+
+} // extern "C"

@@ -1,0 +1,114 @@
+/**
+ * device_solver.hpp -- device-resident state and kernel launches for the iso2d update.
+ *
+ * Host-visible interface of the CUDA side (kernels.cu).  One device_solver_t owns
+ * the static mesh data on one GPU (block geometry, neighbour tables, buffer-zone
+ * rate, initial state) and the scratch needed by a stage; device_field_t is a
+ * conserved state U in the device layout [field][block][i][j] (structure of
+ * arrays, y fastest -- the reference's row-major (N,N) block per tuple component).
+ */
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <vector>
+#include "solver_data.hpp"
+
+namespace m3b
+{
+    /** Reduced outputs of one stage launch (host copy). */
+    struct stage_result_t
+    {
+        double sums[16];        // dev::ACC_* / GRV_* / BUF_* running sums, already multiplied by cell area (not by dt)
+        double dt_min;          // min over cells of spacing / max wavespeed of the output state (if requested)
+        unsigned int num_negative;   // cells with sigma < 0 in the un-combined update (validate_u, scheme.cpp:726-752)
+        unsigned int pad;
+    };
+
+    struct offender_t { int block, cell; double sigma; };
+
+    struct stage_inputs_t
+    {
+        double time, dt, theta;
+        two_body_t bodies;
+        double rk_b0 = 0.0;
+        bool combine = false;       // out = Un * b0 + updated * (1 - b0)
+        bool compute_dt = false;
+    };
+
+    class device_field_t
+    {
+    public:
+        device_field_t(std::size_t num_doubles, int device);
+        ~device_field_t();
+        device_field_t(const device_field_t&) = delete;
+        device_field_t& operator=(const device_field_t&) = delete;
+        double* data = nullptr;
+        std::size_t count = 0;
+        int device = 0;
+    };
+
+    class device_solver_t
+    {
+    public:
+        /** general_only: route every block through the any-tree kernels (used by tests). */
+        device_solver_t(const solver_data_t& solver_data, int device, bool general_only = false);
+        ~device_solver_t();
+
+        int device() const { return device_id; }
+        std::size_t field_stride() const { return cells; }      // doubles per conserved component
+        std::size_t state_doubles() const { return 3 * cells; }
+        void* stream() const { return stream_; }
+
+        /** Copy a state between the host layout [B][3][N][N] and the device layout [3][B][N][N]. */
+        void upload(const double* host_block_major, device_field_t& dst);
+        void download(const device_field_t& src, double* host_block_major);
+        void copy(const device_field_t& src, device_field_t& dst);
+        void load_initial(device_field_t& dst);
+        /** dst = a * wa + b * wb (solution_t::operator+ / *, scheme.cpp:1033-1069) */
+        void combine(const device_field_t& a, double wa, const device_field_t& b, double wb, device_field_t& dst);
+
+        /**
+         * One RK stage, binary::advance_u phases P1-P8 + P11 (scheme.cpp:790-904):
+         * out = update(in) [optionally RK-combined with un].  Asynchronous; results
+         * land in the slot returned by stage_result() after sync().
+         */
+        void launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot);
+
+        /** binary::maximum_timestep (scheme.cpp:1107-1126) of a state; result in slot.dt_min. */
+        void launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot);
+
+        void sync();
+        const stage_result_t& stage_result(int slot) const { return host_results[slot]; }
+        std::vector<offender_t> offenders(int slot);
+
+        /** Number of kernel launches issued so far (bench.py reports it as gpu_launches). */
+        std::uint64_t launch_count() const { return launches; }
+
+        int num_regular_blocks() const { return num_regular; }
+
+        /** Per-kernel CUDA-event timing of the fused stage kernel (bench.py roofline). */
+        void set_stage_timing(bool on);
+        double stage_kernel_ms_total() const { return stage_ms_total; }
+        std::uint64_t stage_kernel_launches() const { return stage_timed_launches; }
+        void collect_stage_timing();
+
+        static constexpr int num_slots = 8;
+        static constexpr int max_offenders = 64;
+
+    private:
+        struct impl_t;
+        std::unique_ptr<impl_t> impl;
+        int device_id = 0;
+        int N = 0, B = 0;
+        std::size_t cells = 0;
+        void* stream_ = nullptr;
+        stage_result_t* host_results = nullptr;     // pinned
+        std::uint64_t launches = 0;
+        bool force_general = false;
+        int num_regular = 0;
+        bool stage_timing = false;
+        double stage_ms_total = 0.0;
+        std::uint64_t stage_timed_launches = 0;
+    };
+}

@@ -1,0 +1,268 @@
+/**
+ * iso2d_device.cuh -- point-wise device physics of the isothermal-2D `binary` update.
+ *
+ * fp64 throughout.  Each function names the reference routine it replaces
+ * (paths relative to Mara3 src/).  The arithmetic is algebraically the
+ * reference's but strength-reduced for the B200 fp64 pipe (the stage kernel is
+ * fp64-issue bound, not HBM bound): reciprocals / reciprocal square roots are a
+ * MUFU seed plus one cubically convergent correction (relative error < 1e-15),
+ * pow(x, 1.5) and pow(x, 0.5) become products of rsqrt, and exp() in the sink
+ * term is skipped where it underflows any possible contribution.  The allowed
+ * mismatch against the reference is 1e-12 relative per cell per step; the parity
+ * tests in tests/ measure it.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "iso2d_sums.hpp"
+
+namespace m3b { namespace dev {
+
+/** Per-run physical constants (solver_data_t scalars, subprog_binary.hpp:76-97). */
+struct model_t
+{
+    double softening_radius2;   // rs^2
+    double sink_rate;
+    double sink_inv_2s2;        // 1 / (2 sink_radius^2)
+    double inv_mach2;           // 1 / M^2
+    double inv_mach;
+    double alpha, nu, alpha_cutoff_radius;
+    double density_floor;
+    int axisymmetric_cs2;
+};
+
+/** Per-stage inputs (body positions at the stage time; scheme.cpp:814). */
+struct stage_t
+{
+    double time;        // solution.time of the stage input
+    double dt;
+    double theta;       // plm_theta, or 0 in safe mode (scheme.cpp:792)
+    double x1, y1, m1;  // body 1 position, mass
+    double x2, y2, m2;  // body 2
+    double rk_b0;       // if combine: out = Un * b0 + updated * (1 - b0)   (subprog_binary.cpp:272-275)
+    int combine;
+    int compute_dt;     // also reduce spacing / max wavespeed of the OUTPUT state (scheme.cpp:1107-1126)
+};
+
+struct prim_t { double s, vx, vy; };
+
+// ---------------------------------------------------------------------------
+// fast reciprocal / rsqrt: hardware seed (~2^-20) + one third-order step
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);                  // e = 1 - x y^2
+    double p = fma(0.375, e, 0.5);
+    return fma(y, p * e, y);                     // y (1 + e/2 + 3 e^2 / 8)
+}
+
+__device__ __forceinline__ prim_t cons_to_prim(double s, double px, double py)
+{
+    // iso2d::recover_primitive (physics_iso2d.hpp:351-362): (sigma, px / sigma, py / sigma)
+    double inv = fast_rcp(s);
+    return {s, px * inv, py * inv};
+}
+
+/**
+ * Un-divided PLM difference: mara::plm_gradient (math_interpolation.hpp:85-94),
+ * i.e. 0.25 |sgn a + sgn b| (sgn a + sgn c) min(|a|, |b|, |c|), which is
+ * sgn(a) min(...) when a, b, c share a sign bit and zero otherwise.
+ */
+__device__ __forceinline__ double plm_diff(double yl, double y0, double yr, double theta)
+{
+    double a = (y0 - yl) * theta;
+    double b = (yr - yl) * 0.5;
+    double c = (yr - y0) * theta;
+    int ha = __double2hiint(a), hb = __double2hiint(b), hc = __double2hiint(c);
+    double m = fmin(fmin(fabs(a), fabs(b)), fabs(c));
+    bool same = ((ha ^ hb) | (ha ^ hc)) >= 0;    // sign bits of all three agree
+    return same ? copysign(m, a) : 0.0;
+}
+
+/** Sound speed squared and geometry-only viscosity factor at a point. */
+struct eos_t { double cs2, cs, nu; };
+
+/**
+ * cs2_at_position + nu_at_position (scheme.cpp:160-193).
+ * y1, y2 out: 1 / sqrt(dr_k^2 + rs^2) for the two bodies (re-used by gravity).
+ */
+__device__ __forceinline__ double sound_speed_squared(const model_t& M, const stage_t& S, double x, double y, double& y1, double& y2)
+{
+    double dx1 = x - S.x1, dy1 = y - S.y1, dx2 = x - S.x2, dy2 = y - S.y2;
+    double d1 = fma(dx1, dx1, fma(dy1, dy1, M.softening_radius2));
+    double d2 = fma(dx2, dx2, fma(dy2, dy2, M.softening_radius2));
+    y1 = fast_rsqrt(d1);
+    y2 = fast_rsqrt(d2);
+
+    if (M.axisymmetric_cs2)
+    {
+        return fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2;      // GM / r / M^2
+    }
+    return fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;              // -(phi1 + phi2) / M^2
+}
+
+__device__ __forceinline__ eos_t eos_at_face(const model_t& M, const stage_t& S, double x, double y)
+{
+    double y1, y2;
+    eos_t e;
+    e.cs2 = sound_speed_squared(M, S, x, y, y1, y2);
+    double ics = fast_rsqrt(e.cs2);
+    e.cs = e.cs2 * ics;
+    double r2 = fma(x, x, y * y);
+
+    if (M.nu > 0.0 || M.alpha_cutoff_radius > 0.0)
+    {
+        double r = r2 * fast_rsqrt(r2);
+        double profile = M.alpha_cutoff_radius > 0.0 ? 0.5 * (1.0 + tanh(3.0 * (r - M.alpha_cutoff_radius))) : 1.0;
+        e.nu = M.nu > 0.0 ? profile * M.nu : profile * M.alpha * e.cs * (r * M.inv_mach);
+    }
+    else
+    {
+        // alpha * sqrt(cs2) * r / M with a single square root: sqrt(cs2 * r^2)
+        double q = e.cs2 * r2;
+        e.nu = M.alpha * M.inv_mach * (q * fast_rsqrt(q));
+    }
+    return e;
+}
+
+/**
+ * HLLE + viscous flux through a face with normal along `AXIS`:
+ * intercell_flux_u (scheme.cpp:268-293) = iso2d::riemann_hlle (physics_iso2d.hpp:488-506)
+ * + viscous_flux (scheme.cpp:220-262).
+ *
+ *   pl, pr       cell-centre primitives left / right of the face
+ *   gl, gr       longitudinal gradients (all three components) of the left / right cell
+ *   hlx..hry     transverse gradients of vx, vy in the left / right cell
+ *   half_step    multiplies gl, gr to reach the face (0.5 * spacing for physical gradients)
+ *   visc_scale   multiplies the gradients inside the viscous stress (1 for physical gradients)
+ */
+template<int AXIS>
+__device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, prim_t gl, prim_t gr,
+    double hlx, double hly, double hrx, double hry, double half_step, double visc_scale, double F[3])
+{
+    prim_t L = {fma(gl.s, half_step, pl.s), fma(gl.vx, half_step, pl.vx), fma(gl.vy, half_step, pl.vy)};
+    prim_t R = {fma(-gr.s, half_step, pr.s), fma(-gr.vx, half_step, pr.vx), fma(-gr.vy, half_step, pr.vy)};
+
+    double vl = AXIS == 0 ? L.vx : L.vy;
+    double vr = AXIS == 0 ? R.vx : R.vy;
+    double ap = fmax(0.0, fmax(vl + e.cs, vr + e.cs));
+    double am = fmin(0.0, fmin(vl - e.cs, vr - e.cs));
+    double inv = fast_rcp(ap - am);
+    double apam = ap * am;
+
+    double Ul1 = L.s * L.vx, Ul2 = L.s * L.vy, Ur1 = R.s * R.vx, Ur2 = R.s * R.vy;
+    double Fl0 = vl * L.s, Fr0 = vr * R.s;
+    double pgl = L.s * e.cs2, pgr = R.s * e.cs2;
+    double Fl1 = AXIS == 0 ? fma(Fl0, L.vx, pgl) : Fl0 * L.vx;
+    double Fl2 = AXIS == 0 ? Fl0 * L.vy : fma(Fl0, L.vy, pgl);
+    double Fr1 = AXIS == 0 ? fma(Fr0, R.vx, pgr) : Fr0 * R.vx;
+    double Fr2 = AXIS == 0 ? Fr0 * R.vy : fma(Fr0, R.vy, pgr);
+
+    double f0 = fma(Fl0, ap, fma(-Fr0, am, -(L.s - R.s) * apam)) * inv;
+    double f1 = fma(Fl1, ap, fma(-Fr1, am, -(Ul1 - Ur1) * apam)) * inv;
+    double f2 = fma(Fl2, ap, fma(-Fr2, am, -(Ul2 - Ur2) * apam)) * inv;
+
+    // mu = 0.5 nu (sigma_l + sigma_r); the stresses use face averages 0.5 (g_l + g_r)
+    double mu = (0.25 * visc_scale) * e.nu * (L.s + R.s);
+    double long_x = gl.vx + gr.vx, long_y = gl.vy + gr.vy;
+    double tran_x = hlx + hrx,     tran_y = hly + hry;
+
+    if (AXIS == 0)
+    {
+        // tau_xx = mu (dx ux - dy uy), tau_xy = mu (dx uy + dy ux)
+        f1 = fma(-mu, long_x - tran_y, f1);
+        f2 = fma(-mu, long_y + tran_x, f2);
+    }
+    else
+    {
+        // tau_yx = mu (dx uy + dy ux), tau_yy = -mu (dx ux - dy uy); dx from the transverse set
+        f1 = fma(-mu, tran_y + long_x, f1);
+        f2 = fma( mu, tran_x - long_y, f2);
+    }
+    F[0] = f0; F[1] = f1; F[2] = f2;
+}
+
+/** Running sums behind source_term_total_t (scheme.cpp:22-35, 390-408), before the dt * dA factor. */
+using namespace m3b::sums;
+
+/**
+ * source_terms_u (scheme.cpp:345-411): gravity of both bodies, both sinks, buffer
+ * damping and the density floor, summed in the reference's order.  Adds this
+ * cell's contributions to sums[].  Returns y1, y2 (inverse softened distances)
+ * for the fused time-step estimate.
+ */
+__device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S, double x, double y,
+    double s, double px, double py, double u0s, double u0x, double u0y, double br,
+    double src[3], double sums[NUM_SUMS], double& y1, double& y2)
+{
+    double dx1 = x - S.x1, dy1 = y - S.y1, dx2 = x - S.x2, dy2 = y - S.y2;
+    double r1 = fma(dx1, dx1, dy1 * dy1);
+    double r2 = fma(dx2, dx2, dy2 * dy2);
+    y1 = fast_rsqrt(r1 + M.softening_radius2);
+    y2 = fast_rsqrt(r2 + M.softening_radius2);
+
+    // grav_vdot_field * sigma: -dr / (dr^2 + rs^2)^(3/2) G M sigma   (scheme.cpp:85-95, 377-378)
+    double k1 = -(y1 * y1) * y1 * S.m1 * s;
+    double k2 = -(y2 * y2) * y2 * S.m2 * s;
+    double fx1 = dx1 * k1, fy1 = dy1 * k1, fx2 = dx2 * k2, fy2 = dy2 * k2;
+
+    sums[GRV_FX + 0] += fx1;  sums[GRV_FY + 0] += fy1;  sums[GRV_TQ + 0] += fma(x, fy1, -y * fx1);
+    sums[GRV_FX + 1] += fx2;  sums[GRV_FY + 1] += fy2;  sums[GRV_TQ + 1] += fma(x, fy2, -y * fx2);
+
+    double a0 = 0.0, a1 = (fx1 + fx2) * S.dt, a2 = (fy1 + fy2) * S.dt;
+
+    // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)).  Beyond a2 = 100 the
+    // factor is < 4e-44: no representable effect on the state and < 1e-40 relative on the totals.
+    double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
+
+    if (e1 < 100.0 || e2 < 100.0)
+    {
+        double w1 = e1 < 100.0 ? M.sink_rate * exp(-e1) : 0.0;
+        double w2 = e2 < 100.0 ? M.sink_rate * exp(-e2) : 0.0;
+        double lz = fma(x, py, -y * px);
+        sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
+        sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
+        sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
+        sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        double w = -(w1 + w2) * S.dt;
+        a0 = fma(s, w, a0);  a1 = fma(px, w, a1);  a2 = fma(py, w, a2);
+    }
+    // buffer zone (scheme.cpp:384): (U0 - u) * rate * dt; rate is exactly 0 away from the edge
+    if (br != 0.0)
+    {
+        double b0 = (u0s - s) * br, b1 = (u0x - px) * br, b2 = (u0y - py) * br;
+        sums[BUF_M] += b0;
+        sums[BUF_L] += fma(x, b2, -y * b1);
+        a0 = fma(b0, S.dt, a0);  a1 = fma(b1, S.dt, a1);  a2 = fma(b2, S.dt, a2);
+    }
+    // density floor (scheme.cpp:385-388): u * 0.01 where sigma < floor
+    if (s < M.density_floor)
+    {
+        a0 = fma(s, 1e-2, a0);  a1 = fma(px, 1e-2, a1);  a2 = fma(py, 1e-2, a2);
+    }
+    src[0] = a0; src[1] = a1; src[2] = a2;
+}
+
+/** max_wavespeed (physics_iso2d.hpp:330-337) with cs2 at the cell centre from y1, y2. */
+__device__ __forceinline__ double max_wavespeed(const model_t& M, const stage_t& S, double x, double y,
+    double y1, double y2, double s, double px, double py)
+{
+    double cs2 = M.axisymmetric_cs2 ? fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2 : fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;
+    double cs = cs2 * fast_rsqrt(cs2);
+    double inv = fast_rcp(s);
+    double vx = fabs(px * inv), vy = fabs(py * inv);
+    return fmax(vx, vy) + cs;       // max(|v - cs|, |v + cs|) = |v| + cs for cs >= 0
+}
+
+}} // namespace m3b::dev

@@ -1,0 +1,931 @@
+/**
+ * kernels.cu -- CUDA kernels (sm_100a) and launch logic of the iso2d `binary` update.
+ *
+ * Replaces, per RK stage, the reference's phases P1-P8 and P11 of binary::advance_u
+ * (Mara3 src/subprog_binary_scheme.cpp:790-904) and binary::maximum_timestep
+ * (:1107-1126).  Two paths produce the same update:
+ *
+ *   stage_fused<TX,TY>   for "regular" blocks (all 8 neighbours are same-level leaves):
+ *                        one CTA per TX x TY tile; the tile plus a 2-cell halo is read
+ *                        once from HBM, primitives / PLM differences / face fluxes live
+ *                        in shared memory, and the updated cells are written once.
+ *   general_*            for blocks touching a refinement jump: guard values are
+ *                        fetched through per-face neighbour tables with the reference's
+ *                        prolongation (injection) / restriction (2x2 mean) rules for
+ *                        primitives AND gradients (mesh_tree_operators.hpp:223-252), and
+ *                        coarse faces next to finer blocks take the sum of the two fine
+ *                        fluxes (scheme.cpp:614-720).
+ *
+ * Each CTA also reduces the 16 source-term sums, the CFL minimum and the
+ * negative-density count; finish_stage folds the per-CTA rows in a fixed order.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "device_solver.hpp"
+#include "iso2d_device.cuh"
+
+using namespace m3b;
+using namespace m3b::dev;
+
+#define M3B_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
+
+namespace
+{
+    constexpr int THREADS = 256;
+    constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
+
+    struct face_nbr_dev_t
+    {
+        int kind;                       // 0 same, 1 coarser, 2 finer
+        int leaf[4];
+        int bx, by;
+        int pad;
+    };
+
+    struct mesh_dev_t
+    {
+        int B, N;
+        size_t FS;                      // field stride = B * N * N
+        const double* xv;               // [B][N+1]
+        const double* yv;               // [B][N+1]
+        const double* spacing;          // [B]
+        const face_nbr_dev_t* nbr;      // [B][4]
+        const int* nbr9;                // [B][9] same-level neighbour leaf ids (regular blocks only)
+        const int* gslot;               // [B] slot of the block in the gradient scratch, or -1
+        const double* U0;               // [3][FS]
+        const double* br;               // [FS]
+        size_t GS;                      // gradient scratch stride
+    };
+
+    struct fail_dev_t
+    {
+        unsigned int count;
+        unsigned int pad;
+        offender_t list[device_solver_t::max_offenders];
+    };
+
+
+    // =======================================================================
+    // Block-wide reduction of the stage outputs
+    // =======================================================================
+    __device__ __forceinline__ double warp_sum(double v)
+    {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+
+    __device__ __forceinline__ double warp_min(double v)
+    {
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+
+    /**
+     * Fold the per-thread sums / CFL minimum into one row.  `red` is shared scratch of
+     * (THREADS / 32) * (NUM_SUMS + 1) doubles.  `mask` says which groups of sums can be
+     * non-zero anywhere in the CTA (bit 0: gravity, bit 1: sinks, bit 2: buffer).
+     */
+    __device__ void reduce_and_store(double* red, const double sums[NUM_SUMS], double dtmin, double scale, double* row)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = THREADS / 32;
+
+        for (int k = 0; k < NUM_SUMS; ++k)
+        {
+            double v = warp_sum(sums[k]);
+            if (lane == 0) red[warp * (NUM_SUMS + 1) + k] = v;
+        }
+        double m = warp_min(dtmin);
+        if (lane == 0) red[warp * (NUM_SUMS + 1) + NUM_SUMS] = m;
+        __syncthreads();
+
+        if (threadIdx.x < NUM_SUMS)
+        {
+            double v = 0.0;
+            for (int w = 0; w < nw; ++w) v += red[w * (NUM_SUMS + 1) + threadIdx.x];
+            row[threadIdx.x] = v * scale;
+        }
+        if (threadIdx.x == NUM_SUMS)
+        {
+            double v = red[NUM_SUMS];
+            for (int w = 1; w < nw; ++w) v = fmin(v, red[w * (NUM_SUMS + 1) + NUM_SUMS]);
+            row[NUM_SUMS] = v;
+        }
+    }
+
+    __device__ __forceinline__ void report_negative(fail_dev_t* fail, int block, int cell, double sigma)
+    {
+        unsigned int n = atomicAdd(&fail->count, 1u);
+        if (n < device_solver_t::max_offenders) fail->list[n] = {block, cell, sigma};
+    }
+
+
+    // =======================================================================
+    // Fused stage kernel for regular blocks
+    // =======================================================================
+    template<int TX, int TY>
+    struct tile_t
+    {
+        static constexpr int PX = TX + 4, PY = TY + 4;      // primitives: tile + 2 halo
+        static constexpr int GX = TX + 2, GY = TY + 2;      // PLM differences: tile + 1 halo
+        double P[3][PX][PY];
+        double G[6][GX][GY];                                // d/dx (s, vx, vy), d/dy (s, vx, vy), un-divided
+        double Fx[3][TX + 1][TY];
+        double Fy[3][TX][TY + 1];
+        double xv[TX + 1];
+        double yv[TY + 1];
+        double red[(THREADS / 32) * (NUM_SUMS + 1)];
+    };
+
+    template<int TX, int TY>
+    __global__ void __launch_bounds__(THREADS, 2) stage_fused(
+        mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ regular_list,
+        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
+        double* __restrict__ partials, fail_dev_t* fail)
+    {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
+
+        const int N = mesh.N;
+        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
+        const int b  = regular_list[blockIdx.x / tiles_per_block];
+        const int t  = blockIdx.x % tiles_per_block;
+        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
+        const size_t FS = mesh.FS;
+        const int tid = threadIdx.x;
+
+        // ---- phase 0: tile + 2-cell halo -> primitives in shared memory (P1 + P2 of advance_u)
+        for (int k = tid; k < T.PX * T.PY; k += THREADS)
+        {
+            int li = k / T.PY, lj = k % T.PY;
+            int gi = i0 - 2 + li, gj = j0 - 2 + lj;
+            int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
+            int dj = gj < 0 ? -1 : (gj >= N ? 1 : 0);
+            int nb = (di | dj) ? mesh.nbr9[b * 9 + (di + 1) * 3 + (dj + 1)] : b;
+            size_t c = (size_t(nb) * N + (gi - di * N)) * N + (gj - dj * N);
+            prim_t p = cons_to_prim(Uin[c], Uin[FS + c], Uin[2 * FS + c]);
+            T.P[0][li][lj] = p.s;
+            T.P[1][li][lj] = p.vx;
+            T.P[2][li][lj] = p.vy;
+        }
+        if (tid <= TX) T.xv[tid] = mesh.xv[size_t(b) * (N + 1) + i0 + tid];
+        if (tid >= 64 && tid - 64 <= TY) T.yv[tid - 64] = mesh.yv[size_t(b) * (N + 1) + j0 + tid - 64];
+        __syncthreads();
+
+        // ---- phase 1: PLM differences on tile + 1 halo (P3; the guard gradients of P4 are the neighbours' own)
+        for (int k = tid; k < T.GX * T.GY; k += THREADS)
+        {
+            int li = k / T.GY, lj = k % T.GY;       // gradient cell (li, lj) <-> primitive cell (li + 1, lj + 1)
+            #pragma unroll
+            for (int q = 0; q < 3; ++q)
+            {
+                double c = T.P[q][li + 1][lj + 1];
+                T.G[q][li][lj]     = plm_diff(T.P[q][li][lj + 1], c, T.P[q][li + 2][lj + 1], S.theta);
+                T.G[3 + q][li][lj] = plm_diff(T.P[q][li + 1][lj], c, T.P[q][li + 1][lj + 2], S.theta);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: HLLE + viscous fluxes on the (TX+1) x TY x-faces and TX x (TY+1) y-faces (P6)
+        const double h = mesh.spacing[b], inv_h = 1.0 / h;
+
+        auto x_face = [&] (int li, int lj)      // face between tile cells (li - 1, lj) and (li, lj)
+        {
+            eos_t e = eos_at_face(model, S, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]));
+            prim_t pl = {T.P[0][li + 1][lj + 2], T.P[1][li + 1][lj + 2], T.P[2][li + 1][lj + 2]};
+            prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
+            prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]};
+            prim_t gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
+            double F[3];
+            face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5, inv_h, F);
+            T.Fx[0][li][lj] = F[0]; T.Fx[1][li][lj] = F[1]; T.Fx[2][li][lj] = F[2];
+        };
+        auto y_face = [&] (int li, int lj)      // face between tile cells (li, lj - 1) and (li, lj)
+        {
+            eos_t e = eos_at_face(model, S, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj]);
+            prim_t pl = {T.P[0][li + 2][lj + 1], T.P[1][li + 2][lj + 1], T.P[2][li + 2][lj + 1]};
+            prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
+            prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]};
+            prim_t gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
+            double F[3];
+            face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
+            T.Fy[0][li][lj] = F[0]; T.Fy[1][li][lj] = F[1]; T.Fy[2][li][lj] = F[2];
+        };
+        for (int k = tid; k < TX * TY; k += THREADS)
+        {
+            x_face(k / TY, k % TY);
+            y_face(k / TY, k % TY);
+        }
+        for (int k = tid; k < TX + TY; k += THREADS)
+        {
+            if (k < TY) x_face(TX, k); else y_face(k - TY, TY);
+        }
+        __syncthreads();
+
+        // ---- phase 3: conservative update + source terms (P8), validation (P11), CFL estimate
+        double sums[NUM_SUMS];
+        #pragma unroll
+        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
+        double dtmin = 1e300;
+        const double dt_over_h = S.dt * inv_h;
+
+        for (int k = tid; k < TX * TY; k += THREADS)
+        {
+            int li = k / TY, lj = k % TY;
+            size_t c = (size_t(b) * N + (i0 + li)) * N + (j0 + lj);
+            double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
+            double br = mesh.br[c];
+            double u0s = 0.0, u0x = 0.0, u0y = 0.0;
+            if (br != 0.0) { u0s = mesh.U0[c]; u0x = mesh.U0[FS + c]; u0y = mesh.U0[2 * FS + c]; }
+
+            double x = 0.5 * (T.xv[li] + T.xv[li + 1]), y = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
+            double src[3], y1, y2;
+            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
+
+            double n0 = s  - ((T.Fx[0][li + 1][lj] - T.Fx[0][li][lj]) + (T.Fy[0][li][lj + 1] - T.Fy[0][li][lj])) * dt_over_h + src[0];
+            double n1 = px - ((T.Fx[1][li + 1][lj] - T.Fx[1][li][lj]) + (T.Fy[1][li][lj + 1] - T.Fy[1][li][lj])) * dt_over_h + src[1];
+            double n2 = py - ((T.Fx[2][li + 1][lj] - T.Fx[2][li][lj]) + (T.Fy[2][li][lj + 1] - T.Fy[2][li][lj])) * dt_over_h + src[2];
+
+            if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
+
+            if (S.combine)
+            {
+                double w = 1.0 - S.rk_b0;
+                n0 = Un[c] * S.rk_b0 + n0 * w;
+                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
+                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
+            }
+            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
+
+            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
+        }
+        reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
+    }
+
+
+    // =======================================================================
+    // General path: any 2:1 balanced tree
+    // =======================================================================
+
+    /** Location of a (possibly guard) cell of block b: which leaves hold it and how to combine them. */
+    struct cell_ref_t
+    {
+        int kind;           // 0: one cell of `leaf[0]`; 2: mean of 2x2 cells spread over up to 4 leaves
+        int leaf[4];
+        int ci[4], cj[4];
+    };
+
+    /** get_cell_block (mesh_tree_operators.hpp:223-252) resolved for one cell (i, j), -1 <= i, j <= N. */
+    __device__ __forceinline__ cell_ref_t resolve_cell(const mesh_dev_t& m, int b, int i, int j)
+    {
+        const int N = m.N;
+        cell_ref_t r;
+        r.kind = 0;
+
+        if (i >= 0 && i < N && j >= 0 && j < N)
+        {
+            r.leaf[0] = b; r.ci[0] = i; r.cj[0] = j;
+            return r;
+        }
+        int side = i < 0 ? 0 : (i >= N ? 1 : (j < 0 ? 2 : 3));
+        int ii = i < 0 ? N - 1 : (i >= N ? 0 : i);
+        int jj = j < 0 ? N - 1 : (j >= N ? 0 : j);
+        const face_nbr_dev_t nb = m.nbr[b * 4 + side];
+
+        if (nb.kind == 0)           // same level: the neighbour's own cell
+        {
+            r.leaf[0] = nb.leaf[0]; r.ci[0] = ii; r.cj[0] = jj;
+        }
+        else if (nb.kind == 1)      // coarser: piecewise-constant prolongation (mesh_prolong_restrict.hpp:161-196)
+        {
+            r.leaf[0] = nb.leaf[0]; r.ci[0] = (nb.bx * N + ii) / 2; r.cj[0] = (nb.by * N + jj) / 2;
+        }
+        else                        // finer: 2x2 mean over the children (mesh_prolong_restrict.hpp:124-132, 262-272)
+        {
+            r.kind = 2;
+            #pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                int fi = 2 * ii + (q & 1), fj = 2 * jj + (q >> 1);
+                r.leaf[q] = nb.leaf[(fi >= N) + 2 * (fj >= N)];
+                r.ci[q] = fi % N; r.cj[q] = fj % N;
+            }
+        }
+        return r;
+    }
+
+    __device__ __forceinline__ prim_t load_prim(const mesh_dev_t& m, const double* U, int leaf, int i, int j)
+    {
+        size_t c = (size_t(leaf) * m.N + i) * m.N + j;
+        return cons_to_prim(U[c], U[m.FS + c], U[2 * m.FS + c]);
+    }
+
+    /** Primitive at cell (i, j) of block b with guard fill: extend(p0, axis, 1) (scheme.cpp:132-142). */
+    __device__ __forceinline__ prim_t prim_at(const mesh_dev_t& m, const double* U, int b, int i, int j)
+    {
+        cell_ref_t r = resolve_cell(m, b, i, j);
+        if (r.kind == 0) return load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
+        prim_t p00 = load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
+        prim_t p10 = load_prim(m, U, r.leaf[1], r.ci[1], r.cj[1]);
+        prim_t p01 = load_prim(m, U, r.leaf[2], r.ci[2], r.cj[2]);
+        prim_t p11 = load_prim(m, U, r.leaf[3], r.ci[3], r.cj[3]);
+        // restrict on axis 0 then on axis 1, each (h0 + h1) / 2
+        return {((p00.s + p10.s) * 0.5 + (p01.s + p11.s) * 0.5) * 0.5,
+                ((p00.vx + p10.vx) * 0.5 + (p01.vx + p11.vx) * 0.5) * 0.5,
+                ((p00.vy + p10.vy) * 0.5 + (p01.vy + p11.vy) * 0.5) * 0.5};
+    }
+
+    __device__ __forceinline__ prim_t load_grad(const mesh_dev_t& m, const double* G, int axis, int leaf, int i, int j)
+    {
+        size_t c = (size_t(m.gslot[leaf]) * m.N + i) * m.N + j;
+        const double* g = G + size_t(3 * axis) * m.GS;
+        return {g[c], g[m.GS + c], g[2 * m.GS + c]};
+    }
+
+    /** Gradient (d/d axis) at cell (i, j) of block b with guard fill: extend(gx, ...) etc. (scheme.cpp:810-813). */
+    __device__ __forceinline__ prim_t grad_at(const mesh_dev_t& m, const double* G, int axis, int b, int i, int j)
+    {
+        cell_ref_t r = resolve_cell(m, b, i, j);
+        if (r.kind == 0) return load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
+        prim_t g00 = load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
+        prim_t g10 = load_grad(m, G, axis, r.leaf[1], r.ci[1], r.cj[1]);
+        prim_t g01 = load_grad(m, G, axis, r.leaf[2], r.ci[2], r.cj[2]);
+        prim_t g11 = load_grad(m, G, axis, r.leaf[3], r.ci[3], r.cj[3]);
+        return {((g00.s + g10.s) * 0.5 + (g01.s + g11.s) * 0.5) * 0.5,
+                ((g00.vx + g10.vx) * 0.5 + (g01.vx + g11.vx) * 0.5) * 0.5,
+                ((g00.vy + g10.vy) * 0.5 + (g01.vy + g11.vy) * 0.5) * 0.5};
+    }
+
+    /** P2 + P3 for the listed blocks: physical PLM gradients at the block's own spacing. */
+    __global__ void __launch_bounds__(THREADS) general_gradients(
+        mesh_dev_t mesh, const stage_t S, const int* __restrict__ list,
+        const double* __restrict__ Uin, double* __restrict__ G)
+    {
+        const int N = mesh.N, b = list[blockIdx.x];
+        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
+        const size_t base = size_t(mesh.gslot[b]) * N * N;
+
+        for (int k = threadIdx.x; k < N * N; k += THREADS)
+        {
+            int i = k / N, j = k % N;
+            prim_t c  = prim_at(mesh, Uin, b, i, j);
+            prim_t xl = prim_at(mesh, Uin, b, i - 1, j), xr = prim_at(mesh, Uin, b, i + 1, j);
+            prim_t yl = prim_at(mesh, Uin, b, i, j - 1), yr = prim_at(mesh, Uin, b, i, j + 1);
+            G[0 * mesh.GS + base + k] = plm_diff(xl.s,  c.s,  xr.s,  theta) * inv_h;
+            G[1 * mesh.GS + base + k] = plm_diff(xl.vx, c.vx, xr.vx, theta) * inv_h;
+            G[2 * mesh.GS + base + k] = plm_diff(xl.vy, c.vy, xr.vy, theta) * inv_h;
+            G[3 * mesh.GS + base + k] = plm_diff(yl.s,  c.s,  yr.s,  theta) * inv_h;
+            G[4 * mesh.GS + base + k] = plm_diff(yl.vx, c.vx, yr.vx, theta) * inv_h;
+            G[5 * mesh.GS + base + k] = plm_diff(yl.vy, c.vy, yr.vy, theta) * inv_h;
+        }
+    }
+
+    /**
+     * Flux (times face length) through face f (0..N) of block b along AXIS at transverse index k,
+     * as block b computes it: block_fluxes_u (scheme.cpp:472-516).
+     */
+    template<int AXIS>
+    __device__ void general_face_flux(const mesh_dev_t& m, const model_t& model, const stage_t& S,
+        const double* U, const double* G, int b, int f, int k, double F[3])
+    {
+        const int N = m.N;
+        const double* xv = m.xv + size_t(b) * (N + 1);
+        const double* yv = m.yv + size_t(b) * (N + 1);
+        int li = AXIS == 0 ? f - 1 : k, lj = AXIS == 0 ? k : f - 1;
+        int ri = AXIS == 0 ? f : k,     rj = AXIS == 0 ? k : f;
+        double x   = AXIS == 0 ? xv[f] : 0.5 * (xv[k] + xv[k + 1]);
+        double y   = AXIS == 0 ? 0.5 * (yv[k] + yv[k + 1]) : yv[f];
+        double len = AXIS == 0 ? yv[k + 1] - yv[k] : xv[k + 1] - xv[k];
+
+        prim_t pl = prim_at(m, U, b, li, lj), pr = prim_at(m, U, b, ri, rj);
+        prim_t gl = grad_at(m, G, AXIS, b, li, lj), gr = grad_at(m, G, AXIS, b, ri, rj);
+        prim_t hl = grad_at(m, G, 1 - AXIS, b, li, lj), hr = grad_at(m, G, 1 - AXIS, b, ri, rj);
+        eos_t e = eos_at_face(model, S, x, y);
+        face_flux<AXIS>(e, pl, pr, gl, gr, hl.vx, hl.vy, hr.vx, hr.vy, 0.5 * m.spacing[b], 1.0, F);
+        F[0] *= len; F[1] *= len; F[2] *= len;
+    }
+
+    /** The same with correct_fluxes_{x,y} applied (scheme.cpp:614-720). */
+    template<int AXIS>
+    __device__ void general_face_flux_corrected(const mesh_dev_t& m, const model_t& model, const stage_t& S,
+        const double* U, const double* G, int b, int f, int k, double F[3])
+    {
+        const int N = m.N;
+        int side = f == 0 ? 2 * AXIS : (f == N ? 2 * AXIS + 1 : -1);
+
+        if (side >= 0 && m.nbr[b * 4 + side].kind == 2)
+        {
+            // the neighbour region is refined: sum of the two fine faces, computed as the fine blocks do
+            const face_nbr_dev_t nb = m.nbr[b * 4 + side];
+            int near = side % 2 ? 0 : 1;                    // children adjacent to this face
+            int fine_face = side % 2 ? 0 : N;
+            double A[3], C[3];
+            int k0 = 2 * k, k1 = 2 * k + 1;
+            int c0 = AXIS == 0 ? nb.leaf[near + 2 * (k0 >= N)] : nb.leaf[(k0 >= N) + 2 * near];
+            int c1 = AXIS == 0 ? nb.leaf[near + 2 * (k1 >= N)] : nb.leaf[(k1 >= N) + 2 * near];
+            general_face_flux<AXIS>(m, model, S, U, G, c0, fine_face, k0 % N, A);
+            general_face_flux<AXIS>(m, model, S, U, G, c1, fine_face, k1 % N, C);
+            F[0] = A[0] + C[0]; F[1] = A[1] + C[1]; F[2] = A[2] + C[2];
+            return;
+        }
+        general_face_flux<AXIS>(m, model, S, U, G, b, f, k, F);
+    }
+
+    /** P6-P8 + P11 for the listed blocks, one CTA per block. */
+    __global__ void __launch_bounds__(THREADS) general_update(
+        mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ list,
+        const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
+        double* __restrict__ partials, fail_dev_t* fail)
+    {
+        __shared__ double red[(THREADS / 32) * (NUM_SUMS + 1)];
+        const int N = mesh.N, b = list[blockIdx.x];
+        const size_t FS = mesh.FS;
+        const double* xv = mesh.xv + size_t(b) * (N + 1);
+        const double* yv = mesh.yv + size_t(b) * (N + 1);
+        const double h = mesh.spacing[b];
+
+        double sums[NUM_SUMS];
+        #pragma unroll
+        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
+        double dtmin = 1e300;
+
+        for (int k = threadIdx.x; k < N * N; k += THREADS)
+        {
+            int i = k / N, j = k % N;
+            size_t c = size_t(b) * N * N + k;
+            double Fl[3], Fr[3], Fb[3], Ft[3];
+            general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i, j, Fl);
+            general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i + 1, j, Fr);
+            general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j, i, Fb);
+            general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j + 1, i, Ft);
+
+            double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
+            double br = mesh.br[c];
+            double u0s = mesh.U0[c], u0x = mesh.U0[FS + c], u0y = mesh.U0[2 * FS + c];
+            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
+            double dt_over_dA = S.dt / ((xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]));
+            double src[3], y1, y2;
+            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
+
+            double n0 = s  - ((Fr[0] - Fl[0]) + (Ft[0] - Fb[0])) * dt_over_dA + src[0];
+            double n1 = px - ((Fr[1] - Fl[1]) + (Ft[1] - Fb[1])) * dt_over_dA + src[1];
+            double n2 = py - ((Fr[2] - Fl[2]) + (Ft[2] - Fb[2])) * dt_over_dA + src[2];
+
+            if (n0 < 0.0) report_negative(fail, b, k, n0);
+
+            if (S.combine)
+            {
+                double w = 1.0 - S.rk_b0;
+                n0 = Un[c] * S.rk_b0 + n0 * w;
+                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
+                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
+            }
+            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
+
+            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
+        }
+        reduce_and_store(red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
+    }
+
+
+    // =======================================================================
+    // Stand-alone CFL pass, row folding, layout changes
+    // =======================================================================
+
+    /** maximum_timestep (scheme.cpp:1107-1126): per-CTA min of spacing / max wavespeed. */
+    __global__ void __launch_bounds__(THREADS) max_timestep_kernel(
+        mesh_dev_t mesh, model_t model, const stage_t S, const double* __restrict__ U, double* __restrict__ partials)
+    {
+        __shared__ double red[THREADS / 32];
+        const int N = mesh.N, b = blockIdx.x;
+        const double* xv = mesh.xv + size_t(b) * (N + 1);
+        const double* yv = mesh.yv + size_t(b) * (N + 1);
+        const double h = mesh.spacing[b];
+        double dtmin = 1e300;
+
+        for (int k = threadIdx.x; k < N * N; k += THREADS)
+        {
+            int i = k / N, j = k % N;
+            size_t c = size_t(b) * N * N + k;
+            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
+            double y1, y2;
+            sound_speed_squared(model, S, x, y, y1, y2);
+            dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, U[c], U[mesh.FS + c], U[2 * mesh.FS + c]));
+        }
+        dtmin = warp_min(dtmin);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dtmin;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            for (int w = 1; w < THREADS / 32; ++w) dtmin = fmin(dtmin, red[w]);
+            double* row = partials + size_t(b) * ROW;
+            for (int k = 0; k < NUM_SUMS; ++k) row[k] = 0.0;
+            row[NUM_SUMS] = dtmin;
+        }
+    }
+
+    /** Fold the per-CTA rows in a fixed order (deterministic), publish the stage result. */
+    __global__ void __launch_bounds__(THREADS) finish_stage(const double* __restrict__ partials, int num_rows, fail_dev_t* fail, stage_result_t* result)
+    {
+        __shared__ double red[THREADS];
+        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = THREADS / 32;
+        double v = col == NUM_SUMS ? 1e300 : 0.0;
+
+        if (col <= NUM_SUMS)
+        {
+            for (int r = grp; r < num_rows; r += ngrp)
+            {
+                double p = partials[size_t(r) * ROW + col];
+                v = col == NUM_SUMS ? fmin(v, p) : v + p;
+            }
+        }
+        red[threadIdx.x] = v;
+        __syncthreads();
+
+        if (grp == 0 && col <= NUM_SUMS)
+        {
+            for (int g = 1; g < ngrp; ++g)
+            {
+                double p = red[g * 32 + col];
+                v = col == NUM_SUMS ? fmin(v, p) : v + p;
+            }
+            if (col < NUM_SUMS) result->sums[col] = v; else result->dt_min = v;
+        }
+        if (threadIdx.x == 0) result->num_negative = fail->count;
+    }
+
+    /** [B][3][NN] (host, block major) <-> [3][B][NN] (device, field major) */
+    __global__ void permute_state(const double* __restrict__ src, double* __restrict__ dst, int B, int NN, int to_device)
+    {
+        size_t n = size_t(B) * 3 * NN;
+        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
+        {
+            size_t cell = k % NN, q = (k / NN) % 3, b = k / (size_t(3) * NN);
+            size_t field_major = (q * B + b) * NN + cell;
+            if (to_device) dst[field_major] = src[k]; else dst[k] = src[field_major];
+        }
+    }
+
+    __global__ void axpby_kernel(const double* __restrict__ a, double wa, const double* __restrict__ b, double wb, double* __restrict__ dst, size_t n)
+    {
+        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
+        {
+            dst[k] = a[k] * wa + b[k] * wb;
+        }
+    }
+
+    template<typename T>
+    T* device_upload(const std::vector<T>& v)
+    {
+        T* p = nullptr;
+        M3B_CUDA(cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(T)));
+        if (! v.empty()) M3B_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+}
+
+
+
+
+// ===========================================================================
+// device_field_t
+// ===========================================================================
+device_field_t::device_field_t(std::size_t num_doubles, int device) : count(num_doubles), device(device)
+{
+    M3B_CUDA(cudaSetDevice(device));
+    M3B_CUDA(cudaMalloc(&data, std::max<size_t>(1, count) * sizeof(double)));
+}
+
+device_field_t::~device_field_t()
+{
+    if (data) cudaFree(data);
+}
+
+
+
+
+// ===========================================================================
+// device_solver_t
+// ===========================================================================
+struct device_solver_t::impl_t
+{
+    mesh_dev_t mesh {};
+    model_t model {};
+    int tile_x = 0, tile_y = 0;
+    std::vector<int> regular, irregular, gradient_blocks;
+    int* d_regular = nullptr;
+    int* d_irregular = nullptr;
+    int* d_gradient_blocks = nullptr;
+    double* d_gradients = nullptr;
+    double* d_partials = nullptr;
+    double* d_staging = nullptr;            // [B][3][NN] for layout changes
+    fail_dev_t* d_fail = nullptr;           // [num_slots]
+    stage_result_t* d_results = nullptr;    // [num_slots]
+    std::vector<void*> owned;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    size_t fused_smem = 0;
+    int sm_count = 148;
+};
+
+device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool general_only) : impl(new impl_t), device_id(device), force_general(general_only)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        throw std::runtime_error("mara3_b200: no CUDA device is available (this library has no CPU fallback)");
+    M3B_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    M3B_CUDA(cudaGetDeviceProperties(&prop, device));
+    impl->sm_count = prop.multiProcessorCount;
+
+    N = sd.block_size;
+    B = sd.num_blocks;
+    cells = sd.num_cells();
+    const auto& tree = *sd.tree;
+
+    cudaStream_t s;
+    M3B_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    stream_ = s;
+
+    // ---- static mesh data
+    auto spacing = std::vector<double>(B);
+    auto nbr = std::vector<face_nbr_dev_t>(size_t(B) * 4);
+    auto nbr9 = std::vector<int>(size_t(B) * 9, -1);
+    auto in_gradient_set = std::vector<char>(B, 0);
+
+    for (int b = 0; b < B; ++b)
+    {
+        spacing[b] = sd.spacing(tree.index(b).level);
+        bool regular = true;
+
+        for (int side = 0; side < 4; ++side)
+        {
+            auto fn = tree.face_neighbor(b, side);
+            auto& d = nbr[size_t(b) * 4 + side];
+            d.kind = int(fn.kind);
+            for (int q = 0; q < 4; ++q) d.leaf[q] = fn.leaf[q];
+            d.bx = fn.bx; d.by = fn.by; d.pad = 0;
+        }
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj)
+            {
+                int l = tree.same_level_neighbor(b, di, dj);
+                nbr9[size_t(b) * 9 + (di + 1) * 3 + (dj + 1)] = l;
+                if (l < 0) regular = false;
+            }
+        (regular ? impl->regular : impl->irregular).push_back(b);
+    }
+    // tile shape of the fused kernel; blocks whose size no tile divides all take the general path
+    if      (N % 32 == 0) { impl->tile_x = 16; impl->tile_y = 32; }
+    else if (N % 24 == 0) { impl->tile_x = 12; impl->tile_y = 24; }
+    else if (N % 16 == 0) { impl->tile_x = 16; impl->tile_y = 16; }
+    else if (N % 8 == 0)  { impl->tile_x = 8;  impl->tile_y = 8; }
+    else
+    {
+        impl->irregular.insert(impl->irregular.end(), impl->regular.begin(), impl->regular.end());
+        std::sort(impl->irregular.begin(), impl->irregular.end());
+        impl->regular.clear();
+    }
+    num_regular = int(impl->regular.size());
+
+    auto gslot = std::vector<int>(B, -1);
+    auto mark = [&] (int l) { if (l >= 0) in_gradient_set[l] = 1; };
+
+    // the general path reads gradients of its own blocks and of every face neighbour they fetch from
+    for (int b : impl->irregular)
+    {
+        mark(b);
+        for (int side = 0; side < 4; ++side) for (int q = 0; q < 4; ++q) mark(nbr[size_t(b) * 4 + side].leaf[q]);
+    }
+    if (force_general) for (int b = 0; b < B; ++b) mark(b);
+    for (int b = 0; b < B; ++b) if (in_gradient_set[b]) { gslot[b] = int(impl->gradient_blocks.size()); impl->gradient_blocks.push_back(b); }
+
+    impl->mesh.B = B;
+    impl->mesh.N = N;
+    impl->mesh.FS = cells;
+    impl->mesh.GS = impl->gradient_blocks.size() * size_t(N) * N;
+    impl->mesh.xv = device_upload(sd.xv);
+    impl->mesh.yv = device_upload(sd.yv);
+    impl->mesh.spacing = device_upload(spacing);
+    impl->mesh.nbr = device_upload(nbr);
+    impl->mesh.nbr9 = device_upload(nbr9);
+    impl->mesh.gslot = device_upload(gslot);
+    impl->mesh.U0 = device_upload(sd.initial_conserved_u);
+    impl->mesh.br = device_upload(sd.buffer_rate_field);
+    impl->d_regular = device_upload(impl->regular);
+    impl->d_irregular = device_upload(impl->irregular);
+    impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
+
+    auto all_blocks = std::vector<int>(B);
+    for (int b = 0; b < B; ++b) all_blocks[b] = b;
+    impl->owned.push_back(device_upload(all_blocks));
+
+    impl->model.softening_radius2   = sd.softening_radius * sd.softening_radius;
+    impl->model.sink_rate           = sd.sink_rate;
+    impl->model.sink_inv_2s2        = 1.0 / (sd.sink_radius * sd.sink_radius) / 2.0;
+    impl->model.inv_mach2           = 1.0 / sd.mach_number / sd.mach_number;
+    impl->model.inv_mach            = 1.0 / sd.mach_number;
+    impl->model.alpha               = sd.alpha;
+    impl->model.nu                  = sd.nu;
+    impl->model.alpha_cutoff_radius = sd.alpha_cutoff_radius;
+    impl->model.density_floor       = sd.density_floor;
+    impl->model.axisymmetric_cs2    = sd.axisymmetric_cs2;
+
+    // ---- scratch
+    size_t max_rows = size_t(B) * std::max(1, (N / std::max(1, impl->tile_x)) * (N / std::max(1, impl->tile_y))) + B;
+    M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * cells * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_fail, num_slots * sizeof(fail_dev_t)));
+    M3B_CUDA(cudaMalloc(&impl->d_results, num_slots * sizeof(stage_result_t)));
+    M3B_CUDA(cudaMallocHost(&host_results, num_slots * sizeof(stage_result_t)));
+    M3B_CUDA(cudaMalloc(&impl->d_gradients, std::max<size_t>(1, 6 * impl->mesh.GS) * sizeof(double)));
+
+    auto set_smem = [&] (auto kernel, size_t bytes)
+    {
+        impl->fused_smem = bytes;
+        M3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    };
+    if (impl->tile_x == 16 && impl->tile_y == 32) set_smem(stage_fused<16, 32>, sizeof(tile_t<16, 32>));
+    if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
+    if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
+    if (impl->tile_x == 8  && impl->tile_y == 8)  set_smem(stage_fused<8, 8>, sizeof(tile_t<8, 8>));
+}
+
+device_solver_t::~device_solver_t()
+{
+    cudaSetDevice(device_id);
+    cudaStreamSynchronize(cudaStream_t(stream_));
+    for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.nbr,
+                   (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
+                   (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
+                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_fail, (void*) impl->d_results})
+        if (p) cudaFree(p);
+    for (auto p : impl->owned) cudaFree(p);
+    for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (host_results) cudaFreeHost(host_results);
+    cudaStreamDestroy(cudaStream_t(stream_));
+}
+
+void device_solver_t::upload(const double* host, device_field_t& dst)
+{
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+    M3B_CUDA(cudaMemcpyAsync(impl->d_staging, host, 3 * cells * sizeof(double), cudaMemcpyHostToDevice, s));
+    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(impl->d_staging, dst.data, B, N * N, 1);
+    ++launches;
+    M3B_CUDA(cudaGetLastError());
+}
+
+void device_solver_t::download(const device_field_t& src, double* host)
+{
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(src.data, impl->d_staging, B, N * N, 0);
+    ++launches;
+    M3B_CUDA(cudaGetLastError());
+    M3B_CUDA(cudaMemcpyAsync(host, impl->d_staging, 3 * cells * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaStreamSynchronize(s));
+}
+
+void device_solver_t::copy(const device_field_t& src, device_field_t& dst)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    M3B_CUDA(cudaMemcpyAsync(dst.data, src.data, 3 * cells * sizeof(double), cudaMemcpyDeviceToDevice, cudaStream_t(stream_)));
+}
+
+void device_solver_t::load_initial(device_field_t& dst)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    M3B_CUDA(cudaMemcpyAsync(dst.data, impl->mesh.U0, 3 * cells * sizeof(double), cudaMemcpyDeviceToDevice, cudaStream_t(stream_)));
+}
+
+void device_solver_t::combine(const device_field_t& a, double wa, const device_field_t& b, double wb, device_field_t& dst)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    axpby_kernel<<<impl->sm_count * 4, 256, 0, cudaStream_t(stream_)>>>(a.data, wa, b.data, wb, dst.data, 3 * cells);
+    ++launches;
+    M3B_CUDA(cudaGetLastError());
+}
+
+void device_solver_t::set_stage_timing(bool on)
+{
+    stage_timing = on;
+}
+
+void device_solver_t::collect_stage_timing()
+{
+    sync();
+    for (auto& ev : impl->timing_events)
+    {
+        float ms = 0.f;
+        M3B_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        stage_ms_total += ms;
+        ++stage_timed_launches;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    impl->timing_events.clear();
+}
+
+void device_solver_t::launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot)
+{
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+
+    if (inputs.combine && ! un) throw std::invalid_argument("launch_stage: combine requires the step-start state");
+    if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
+
+    stage_t st;
+    st.time = inputs.time;
+    st.dt = inputs.dt;
+    st.theta = inputs.theta;
+    st.x1 = inputs.bodies.body1.x; st.y1 = inputs.bodies.body1.y; st.m1 = inputs.bodies.body1.mass;
+    st.x2 = inputs.bodies.body2.x; st.y2 = inputs.bodies.body2.y; st.m2 = inputs.bodies.body2.mass;
+    st.rk_b0 = inputs.rk_b0;
+    st.combine = inputs.combine;
+    st.compute_dt = inputs.compute_dt;
+
+    M3B_CUDA(cudaMemsetAsync(impl->d_fail + slot, 0, 8, s));
+
+    const double* un_data = un ? un->data : nullptr;
+    int num_fused = force_general ? 0 : int(impl->regular.size());
+    int num_general = force_general ? B : int(impl->irregular.size());
+    const int* d_general = force_general ? static_cast<const int*>(impl->owned[0]) : impl->d_irregular;
+    int fused_ctas = num_fused * (impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0);
+
+    if (fused_ctas > 0)
+    {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (stage_timing)
+        {
+            M3B_CUDA(cudaEventCreate(&e0));
+            M3B_CUDA(cudaEventCreate(&e1));
+            M3B_CUDA(cudaEventRecord(e0, s));
+        }
+        #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<fused_ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
+            impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot)
+        if      (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
+        else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
+        else if (impl->tile_x == 16 && impl->tile_y == 16) M3B_LAUNCH_FUSED(16, 16);
+        else                                               M3B_LAUNCH_FUSED(8, 8);
+        #undef M3B_LAUNCH_FUSED
+        ++launches;
+        M3B_CUDA(cudaGetLastError());
+        if (stage_timing)
+        {
+            M3B_CUDA(cudaEventRecord(e1, s));
+            impl->timing_events.emplace_back(e0, e1);
+        }
+    }
+    if (num_general > 0)
+    {
+        // gradients are needed for the general blocks and every block they can fetch from
+        int ng = int(impl->gradient_blocks.size());
+        general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
+            in.data, impl->d_gradients, un_data, out.data, impl->d_partials + size_t(fused_ctas) * ROW, impl->d_fail + slot);
+        launches += 2;
+        M3B_CUDA(cudaGetLastError());
+    }
+    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, impl->d_fail + slot, impl->d_results + slot);
+    ++launches;
+    M3B_CUDA(cudaGetLastError());
+    M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
+}
+
+void device_solver_t::launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot)
+{
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+    stage_t st = stage_t();
+    st.time = time;
+    st.x1 = bodies.body1.x; st.y1 = bodies.body1.y; st.m1 = bodies.body1.mass;
+    st.x2 = bodies.body2.x; st.y2 = bodies.body2.y; st.m2 = bodies.body2.mass;
+    M3B_CUDA(cudaMemsetAsync(impl->d_fail + slot, 0, 8, s));
+    max_timestep_kernel<<<B, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
+    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, B, impl->d_fail + slot, impl->d_results + slot);
+    launches += 2;
+    M3B_CUDA(cudaGetLastError());
+    M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
+}
+
+void device_solver_t::sync()
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
+}
+
+std::vector<offender_t> device_solver_t::offenders(int slot)
+{
+    fail_dev_t f;
+    M3B_CUDA(cudaSetDevice(device_id));
+    M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
+    M3B_CUDA(cudaMemcpy(&f, impl->d_fail + slot, sizeof(fail_dev_t), cudaMemcpyDeviceToHost));
+    auto n = std::min<unsigned>(f.count, max_offenders);
+    auto v = std::vector<offender_t>(f.list, f.list + n);
+    std::sort(v.begin(), v.end(), [] (const offender_t& a, const offender_t& b) { return a.block != b.block ? a.block < b.block : a.cell < b.cell; });
+    return v;
+}
