@@ -54,7 +54,9 @@ const char* m3b_global_error(void);                     /* message of the last f
  * (subprog_binary.cpp:155-164, subprog_binary_solver_data.cpp:18-115, scheme.cpp:42-49).
  * argv holds "key=value" tokens with the reference's 39 keys; unknown keys, duplicates and
  * bad values fail exactly as the reference's config_t does (app_config.hpp:103-136, 223-245).
- * flags: bit 0 = route every block through the general (any-tree) kernels (testing). */
+ * flags: bit 0 = route every block through the general (any-tree) kernels (testing);
+ *        bit 1 = host only: solver_data queries without a device context;
+ *        bit 2 = use the tiled stage kernel even where the warp-strip kernel applies (testing). */
 m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, int flags);
 void        m3b_solver_destroy(m3b_solver_t* s);
 const char* m3b_last_error(const m3b_solver_t* s);
@@ -104,6 +106,11 @@ int         m3b_advance_host(m3b_solver_t* s, const double* u_in, const double* 
 int         m3b_next_solution_host(m3b_solver_t* s, const double* u_in, const double* scalars_in,
                                    double* u_out, double* scalars_out, double* dt_used, int* fell_back);
 
+/* ---- two-body model (host only; model_two_body.hpp:220-281, 295-402) ------------------------
+ * elements: 10 doubles as in the scalars; bodies: mass, x, y, vx, vy of body 1 then body 2 */
+int         m3b_two_body_state(const double* elements10, double t, double* bodies10_out);
+int         m3b_orbital_elements(const double* bodies10, double t, double* elements10_out);   /* 0, or 2 if unbound */
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* lines the reference prints before throwing ("negative density ... (at position [...])") */
 int         m3b_num_messages(const m3b_solver_t* s);
@@ -113,6 +120,8 @@ uint64_t    m3b_kernel_launches(const m3b_solver_t* s);               /* kernels
 /* CUDA-event timing of the fused stage kernel on its own stream (for the roofline) */
 void        m3b_stage_timing(m3b_solver_t* s, int enable);
 int         m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches);
+/* launch on a caller-owned cudaStream_t from now on (NULL: back to the solver's own stream) */
+int         m3b_set_stream(m3b_solver_t* s, void* cuda_stream);
 void        m3b_synchronize(m3b_solver_t* s);
 
 #ifdef __cplusplus

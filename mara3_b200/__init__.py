@@ -24,6 +24,7 @@ NUM_SCALARS = 43
 OK, NEGATIVE_DENSITY, UNBOUND_ORBIT, UNSUPPORTED = 0, 1, 2, 3
 FLAG_GENERAL_ONLY = 1   # every block through the any-tree kernels (tests)
 FLAG_HOST_ONLY = 2      # mesh / solver_data queries only; no device context
+FLAG_TILED_KERNEL = 4   # stage_fused instead of stage_strip (tests)
 
 SCALAR_NAMES = (
     ["time", "iter_num", "iter_den"]
@@ -112,6 +113,9 @@ def load_library():
     L.m3b_stage_timing.argtypes = [vp, C.c_int]
     L.m3b_stage_timing_read.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
     L.m3b_synchronize.argtypes = [vp]
+    L.m3b_two_body_state.argtypes = [dp, C.c_double, dp]
+    L.m3b_orbital_elements.argtypes = [dp, C.c_double, dp]
+    L.m3b_set_stream.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -182,13 +186,13 @@ class Solution:
 class Solver:
     """run_config + solver_data_t + the device context (one GPU)."""
 
-    def __init__(self, config=None, device=0, general_only=False, host_only=False, quiet=True, argv=None, **keys):
+    def __init__(self, config=None, device=0, general_only=False, host_only=False, tiled_kernel=False, quiet=True, argv=None, **keys):
         L = load_library()
         items = dict(config or {})
         items.update(keys)
         tokens = list(argv or []) + [f"{k}={_format(v)}" for k, v in items.items()]
         arr = (C.c_char_p * max(1, len(tokens)))(*[t.encode() for t in tokens])
-        flags = (FLAG_GENERAL_ONLY if general_only else 0) | (FLAG_HOST_ONLY if host_only else 0)
+        flags = (FLAG_GENERAL_ONLY if general_only else 0) | (FLAG_HOST_ONLY if host_only else 0) | (FLAG_TILED_KERNEL if tiled_kernel else 0)
         self._h = L.m3b_solver_create(len(tokens), arr, int(device), flags)
         if not self._h:
             raise Mara3Error(L.m3b_global_error().decode())
@@ -309,6 +313,10 @@ class Solver:
         self._check(_lib.m3b_stage_timing_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned CUDA stream (an integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(_lib.m3b_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def synchronize(self):
         _lib.m3b_synchronize(self._h)
 
@@ -324,3 +332,22 @@ def _format(v):
 def create_solver_data(config=None, **kwargs):
     """create_run_config + create_solver_data + set_scheme_globals."""
     return Solver(config, **kwargs)
+
+
+def two_body_state(elements, t):
+    """mara::compute_two_body_state: elements (10 doubles) -> [[mass, x, y, vx, vy], [..]]."""
+    L = load_library()
+    e = _host_array(elements, (10,))
+    out = np.empty((2, 5), dtype=np.float64)
+    L.m3b_two_body_state(_dptr(e), float(t), _dptr(out))
+    return out
+
+
+def orbital_elements(bodies, t):
+    """mara::compute_orbital_elements; raises ValueError for an unbound pair (the reference throws)."""
+    L = load_library()
+    b = _host_array(bodies, (2, 5))
+    out = np.empty(10, dtype=np.float64)
+    if L.m3b_orbital_elements(_dptr(b), float(t), _dptr(out)):
+        raise ValueError("mara::compute_orbital_elements (two_body_state does not correspond to a bound orbit)")
+    return out

@@ -65,7 +65,7 @@ m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, i
         auto config = config_t::from_argv(argc, argv);
         if (! config.get_string("restart").empty())
             throw std::invalid_argument("restart= is handled by the checkpoint reader, not by m3b_solver_create");
-        s->solver = std::make_unique<binary_solver_t>(config, (flags & 2) ? -1 : device, (flags & 1) != 0);
+        s->solver = std::make_unique<binary_solver_t>(config, (flags & 2) ? -1 : device, (flags & 1) != 0, (flags & 4) != 0);
         return s.release();
     }
     catch (const std::exception& e)
@@ -253,6 +253,30 @@ int m3b_next_solution_host(m3b_solver_t* s, const double* u_in, const double* sc
     });
 }
 
+int m3b_two_body_state(const double* e, double t, double* out)
+{
+    auto el = elements_t{e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9]};
+    auto s = two_body_state(el, t);
+    const point_mass_t* b[2] = {&s.body1, &s.body2};
+    for (int k = 0; k < 2; ++k)
+    {
+        out[5 * k + 0] = b[k]->mass; out[5 * k + 1] = b[k]->x; out[5 * k + 2] = b[k]->y;
+        out[5 * k + 3] = b[k]->vx;   out[5 * k + 4] = b[k]->vy;
+    }
+    return M3B_OK;
+}
+
+int m3b_orbital_elements(const double* b, double t, double* out)
+{
+    auto s = two_body_t{{b[0], b[1], b[2], b[3], b[4]}, {b[5], b[6], b[7], b[8], b[9]}};
+    auto e = elements_t();
+    if (! orbital_elements(s, t, e)) return M3B_UNBOUND_ORBIT;
+    const double v[10] = {e.pomega, e.tau, e.cm_position_x, e.cm_position_y, e.cm_velocity_x, e.cm_velocity_y,
+                          e.separation, e.total_mass, e.mass_ratio, e.eccentricity};
+    for (int k = 0; k < 10; ++k) out[k] = v[k];
+    return M3B_OK;
+}
+
 int m3b_num_messages(const m3b_solver_t* s) { return int(s->solver->last_messages().size()); }
 const char* m3b_message(const m3b_solver_t* s, int n) { return s->solver->last_messages().at(n).c_str(); }
 void m3b_set_quiet(m3b_solver_t* s, int quiet) { s->solver->set_quiet(quiet != 0); }
@@ -268,6 +292,11 @@ int m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches)
         *launches = s->solver->device().stage_kernel_launches();
         return M3B_OK;
     });
+}
+
+int m3b_set_stream(m3b_solver_t* s, void* cuda_stream)
+{
+    return guarded(s, [&] { s->solver->device().set_stream(cuda_stream); return M3B_OK; });
 }
 
 void m3b_synchronize(m3b_solver_t* s) { try { s->solver->device().sync(); } catch (...) {} }

@@ -20,6 +20,7 @@ namespace m3b
     struct stage_result_t
     {
         double sums[16];        // dev::ACC_* / GRV_* / BUF_* running sums, already multiplied by cell area (not by dt)
+        double work[2];         // sum over blocks of the per-block work integral on each body (scheme.cpp:407-408)
         double dt_min;          // min over cells of spacing / max wavespeed of the output state (if requested)
         unsigned int num_negative;   // cells with sigma < 0 in the un-combined update (validate_u, scheme.cpp:726-752)
         unsigned int pad;
@@ -51,14 +52,17 @@ namespace m3b
     class device_solver_t
     {
     public:
-        /** general_only: route every block through the any-tree kernels (used by tests). */
-        device_solver_t(const solver_data_t& solver_data, int device, bool general_only = false);
+        /** general_only: route every block through the any-tree kernels; tiled_kernel: use stage_fused
+         *  even where stage_strip applies (both used by tests to cross-check the kernels). */
+        device_solver_t(const solver_data_t& solver_data, int device, bool general_only = false, bool tiled_kernel = false);
         ~device_solver_t();
 
         int device() const { return device_id; }
         std::size_t field_stride() const { return cells; }      // doubles per conserved component
         std::size_t state_doubles() const { return 3 * cells; }
         void* stream() const { return stream_; }
+        /** Launch on a caller-owned CUDA stream (e.g. torch's current stream) from now on. */
+        void set_stream(void* cuda_stream);
 
         /** Copy a state between the host layout [B][3][N][N] and the device layout [3][B][N][N]. */
         void upload(const double* host_block_major, device_field_t& dst);
@@ -103,6 +107,7 @@ namespace m3b
         int N = 0, B = 0;
         std::size_t cells = 0;
         void* stream_ = nullptr;
+        void* own_stream = nullptr;
         stage_result_t* host_results = nullptr;     // pinned
         std::uint64_t launches = 0;
         bool force_general = false;

@@ -267,6 +267,10 @@ namespace
     }
 
 
+}
+#include "stage_strip.cuh"
+namespace
+{
     // =======================================================================
     // General path: any 2:1 balanced tree
     // =======================================================================
@@ -528,10 +532,27 @@ namespace
         }
     }
 
-    /** Fold the per-CTA rows in a fixed order (deterministic), publish the stage result. */
-    __global__ void __launch_bounds__(THREADS) finish_stage(const double* __restrict__ partials, int num_rows, fail_dev_t* fail, stage_result_t* result)
+    /** Inputs of the per-block `work` integral (scheme.cpp:363-374, 407-408). */
+    struct work_inputs_t
+    {
+        double mass[2], vx[2], vy[2];   // the two bodies at the stage time
+        double dt;
+        int rows_per_fused_block;       // CTA rows per block written by the fused kernel
+        int num_fused_blocks;
+        int num_general_blocks;         // one row each, after the fused rows
+    };
+
+    /**
+     * Fold the per-CTA rows in a fixed order (deterministic) and publish the stage result.
+     * The reference evaluates the work done on each body PER BLOCK from that block's accreted
+     * mass and momentum -- a non-linear function -- and then sums over blocks
+     * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
+     */
+    __global__ void __launch_bounds__(THREADS) finish_stage(const double* __restrict__ partials, int num_rows, work_inputs_t W,
+        fail_dev_t* fail, stage_result_t* result)
     {
         __shared__ double red[THREADS];
+        __shared__ double wred[2][THREADS];
         const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = THREADS / 32;
         double v = col == NUM_SUMS ? 1e300 : 0.0;
 
@@ -544,6 +565,33 @@ namespace
             }
         }
         red[threadIdx.x] = v;
+
+        double work[2] = {0.0, 0.0};
+        for (int blk = threadIdx.x; blk < W.num_fused_blocks + W.num_general_blocks; blk += THREADS)
+        {
+            const bool fused = blk < W.num_fused_blocks;
+            const int r0 = fused ? blk * W.rows_per_fused_block : W.num_fused_blocks * W.rows_per_fused_block + (blk - W.num_fused_blocks);
+            const int nr = fused ? W.rows_per_fused_block : 1;
+
+            for (int k = 0; k < 2; ++k)
+            {
+                double dm = 0.0, dpx = 0.0, dpy = 0.0;
+                for (int r = r0; r < r0 + nr; ++r)
+                {
+                    dm  += partials[size_t(r) * ROW + ACC_MASS + k];
+                    dpx += partials[size_t(r) * ROW + ACC_PX + k];
+                    dpy += partials[size_t(r) * ROW + ACC_PY + k];
+                }
+                if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
+                {
+                    double M0 = W.mass[k], px0 = W.vx[k] * M0, py0 = W.vy[k] * M0;
+                    double M1 = M0 + dm * W.dt, px1 = px0 + dpx * W.dt, py1 = py0 + dpy * W.dt;
+                    work[k] += ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
+                }
+            }
+        }
+        wred[0][threadIdx.x] = work[0];
+        wred[1][threadIdx.x] = work[1];
         __syncthreads();
 
         if (grp == 0 && col <= NUM_SUMS)
@@ -554,6 +602,13 @@ namespace
                 v = col == NUM_SUMS ? fmin(v, p) : v + p;
             }
             if (col < NUM_SUMS) result->sums[col] = v; else result->dt_min = v;
+        }
+        if (threadIdx.x == 32 || threadIdx.x == 33)
+        {
+            const int k = threadIdx.x - 32;
+            double w = 0.0;
+            for (int t = 0; t < THREADS; ++t) w += wred[k][t];
+            result->work[k] = w;
         }
         if (threadIdx.x == 0) result->num_negative = fail->count;
     }
@@ -616,6 +671,8 @@ struct device_solver_t::impl_t
     mesh_dev_t mesh {};
     model_t model {};
     int tile_x = 0, tile_y = 0;
+    bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
+    unsigned char* d_tile_flags = nullptr;
     std::vector<int> regular, irregular, gradient_blocks;
     int* d_regular = nullptr;
     int* d_irregular = nullptr;
@@ -631,7 +688,7 @@ struct device_solver_t::impl_t
     int sm_count = 148;
 };
 
-device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool general_only) : impl(new impl_t), device_id(device), force_general(general_only)
+device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool general_only, bool tiled_kernel) : impl(new impl_t), device_id(device), force_general(general_only)
 {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -648,7 +705,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
 
     cudaStream_t s;
     M3B_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    stream_ = s;
+    stream_ = own_stream = s;
 
     // ---- static mesh data
     auto spacing = std::vector<double>(B);
@@ -679,7 +736,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         (regular ? impl->regular : impl->irregular).push_back(b);
     }
     // tile shape of the fused kernel; blocks whose size no tile divides all take the general path
-    if      (N % 32 == 0) { impl->tile_x = 16; impl->tile_y = 32; }
+    if      (N % 32 == 0) { impl->tile_x = 16; impl->tile_y = 32; impl->strip = ! tiled_kernel; }
     else if (N % 24 == 0) { impl->tile_x = 12; impl->tile_y = 24; }
     else if (N % 16 == 0) { impl->tile_x = 16; impl->tile_y = 16; }
     else if (N % 8 == 0)  { impl->tile_x = 8;  impl->tile_y = 8; }
@@ -715,6 +772,22 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->mesh.gslot = device_upload(gslot);
     impl->mesh.U0 = device_upload(sd.initial_conserved_u);
     impl->mesh.br = device_upload(sd.buffer_rate_field);
+    if (impl->tile_x)
+    {
+        // static per-tile flags: bit 0 = the buffer-zone rate is non-zero somewhere in the tile
+        const int tx = impl->tile_x, ty = impl->tile_y, tiles_y = N / ty, tpb = (N / tx) * tiles_y;
+        auto flags = std::vector<unsigned char>(size_t(B) * tpb, 0);
+        for (int b = 0; b < B; ++b)
+            for (int t = 0; t < tpb; ++t)
+            {
+                bool any = false;
+                for (int i = (t / tiles_y) * tx; i < (t / tiles_y + 1) * tx && ! any; ++i)
+                    for (int j = (t % tiles_y) * ty; j < (t % tiles_y + 1) * ty; ++j)
+                        if (sd.buffer_rate_field[(size_t(b) * N + i) * N + j] != 0.0) { any = true; break; }
+                flags[size_t(b) * tpb + t] = any;
+            }
+        impl->d_tile_flags = device_upload(flags);
+    }
     impl->d_regular = device_upload(impl->regular);
     impl->d_irregular = device_upload(impl->irregular);
     impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
@@ -749,6 +822,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         M3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
     };
     if (impl->tile_x == 16 && impl->tile_y == 32) set_smem(stage_fused<16, 32>, sizeof(tile_t<16, 32>));
+    if (impl->strip) set_smem(stage_strip, sizeof(strip_smem_t));
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
     if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
     if (impl->tile_x == 8  && impl->tile_y == 8)  set_smem(stage_fused<8, 8>, sizeof(tile_t<8, 8>));
@@ -761,12 +835,18 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.nbr,
                    (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
                    (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
-                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_fail, (void*) impl->d_results})
+                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail, (void*) impl->d_results})
         if (p) cudaFree(p);
     for (auto p : impl->owned) cudaFree(p);
     for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (host_results) cudaFreeHost(host_results);
-    cudaStreamDestroy(cudaStream_t(stream_));
+    cudaStreamDestroy(cudaStream_t(own_stream));
+}
+
+void device_solver_t::set_stream(void* cuda_stream)
+{
+    sync();
+    stream_ = cuda_stream ? cuda_stream : own_stream;
 }
 
 void device_solver_t::upload(const double* host, device_field_t& dst)
@@ -867,7 +947,10 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
         }
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<fused_ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
             impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot)
-        if      (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
+        if (impl->strip)
+            stage_strip<<<fused_ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_regular, impl->d_tile_flags,
+                in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot);
+        else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
         else if (impl->tile_x == 16 && impl->tile_y == 16) M3B_LAUNCH_FUSED(16, 16);
         else                                               M3B_LAUNCH_FUSED(8, 8);
@@ -890,7 +973,14 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
-    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, impl->d_fail + slot, impl->d_results + slot);
+    work_inputs_t W;
+    W.mass[0] = inputs.bodies.body1.mass; W.vx[0] = inputs.bodies.body1.vx; W.vy[0] = inputs.bodies.body1.vy;
+    W.mass[1] = inputs.bodies.body2.mass; W.vx[1] = inputs.bodies.body2.vx; W.vy[1] = inputs.bodies.body2.vy;
+    W.dt = inputs.dt;
+    W.rows_per_fused_block = num_fused ? fused_ctas / num_fused : 1;
+    W.num_fused_blocks = num_fused;
+    W.num_general_blocks = num_general;
+    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot, impl->d_results + slot);
     ++launches;
     M3B_CUDA(cudaGetLastError());
     M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
@@ -906,7 +996,8 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     st.x2 = bodies.body2.x; st.y2 = bodies.body2.y; st.m2 = bodies.body2.mass;
     M3B_CUDA(cudaMemsetAsync(impl->d_fail + slot, 0, 8, s));
     max_timestep_kernel<<<B, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
-    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, B, impl->d_fail + slot, impl->d_results + slot);
+    work_inputs_t W = {};
+    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, B, W, impl->d_fail + slot, impl->d_results + slot);
     launches += 2;
     M3B_CUDA(cudaGetLastError());
     M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));

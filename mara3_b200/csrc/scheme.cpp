@@ -51,7 +51,7 @@ void solution_t::set_scalars(const double o[num_scalars])
     orbital_elements = get(33);
 }
 
-binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool general_only)
+binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool general_only, bool tiled_kernel)
 : config(run_config)
 , data(create_solver_data(run_config))
 {
@@ -62,7 +62,7 @@ binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool ge
         throw std::invalid_argument("binary::next_solution");
     if (device >= 0)
     {
-        gpu = std::make_unique<device_solver_t>(data, device, general_only);
+        gpu = std::make_unique<device_solver_t>(data, device, general_only, tiled_kernel);
         scratch1 = new_field();
         scratch2 = new_field();
     }
@@ -135,9 +135,7 @@ status_t binary_solver_t::bookkeeping(const solution_t& in, const stage_result_t
         fy[k]       = -r.sums[GRV_FY + k] * dt;
         torque[k]   = -r.sums[GRV_TQ + k] * dt;
 
-        double M0 = body[k]->mass, px0 = body[k]->vx * M0, py0 = body[k]->vy * M0;      // `work` lambda, scheme.cpp:363-374
-        double M1 = M0 + mass_acc[k], px1 = px0 + px_acc[k], py1 = py0 + py_acc[k];
-        work[k] = ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
+        work[k]     = r.work[k];        // evaluated per block on the device, then summed (scheme.cpp:407-408)
     }
     double mass_ejected = -r.sums[BUF_M] * dt;
     double lz_ejected   = -r.sums[BUF_L] * dt;

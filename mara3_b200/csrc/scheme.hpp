@@ -51,7 +51,7 @@ namespace m3b
     class binary_solver_t
     {
     public:
-        binary_solver_t(const config_t& run_config, int device, bool general_only = false);
+        binary_solver_t(const config_t& run_config, int device, bool general_only = false, bool tiled_kernel = false);
 
         const config_t& run_config() const { return config; }
         const solver_data_t& solver_data() const { return data; }
