@@ -74,20 +74,30 @@ __device__ __forceinline__ prim_t cons_to_prim(double s, double px, double py)
     return {s, px * inv, py * inv};
 }
 
+/** min / max by compare-and-select: no NaN canonicalisation (DSETP + 2 SEL instead of ~6 instructions). */
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
 /**
  * Un-divided PLM difference: mara::plm_gradient (math_interpolation.hpp:85-94),
- * i.e. 0.25 |sgn a + sgn b| (sgn a + sgn c) min(|a|, |b|, |c|), which is
- * sgn(a) min(...) when a, b, c share a sign bit and zero otherwise.
+ *   0.25 |sgn a + sgn b| (sgn a + sgn c) min(|a|, |b|, |c|),  a = theta dl, b = (dl + dr) / 2, c = theta dr
+ * with dl = y0 - yl, dr = yr - y0.  b carries the common sign whenever dl and dr agree in sign and
+ * the result is zero when they do not, so it equals sgn(dl) min(theta min(|dl|, |dr|), (|dl| + |dr|) / 2)
+ * when the sign bits of dl and dr agree and 0 otherwise.
  */
+__device__ __forceinline__ double plm_from_differences(double dl, double dr, double theta)
+{
+    double al = fabs(dl), ar = fabs(dr);
+    double m = dmin(theta * dmin(al, ar), 0.5 * (al + ar));
+    int hl = __double2hiint(dl), hr = __double2hiint(dr);
+    int hi = (hl ^ hr) >= 0 ? (__double2hiint(m) | (hl & 0x80000000)) : 0;
+    int lo = (hl ^ hr) >= 0 ? __double2loint(m) : 0;
+    return __hiloint2double(hi, lo);
+}
+
 __device__ __forceinline__ double plm_diff(double yl, double y0, double yr, double theta)
 {
-    double a = (y0 - yl) * theta;
-    double b = (yr - yl) * 0.5;
-    double c = (yr - y0) * theta;
-    int ha = __double2hiint(a), hb = __double2hiint(b), hc = __double2hiint(c);
-    double m = fmin(fmin(fabs(a), fabs(b)), fabs(c));
-    bool same = ((ha ^ hb) | (ha ^ hc)) >= 0;    // sign bits of all three agree
-    return same ? copysign(m, a) : 0.0;
+    return plm_from_differences(y0 - yl, yr - y0, theta);
 }
 
 /** Sound speed squared and geometry-only viscosity factor at a point. */
@@ -112,6 +122,42 @@ __device__ __forceinline__ double sound_speed_squared(const model_t& M, const st
     return fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;              // -(phi1 + phi2) / M^2
 }
 
+/** nu_at_position's cutoff profile / constant-nu branch (scheme.cpp:177-193): rare, kept out of line. */
+__device__ __noinline__ double viscosity_slow_path(double nu, double alpha, double alpha_cutoff_radius, double inv_mach, double cs, double r2)
+{
+    double r = sqrt(r2);
+    double profile = alpha_cutoff_radius > 0.0 ? 0.5 * (1.0 + tanh(3.0 * (r - alpha_cutoff_radius))) : 1.0;
+    return nu > 0.0 ? profile * nu : profile * alpha * cs * (r * inv_mach);
+}
+
+/** sink_rate_field (scheme.cpp:117-126) where it is not negligible: rare, kept out of line. */
+__device__ __noinline__ double sink_weight(double rate, double a2)
+{
+    return a2 < 100.0 ? rate * exp(-a2) : 0.0;
+}
+
+/**
+ * The same from the softened squared distances d_k = |x - x_k|^2 + rs^2 to the two bodies and
+ * r2 = |x|^2 (the strip kernel tabulates their x- and y-parts per tile row / column).
+ */
+__device__ __forceinline__ eos_t eos_from_distances(const model_t& M, const stage_t& S, double d1, double d2, double r2)
+{
+    eos_t e;
+    e.cs2 = M.axisymmetric_cs2 ? fast_rsqrt(r2) * M.inv_mach2 : fma(S.m1, fast_rsqrt(d1), S.m2 * fast_rsqrt(d2)) * M.inv_mach2;
+    e.cs = e.cs2 * fast_rsqrt(e.cs2);
+
+    if (M.nu > 0.0 || M.alpha_cutoff_radius > 0.0)
+    {
+        e.nu = viscosity_slow_path(M.nu, M.alpha, M.alpha_cutoff_radius, M.inv_mach, e.cs, r2);
+    }
+    else
+    {
+        double q = e.cs2 * r2;
+        e.nu = M.alpha * M.inv_mach * (q * fast_rsqrt(q));
+    }
+    return e;
+}
+
 __device__ __forceinline__ eos_t eos_at_face(const model_t& M, const stage_t& S, double x, double y)
 {
     double y1, y2;
@@ -123,9 +169,7 @@ __device__ __forceinline__ eos_t eos_at_face(const model_t& M, const stage_t& S,
 
     if (M.nu > 0.0 || M.alpha_cutoff_radius > 0.0)
     {
-        double r = r2 * fast_rsqrt(r2);
-        double profile = M.alpha_cutoff_radius > 0.0 ? 0.5 * (1.0 + tanh(3.0 * (r - M.alpha_cutoff_radius))) : 1.0;
-        e.nu = M.nu > 0.0 ? profile * M.nu : profile * M.alpha * e.cs * (r * M.inv_mach);
+        e.nu = viscosity_slow_path(M.nu, M.alpha, M.alpha_cutoff_radius, M.inv_mach, e.cs, r2);
     }
     else
     {
@@ -156,22 +200,41 @@ __device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, 
 
     double vl = AXIS == 0 ? L.vx : L.vy;
     double vr = AXIS == 0 ? R.vx : R.vy;
-    double ap = fmax(0.0, fmax(vl + e.cs, vr + e.cs));
-    double am = fmin(0.0, fmin(vl - e.cs, vr - e.cs));
-    double inv = fast_rcp(ap - am);
-    double apam = ap * am;
+    double ap = dmax(0.0, dmax(vl, vr) + e.cs);     // max(0, vl + cs, vr + cs)
+    double am = dmin(0.0, dmin(vl, vr) - e.cs);     // min(0, vl - cs, vr - cs)
+    double f0, f1, f2;
+    const unsigned active = __activemask();
 
-    double Ul1 = L.s * L.vx, Ul2 = L.s * L.vy, Ur1 = R.s * R.vx, Ur2 = R.s * R.vy;
-    double Fl0 = vl * L.s, Fr0 = vr * R.s;
-    double pgl = L.s * e.cs2, pgr = R.s * e.cs2;
-    double Fl1 = AXIS == 0 ? fma(Fl0, L.vx, pgl) : Fl0 * L.vx;
-    double Fl2 = AXIS == 0 ? Fl0 * L.vy : fma(Fl0, L.vy, pgl);
-    double Fr1 = AXIS == 0 ? fma(Fr0, R.vx, pgr) : Fr0 * R.vx;
-    double Fr2 = AXIS == 0 ? Fr0 * R.vy : fma(Fr0, R.vy, pgr);
-
-    double f0 = fma(Fl0, ap, fma(-Fr0, am, -(L.s - R.s) * apam)) * inv;
-    double f1 = fma(Fl1, ap, fma(-Fr1, am, -(Ul1 - Ur1) * apam)) * inv;
-    double f2 = fma(Fl2, ap, fma(-Fr2, am, -(Ul2 - Ur2) * apam)) * inv;
+    if (__all_sync(active, am == 0.0))
+    {
+        // every face of the warp is supersonic towards +n: (Fl ap - Fr 0 - (Ul - Ur) ap 0) / ap = Fl
+        double pgl = L.s * e.cs2;
+        f0 = vl * L.s;
+        f1 = AXIS == 0 ? fma(f0, L.vx, pgl) : f0 * L.vx;
+        f2 = AXIS == 0 ? f0 * L.vy : fma(f0, L.vy, pgl);
+    }
+    else if (__all_sync(active, ap == 0.0))
+    {
+        double pgr = R.s * e.cs2;       // ... towards -n: the flux of the right state
+        f0 = vr * R.s;
+        f1 = AXIS == 0 ? fma(f0, R.vx, pgr) : f0 * R.vx;
+        f2 = AXIS == 0 ? f0 * R.vy : fma(f0, R.vy, pgr);
+    }
+    else
+    {
+        double inv = fast_rcp(ap - am);
+        double apam = ap * am;
+        double Ul1 = L.s * L.vx, Ul2 = L.s * L.vy, Ur1 = R.s * R.vx, Ur2 = R.s * R.vy;
+        double Fl0 = vl * L.s, Fr0 = vr * R.s;
+        double pgl = L.s * e.cs2, pgr = R.s * e.cs2;
+        double Fl1 = AXIS == 0 ? fma(Fl0, L.vx, pgl) : Fl0 * L.vx;
+        double Fl2 = AXIS == 0 ? Fl0 * L.vy : fma(Fl0, L.vy, pgl);
+        double Fr1 = AXIS == 0 ? fma(Fr0, R.vx, pgr) : Fr0 * R.vx;
+        double Fr2 = AXIS == 0 ? Fr0 * R.vy : fma(Fr0, R.vy, pgr);
+        f0 = fma(Fl0, ap, fma(-Fr0, am, -(L.s - R.s) * apam)) * inv;
+        f1 = fma(Fl1, ap, fma(-Fr1, am, -(Ul1 - Ur1) * apam)) * inv;
+        f2 = fma(Fl2, ap, fma(-Fr2, am, -(Ul2 - Ur2) * apam)) * inv;
+    }
 
     // mu = 0.5 nu (sigma_l + sigma_r); the stresses use face averages 0.5 (g_l + g_r)
     double mu = (0.25 * visc_scale) * e.nu * (L.s + R.s);
@@ -228,8 +291,8 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
 
     if (e1 < 100.0 || e2 < 100.0)
     {
-        double w1 = e1 < 100.0 ? M.sink_rate * exp(-e1) : 0.0;
-        double w2 = e2 < 100.0 ? M.sink_rate * exp(-e2) : 0.0;
+        double w1 = sink_weight(M.sink_rate, e1);
+        double w2 = sink_weight(M.sink_rate, e2);
         double lz = fma(x, py, -y * px);
         sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
         sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
@@ -262,7 +325,7 @@ __device__ __forceinline__ double max_wavespeed(const model_t& M, const stage_t&
     double cs = cs2 * fast_rsqrt(cs2);
     double inv = fast_rcp(s);
     double vx = fabs(px * inv), vy = fabs(py * inv);
-    return fmax(vx, vy) + cs;       // max(|v - cs|, |v + cs|) = |v| + cs for cs >= 0
+    return dmax(vx, vy) + cs;       // max(|v - cs|, |v + cs|) = |v| + cs for cs >= 0
 }
 
 }} // namespace m3b::dev

@@ -21,6 +21,7 @@
  */
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -38,6 +39,7 @@ namespace
 {
     constexpr int THREADS = 256;
     constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
+    constexpr int FINISH_THREADS = 1024;
 
     struct face_nbr_dev_t
     {
@@ -548,26 +550,34 @@ namespace
      * mass and momentum -- a non-linear function -- and then sums over blocks
      * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
      */
-    __global__ void __launch_bounds__(THREADS) finish_stage(const double* __restrict__ partials, int num_rows, work_inputs_t W,
+    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* __restrict__ partials, int num_rows, work_inputs_t W,
         fail_dev_t* fail, stage_result_t* result)
     {
-        __shared__ double red[THREADS];
-        __shared__ double wred[2][THREADS];
-        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = THREADS / 32;
-        double v = col == NUM_SUMS ? 1e300 : 0.0;
+        __shared__ double red[FINISH_THREADS];
+        __shared__ double wred[2][FINISH_THREADS];
+        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = FINISH_THREADS / 32;
+        const bool is_min = col == NUM_SUMS;
+        double v = is_min ? 1e300 : 0.0;
 
         if (col <= NUM_SUMS)
         {
-            for (int r = grp; r < num_rows; r += ngrp)
+            int r = grp;
+            for (; r + 3 * ngrp < num_rows; r += 4 * ngrp)      // four rows in flight per thread
+            {
+                double p0 = partials[size_t(r) * ROW + col], p1 = partials[size_t(r + ngrp) * ROW + col];
+                double p2 = partials[size_t(r + 2 * ngrp) * ROW + col], p3 = partials[size_t(r + 3 * ngrp) * ROW + col];
+                v = is_min ? dmin(dmin(v, p0), dmin(dmin(p1, p2), p3)) : (((v + p0) + p1) + p2) + p3;
+            }
+            for (; r < num_rows; r += ngrp)
             {
                 double p = partials[size_t(r) * ROW + col];
-                v = col == NUM_SUMS ? fmin(v, p) : v + p;
+                v = is_min ? dmin(v, p) : v + p;
             }
         }
         red[threadIdx.x] = v;
 
         double work[2] = {0.0, 0.0};
-        for (int blk = threadIdx.x; blk < W.num_fused_blocks + W.num_general_blocks; blk += THREADS)
+        for (int blk = threadIdx.x; blk < W.num_fused_blocks + W.num_general_blocks; blk += FINISH_THREADS)
         {
             const bool fused = blk < W.num_fused_blocks;
             const int r0 = fused ? blk * W.rows_per_fused_block : W.num_fused_blocks * W.rows_per_fused_block + (blk - W.num_fused_blocks);
@@ -599,18 +609,21 @@ namespace
             for (int g = 1; g < ngrp; ++g)
             {
                 double p = red[g * 32 + col];
-                v = col == NUM_SUMS ? fmin(v, p) : v + p;
+                v = is_min ? dmin(v, p) : v + p;
             }
             if (col < NUM_SUMS) result->sums[col] = v; else result->dt_min = v;
         }
-        if (threadIdx.x == 32 || threadIdx.x == 33)
+        if (grp == 1 && col < 2)
         {
-            const int k = threadIdx.x - 32;
             double w = 0.0;
-            for (int t = 0; t < THREADS; ++t) w += wred[k][t];
-            result->work[k] = w;
+            for (int t = 0; t < FINISH_THREADS; ++t) w += wred[col][t];
+            result->work[col] = w;
         }
-        if (threadIdx.x == 0) result->num_negative = fail->count;
+        if (threadIdx.x == 64)
+        {
+            result->num_negative = fail->count;
+            fail->count = 0;            // ready for the next launch that uses this slot
+        }
     }
 
     /** [B][3][NN] (host, block major) <-> [3][B][NN] (device, field major) */
@@ -671,6 +684,7 @@ struct device_solver_t::impl_t
     mesh_dev_t mesh {};
     model_t model {};
     int tile_x = 0, tile_y = 0;
+    int strip_min_ctas = 4;
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     unsigned char* d_tile_flags = nullptr;
     std::vector<int> regular, irregular, gradient_blocks;
@@ -812,8 +826,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * cells * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_fail, num_slots * sizeof(fail_dev_t)));
-    M3B_CUDA(cudaMalloc(&impl->d_results, num_slots * sizeof(stage_result_t)));
-    M3B_CUDA(cudaMallocHost(&host_results, num_slots * sizeof(stage_result_t)));
+    // stage results live in mapped pinned host memory: finish_stage writes them straight to the host
+    M3B_CUDA(cudaHostAlloc(&host_results, num_slots * sizeof(stage_result_t), cudaHostAllocMapped));
+    M3B_CUDA(cudaHostGetDevicePointer(&impl->d_results, host_results, 0));
+    M3B_CUDA(cudaMemset(impl->d_fail, 0, num_slots * sizeof(fail_dev_t)));
     M3B_CUDA(cudaMalloc(&impl->d_gradients, std::max<size_t>(1, 6 * impl->mesh.GS) * sizeof(double)));
 
     auto set_smem = [&] (auto kernel, size_t bytes)
@@ -822,7 +838,15 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         M3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
     };
     if (impl->tile_x == 16 && impl->tile_y == 32) set_smem(stage_fused<16, 32>, sizeof(tile_t<16, 32>));
-    if (impl->strip) set_smem(stage_strip, sizeof(strip_smem_t));
+    if (impl->strip)
+    {
+        // experiment knob: registers per thread vs resident CTAs (default 4 CTAs x 128 threads, 128 registers)
+        const char* e = std::getenv("M3B_STRIP_MIN_CTAS");
+        impl->strip_min_ctas = e ? std::atoi(e) : 4;
+        set_smem(stage_strip<4>, sizeof(strip_smem_t));
+        set_smem(stage_strip<3>, sizeof(strip_smem_t));
+        set_smem(stage_strip<2>, sizeof(strip_smem_t));
+    }
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
     if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
     if (impl->tile_x == 8  && impl->tile_y == 8)  set_smem(stage_fused<8, 8>, sizeof(tile_t<8, 8>));
@@ -835,7 +859,7 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.nbr,
                    (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
                    (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
-                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail, (void*) impl->d_results})
+                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail})
         if (p) cudaFree(p);
     for (auto p : impl->owned) cudaFree(p);
     for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -928,7 +952,6 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
     st.combine = inputs.combine;
     st.compute_dt = inputs.compute_dt;
 
-    M3B_CUDA(cudaMemsetAsync(impl->d_fail + slot, 0, 8, s));
 
     const double* un_data = un ? un->data : nullptr;
     int num_fused = force_general ? 0 : int(impl->regular.size());
@@ -948,8 +971,11 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<fused_ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
             impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot)
         if (impl->strip)
-            stage_strip<<<fused_ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_regular, impl->d_tile_flags,
+        {
+            auto kernel = impl->strip_min_ctas == 2 ? stage_strip<2> : (impl->strip_min_ctas == 3 ? stage_strip<3> : stage_strip<4>);
+            kernel<<<fused_ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_regular, impl->d_tile_flags,
                 in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot);
+        }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
         else if (impl->tile_x == 16 && impl->tile_y == 16) M3B_LAUNCH_FUSED(16, 16);
@@ -980,10 +1006,9 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
     W.rows_per_fused_block = num_fused ? fused_ctas / num_fused : 1;
     W.num_fused_blocks = num_fused;
     W.num_general_blocks = num_general;
-    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot, impl->d_results + slot);
+    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot, impl->d_results + slot);
     ++launches;
     M3B_CUDA(cudaGetLastError());
-    M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
 }
 
 void device_solver_t::launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot)
@@ -994,13 +1019,11 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     st.time = time;
     st.x1 = bodies.body1.x; st.y1 = bodies.body1.y; st.m1 = bodies.body1.mass;
     st.x2 = bodies.body2.x; st.y2 = bodies.body2.y; st.m2 = bodies.body2.mass;
-    M3B_CUDA(cudaMemsetAsync(impl->d_fail + slot, 0, 8, s));
     max_timestep_kernel<<<B, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
     work_inputs_t W = {};
-    finish_stage<<<1, THREADS, 0, s>>>(impl->d_partials, B, W, impl->d_fail + slot, impl->d_results + slot);
+    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, B, W, impl->d_fail + slot, impl->d_results + slot);
     launches += 2;
     M3B_CUDA(cudaGetLastError());
-    M3B_CUDA(cudaMemcpyAsync(host_results + slot, impl->d_results + slot, sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
 }
 
 void device_solver_t::sync()
@@ -1015,7 +1038,7 @@ std::vector<offender_t> device_solver_t::offenders(int slot)
     M3B_CUDA(cudaSetDevice(device_id));
     M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
     M3B_CUDA(cudaMemcpy(&f, impl->d_fail + slot, sizeof(fail_dev_t), cudaMemcpyDeviceToHost));
-    auto n = std::min<unsigned>(f.count, max_offenders);
+    auto n = std::min<unsigned>(host_results[slot].num_negative, max_offenders);
     auto v = std::vector<offender_t>(f.list, f.list + n);
     std::sort(v.begin(), v.end(), [] (const offender_t& a, const offender_t& b) { return a.block != b.block ? a.block < b.block : a.cell < b.cell; });
     return v;

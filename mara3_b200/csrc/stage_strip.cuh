@@ -9,11 +9,11 @@
  *   P0   tile + 2-cell halo: coalesced row loads (15-30 in flight per thread), conserved -> primitive,
  *        into shared memory.
  *   P1   PLM differences on tile + 1 halo, marching down the strip with the x-stencil in registers.
- *   P2/3 one rolled loop down the strip: each iteration computes the low-x and low-y HLLE + viscous
- *        fluxes of a row, issues the loads the row's update will need, and finishes the update of
- *        the row before (its high-x flux is the x-face just computed, its high-y flux comes from
- *        lane + 1 by shuffle); tile-boundary faces and strip-to-strip fluxes go through two small
- *        shared arrays.  Cells are written once; 16 running sums, the CFL minimum and the
+ *   P2/3 a software-pipelined loop down the strip: each iteration issues the loads for the update of
+ *        the row before, computes the low-x and low-y HLLE + viscous fluxes of its row while they are
+ *        in flight, and finishes that update (its high-x flux is the x-face just computed, its high-y
+ *        flux comes from lane + 1 by shuffle); tile-boundary faces and strip-to-strip fluxes go
+ *        through two small shared arrays.  Cells are written once; 16 running sums, the CFL minimum and the
  *        negative-density count are folded per CTA.
  *
  * The loop is rolled on purpose: fully unrolled the kernel is 110 KB of SASS and a fifth of all
@@ -33,6 +33,10 @@ namespace
         double YB[3][SX];                   // y-face fluxes at the tile's high-y boundary
         double xv[SX + 1];
         double yv[SY + 1];
+        // squared-distance tables of the tile's face / centre coordinates to the two bodies (k = 0, 1) and
+        // to the origin (k = 2); the y tables of the bodies already hold the softening rs^2
+        double x2v[3][SX + 1], x2c[3][SX];      // (xv - x_k)^2, (xc - x_k)^2
+        double y2v[3][SY + 1], y2c[3][SY];      // (yv - y_k)^2 [+ rs^2], (yc - y_k)^2 [+ rs^2]
         double red[STRIP_THREADS / 32][NUM_SUMS + 1];
     };
 
@@ -44,7 +48,7 @@ namespace
     /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX */
     __device__ __forceinline__ void strip_x_face(const strip_smem_t& T, const model_t& model, const stage_t& S, double inv_h, int li, int lj, double F[3])
     {
-        eos_t e = eos_at_face(model, S, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]));
+        eos_t e = eos_from_distances(model, S, T.x2v[0][li] + T.y2c[0][lj], T.x2v[1][li] + T.y2c[1][lj], T.x2v[2][li] + T.y2c[2][lj]);
         prim_t pl = {T.P[0][li + 1][lj + 2], T.P[1][li + 1][lj + 2], T.P[2][li + 1][lj + 2]};
         prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
         prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]};
@@ -55,7 +59,7 @@ namespace
     /** y-face between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= SY */
     __device__ __forceinline__ void strip_y_face(const strip_smem_t& T, const model_t& model, const stage_t& S, double inv_h, int li, int lj, double F[3])
     {
-        eos_t e = eos_at_face(model, S, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj]);
+        eos_t e = eos_from_distances(model, S, T.x2c[0][li] + T.y2v[0][lj], T.x2c[1][li] + T.y2v[1][lj], T.x2c[2][li] + T.y2v[2][lj]);
         prim_t pl = {T.P[0][li + 2][lj + 1], T.P[1][li + 2][lj + 1], T.P[2][li + 2][lj + 1]};
         prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
         prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]};
@@ -63,7 +67,8 @@ namespace
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
     }
 
-    __global__ void __launch_bounds__(STRIP_THREADS, 4) stage_strip(
+    template<int MIN_CTAS>
+    __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ regular_list,
         const unsigned char* __restrict__ tile_flags,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
@@ -103,28 +108,73 @@ namespace
 
         // ------------------------------------------------------------------ phase 0: load + primitives
         {
-            // region column c <-> global column j0 - 2 + c; group A: c = lane, group B: c = 32 + lane (lane < 4)
+            // region column c <-> global column j0 - 2 + c; group A: c = lane, group B: c = 32 + lane (lane < 4);
+            // region row r = warp + 4 k <-> global row i0 - 2 + r.  Only rows 0, 1 (k = 0) can lie in the low-x
+            // neighbour and rows 18, 19 (k = 4) in the high-x neighbour.
             const int gjA = j0 - 2 + lane, gjB = j0 + 30 + lane;
             const int djA = gjA < 0 ? -1 : 0, djB = gjB >= N ? 1 : 0;
-            const int colA = gjA - djA * N, colB = gjB - djB * N;
+            const long colA = gjA - djA * N, colB = gjB - djB * N;
             const int* n9 = mesh.nbr9 + size_t(b) * 9;
-            const int nbAm = n9[0 * 3 + djA + 1], nbA0 = n9[1 * 3 + djA + 1], nbAp = n9[2 * 3 + djA + 1];
-            const int nbBm = n9[0 * 3 + djB + 1], nbB0 = n9[1 * 3 + djB + 1], nbBp = n9[2 * 3 + djB + 1];
+            const long NN = long(N) * N;
+            const bool low = i0 == 0 && warp < 2, high = i0 + SX == N && warp >= 2;
+            const long in_block = long(i0 - 2 + warp) * N, stride = 4L * N;
+            const long baseA = n9[3 + djA + 1] * NN + colA + in_block, baseB = n9[3 + djB + 1] * NN + colB + in_block;
+            const long lowA  = low  ? n9[0 + djA + 1] * NN + colA + long(N - 2 + warp) * N : baseA;
+            const long lowB  = low  ? n9[0 + djB + 1] * NN + colB + long(N - 2 + warp) * N : baseB;
+            const long highA = high ? n9[6 + djA + 1] * NN + colA + long(warp - 2) * N : baseA + 4 * stride;
+            const long highB = high ? n9[6 + djB + 1] * NN + colB + long(warp - 2) * N : baseB + 4 * stride;
+            const double* __restrict__ U1 = Uin + FS;
+            const double* __restrict__ U2 = Uin + 2 * FS;
             double uA[5][3], uB[5][3];
 
             #pragma unroll
             for (int k = 0; k < 5; ++k)
             {
-                const int r = warp + 4 * k;                     // region row, 0..19 <-> global row i0 - 2 + r
-                const int gi = i0 - 2 + r;
-                const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
-                const int row = gi - di * N;
-                const int nbA = di < 0 ? nbAm : (di > 0 ? nbAp : nbA0);
-                const int nbB = di < 0 ? nbBm : (di > 0 ? nbBp : nbB0);
-                const size_t cA = (size_t(nbA) * N + row) * N + colA;
-                const size_t cB = (size_t(nbB) * N + row) * N + colB;
-                uA[k][0] = Uin[cA]; uA[k][1] = Uin[FS + cA]; uA[k][2] = Uin[2 * FS + cA];
-                if (lane < 4) { uB[k][0] = Uin[cB]; uB[k][1] = Uin[FS + cB]; uB[k][2] = Uin[2 * FS + cB]; }
+                const long cA = k == 0 ? lowA : (k == 4 ? highA : baseA + k * stride);
+                const long cB = k == 0 ? lowB : (k == 4 ? highB : baseB + k * stride);
+                uA[k][0] = Uin[cA]; uA[k][1] = U1[cA]; uA[k][2] = U2[cA];
+                if (lane < 4) { uB[k][0] = Uin[cB]; uB[k][1] = U1[cB]; uB[k][2] = U2[cB]; }
+            }
+            // coordinate tables while the loads are in flight
+            {
+                const double* xvg = mesh.xv + size_t(b) * (N + 1) + i0;
+                const double* yvg = mesh.yv + size_t(b) * (N + 1) + j0;
+                const double bx[3] = {S.x1, S.x2, 0.0}, by[3] = {S.y1, S.y2, 0.0};
+                const double soft[3] = {model.softening_radius2, model.softening_radius2, 0.0};
+                if (warp == 0)
+                {
+                    if (lane <= SX)
+                    {
+                        const double xv = xvg[lane];
+                        T.xv[lane] = xv;
+                        #pragma unroll
+                        for (int k = 0; k < 3; ++k) T.x2v[k][lane] = (xv - bx[k]) * (xv - bx[k]);
+                    }
+                    if (lane < SX)
+                    {
+                        const double xc = 0.5 * (xvg[lane] + xvg[lane + 1]);
+                        #pragma unroll
+                        for (int k = 0; k < 3; ++k) T.x2c[k][lane] = (xc - bx[k]) * (xc - bx[k]);
+                    }
+                }
+                else if (warp == 1)
+                {
+                    const double yv = yvg[lane], yc = 0.5 * (yvg[lane] + yvg[lane + 1]);
+                    T.yv[lane] = yv;
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        T.y2v[k][lane] = fma(yv - by[k], yv - by[k], soft[k]);
+                        T.y2c[k][lane] = fma(yc - by[k], yc - by[k], soft[k]);
+                    }
+                }
+                else if (warp == 2 && lane == 0)
+                {
+                    const double yv = yvg[SY];
+                    T.yv[SY] = yv;
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k) T.y2v[k][SY] = fma(yv - by[k], yv - by[k], soft[k]);
+                }
             }
             #pragma unroll
             for (int k = 0; k < 5; ++k)
@@ -138,21 +188,19 @@ namespace
                     T.P[0][r][32 + lane] = q.s; T.P[1][r][32 + lane] = q.vx; T.P[2][r][32 + lane] = q.vy;
                 }
             }
-            if (warp == 0 && lane <= SX) T.xv[lane] = mesh.xv[size_t(b) * (N + 1) + i0 + lane];
-            if (warp == 1) T.yv[lane] = mesh.yv[size_t(b) * (N + 1) + j0 + lane];
-            if (warp == 2 && lane == 0) T.yv[SY] = mesh.yv[size_t(b) * (N + 1) + j0 + SY];
         }
         __syncthreads();
 
         // ------------------------------------------------------------------ phase 1: PLM differences
         {
             // gradient rows g = 0..17 (<-> P row g + 1): warps take 5, 5, 4, 4 consecutive rows;
-            // lane <-> gradient column c = lane (<-> P column lane + 1)
+            // lane <-> gradient column c = lane (<-> P column lane + 1).  Marching down the rows the
+            // backward x-difference of a row is the forward difference of the row before.
             const int g0 = warp < 2 ? 5 * warp : 10 + 4 * (warp - 2);
             const int g1 = g0 + (warp < 2 ? 5 : 4);
-            double pm[3], pc[3];
+            double pc[3], dl[3];
             #pragma unroll
-            for (int q = 0; q < 3; ++q) { pm[q] = T.P[q][g0][lane + 1]; pc[q] = T.P[q][g0 + 1][lane + 1]; }
+            for (int q = 0; q < 3; ++q) { pc[q] = T.P[q][g0 + 1][lane + 1]; dl[q] = pc[q] - T.P[q][g0][lane + 1]; }
 
             #pragma unroll 1
             for (int g = g0; g < g1; ++g)
@@ -160,10 +208,11 @@ namespace
                 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                 {
-                    double pp = T.P[q][g + 2][lane + 1];
-                    T.G[q][g][lane]     = plm_diff(pm[q], pc[q], pp, S.theta);
-                    T.G[3 + q][g][lane] = plm_diff(T.P[q][g + 1][lane], pc[q], T.P[q][g + 1][lane + 2], S.theta);
-                    pm[q] = pc[q]; pc[q] = pp;
+                    const double pp = T.P[q][g + 2][lane + 1];
+                    const double dr = pp - pc[q];
+                    T.G[q][g][lane]     = plm_from_differences(dl[q], dr, S.theta);
+                    T.G[3 + q][g][lane] = plm_from_differences(pc[q] - T.P[q][g + 1][lane], T.P[q][g + 1][lane + 2] - pc[q], S.theta);
+                    pc[q] = pp; dl[q] = dr;
                 }
             }
             // gradient columns 32, 33: 36 cells, taken by the two warps with one row less
@@ -174,107 +223,111 @@ namespace
                 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                 {
-                    double ctr = T.P[q][g + 1][c + 1];
-                    T.G[q][g][c]     = plm_diff(T.P[q][g][c + 1], ctr, T.P[q][g + 2][c + 1], S.theta);
-                    T.G[3 + q][g][c] = plm_diff(T.P[q][g + 1][c], ctr, T.P[q][g + 1][c + 2], S.theta);
+                    const double ctr = T.P[q][g + 1][c + 1];
+                    T.G[q][g][c]     = plm_from_differences(ctr - T.P[q][g][c + 1], T.P[q][g + 2][c + 1] - ctr, S.theta);
+                    T.G[3 + q][g][c] = plm_from_differences(ctr - T.P[q][g + 1][c], T.P[q][g + 1][c + 2] - ctr, S.theta);
                 }
             }
         }
         __syncthreads();
 
-        // ------------------------------------------------------------------ phases 2 + 3, one rolled loop
-        // iteration r = -1 : the tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1)
-        // iteration r = 0..3: the low-x and low-y faces of strip row r; loads for cell r; update of cell r - 1
-        // iteration r = 4 : the update of cell 3, whose high-x flux comes from the next strip (or the boundary row)
+        // ------------------------------------------------------------------ phases 2 + 3
         const double h = mesh.spacing[b], inv_h = 1.0 / h;
         const int li0 = STRIP * warp, lj = lane;
         const double dt_over_h = S.dt * inv_h;
         const double yc = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
         const size_t c0 = (size_t(b) * N + (i0 + li0)) * N + (j0 + lj);
+        const double* __restrict__ U0 = mesh.U0;
+        const double* __restrict__ BR = mesh.br;
 
         double sums[NUM_SUMS];
         #pragma unroll
         for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
-        double dtmin = 1e300;
-        double FxLo[3] = {0, 0, 0}, FyLo[3] = {0, 0, 0};       // low-side fluxes of the cell awaiting its update
-        double u[3] = {0, 0, 0}, un[3] = {0, 0, 0}, u0[3] = {0, 0, 0}, br = 0.0;
+        double amax = 0.0;                              // largest signal speed of the updated cells
 
-        #pragma unroll 1
-        for (int r = -1; r <= STRIP; ++r)
+        // Update of the cell in strip row r from its four face fluxes (block_update_u, scheme.cpp:568-587).
+        auto update_cell = [&] (int r, const double* u, const double* u0, double br, const double* un,
+                                const double* FxLo, const double* FxHi, const double* FyLo)
         {
-            double FxNew[3] = {0, 0, 0}, FyNew[3] = {0, 0, 0};
-            double v[3] = {0, 0, 0}, vn[3] = {0, 0, 0}, v0[3] = {0, 0, 0}, vbr = 0.0;
-
-            if (r == 1) __syncthreads();        // XB (written at r = -1, 0) and YB (r = -1) are complete
-
-            if (r >= 0 && r < STRIP)
-            {
-                // inputs of this row's update, consumed one iteration from now
-                const size_t c = c0 + size_t(r) * N;
-                v[0] = Uin[c]; v[1] = Uin[FS + c]; v[2] = Uin[2 * FS + c];
-                if (has_buffer) { vbr = mesh.br[c]; v0[0] = mesh.U0[c]; v0[1] = mesh.U0[FS + c]; v0[2] = mesh.U0[2 * FS + c]; }
-                if (S.combine)  { vn[0] = Un[c]; vn[1] = Un[FS + c]; vn[2] = Un[2 * FS + c]; }
-            }
-            // which faces this thread computes in this iteration
-            const bool do_x = r < 0 ? warp == 0 : r < STRIP;
-            const bool do_y = r < 0 ? (warp == 1 && lane < SX) : r < STRIP;
-            const int xi = r < 0 ? SX : li0 + r, xj = lj;
-            const int yi = r < 0 ? lane : li0 + r, yj = r < 0 ? SY : lj;
-
-            if (do_x) strip_x_face(T, model, S, inv_h, xi, xj, FxNew);
-            if (do_y) strip_y_face(T, model, S, inv_h, yi, yj, FyNew);
-
-            if (r < 0)
-            {
-                if (do_x) { T.XB[0][4][lj] = FxNew[0]; T.XB[1][4][lj] = FxNew[1]; T.XB[2][4][lj] = FxNew[2]; }
-                if (do_y) { T.YB[0][lane] = FyNew[0]; T.YB[1][lane] = FyNew[1]; T.YB[2][lane] = FyNew[2]; }
-            }
-            else if (r == 0)
-            {
-                if (warp > 0) { T.XB[0][warp][lj] = FxNew[0]; T.XB[1][warp][lj] = FxNew[1]; T.XB[2][warp][lj] = FxNew[2]; }
-            }
-            else
-            {
-                // update of cell r - 1: its high-x flux is this iteration's x-face, or the next strip's first face
-                const int li = li0 + r - 1;
-                const size_t c = c0 + size_t(r - 1) * N;
-                double hx[3], hy[3];
-                #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                {
-                    hx[q] = r < STRIP ? FxNew[q] : T.XB[q][warp + 1][lj];
-                    double up = shfl_down1(FyLo[q]);
-                    hy[q] = lane == 31 ? T.YB[q][li] : up;
-                }
-                const double x = 0.5 * (T.xv[li] + T.xv[li + 1]);
-                double src[3], y1, y2;
-                source_terms(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2);
-
-                double n0 = u[0] - ((hx[0] - FxLo[0]) + (hy[0] - FyLo[0])) * dt_over_h + src[0];
-                double n1 = u[1] - ((hx[1] - FxLo[1]) + (hy[1] - FyLo[1])) * dt_over_h + src[1];
-                double n2 = u[2] - ((hx[2] - FxLo[2]) + (hy[2] - FyLo[2])) * dt_over_h + src[2];
-
-                if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
-
-                if (S.combine)
-                {
-                    const double w = 1.0 - S.rk_b0;
-                    n0 = un[0] * S.rk_b0 + n0 * w;
-                    n1 = un[1] * S.rk_b0 + n1 * w;
-                    n2 = un[2] * S.rk_b0 + n2 * w;
-                }
-                Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
-
-                if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, yc, y1, y2, n0, n1, n2));
-            }
+            const int li = li0 + r;
+            const size_t c = c0 + size_t(r) * N;
+            double hy[3];
             #pragma unroll
             for (int q = 0; q < 3; ++q)
             {
-                FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q];
-                u[q] = v[q]; un[q] = vn[q]; u0[q] = v0[q];
+                double up = shfl_down1(FyLo[q]);        // the low-y face of lane + 1 is this cell's high-y face
+                hy[q] = lane == 31 ? T.YB[q][li] : up;
             }
-            br = vbr;
+            const double x = 0.5 * (T.xv[li] + T.xv[li + 1]);
+            double src[3], y1, y2;
+            source_terms(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2);
+
+            double n0 = u[0] - ((FxHi[0] - FxLo[0]) + (hy[0] - FyLo[0])) * dt_over_h + src[0];
+            double n1 = u[1] - ((FxHi[1] - FxLo[1]) + (hy[1] - FyLo[1])) * dt_over_h + src[1];
+            double n2 = u[2] - ((FxHi[2] - FxLo[2]) + (hy[2] - FyLo[2])) * dt_over_h + src[2];
+
+            if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
+
+            if (S.combine)
+            {
+                const double w = 1.0 - S.rk_b0;
+                n0 = un[0] * S.rk_b0 + n0 * w;
+                n1 = un[1] * S.rk_b0 + n1 * w;
+                n2 = un[2] * S.rk_b0 + n2 * w;
+            }
+            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
+
+            if (S.compute_dt) amax = dmax(amax, max_wavespeed(model, S, x, yc, y1, y2, n0, n1, n2));
+        };
+        auto load_cell = [&] (int r, double* u, double* u0, double& br, double* un)
+        {
+            const size_t c = c0 + size_t(r) * N;
+            u[0] = Uin[c]; u[1] = Uin[FS + c]; u[2] = Uin[2 * FS + c];
+            br = has_buffer ? BR[c] : 0.0;
+            u0[0] = has_buffer ? U0[c] : 0.0; u0[1] = has_buffer ? U0[FS + c] : 0.0; u0[2] = has_buffer ? U0[2 * FS + c] : 0.0;
+            un[0] = S.combine ? Un[c] : 0.0; un[1] = S.combine ? Un[FS + c] : 0.0; un[2] = S.combine ? Un[2 * FS + c] : 0.0;
+        };
+
+        // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
+        // faces of strip row 0, whose x-flux is also the high-x flux of the strip below
+        if (warp == 0)
+        {
+            double F[3];
+            strip_x_face(T, model, S, inv_h, SX, lj, F);
+            T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
         }
+        else if (warp == 1 && lane < SX)
+        {
+            double F[3];
+            strip_y_face(T, model, S, inv_h, lane, SY, F);
+            T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
+        }
+        double FxLo[3], FyLo[3];
+        strip_x_face(T, model, S, inv_h, li0, lj, FxLo);
+        strip_y_face(T, model, S, inv_h, li0, lj, FyLo);
+        if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
+        __syncthreads();
+
+        // steady state: the loads for cell r - 1 are issued first and hidden behind the two faces of row r
+        #pragma unroll 1
+        for (int r = 1; r < STRIP; ++r)
+        {
+            double u[3], u0[3], un[3], br, FxNew[3], FyNew[3];
+            load_cell(r - 1, u, u0, br, un);
+            strip_x_face(T, model, S, inv_h, li0 + r, lj, FxNew);
+            strip_y_face(T, model, S, inv_h, li0 + r, lj, FyNew);
+            update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
+            #pragma unroll
+            for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
+        }
+        // epilogue: the last row's high-x flux is the first face of the next strip (or the boundary row)
+        {
+            double u[3], u0[3], un[3], br, FxHi[3];
+            load_cell(STRIP - 1, u, u0, br, un);
+            FxHi[0] = T.XB[0][warp + 1][lj]; FxHi[1] = T.XB[1][warp + 1][lj]; FxHi[2] = T.XB[2][warp + 1][lj];
+            update_cell(STRIP - 1, u, u0, br, un, FxLo, FxHi, FyLo);
+        }
+        const double dtmin = S.compute_dt ? h / amax : 1e300;
 
         // ------------------------------------------------------------------ fold the CTA's sums
         // per-warp shuffle tree over the groups that can be non-zero, then 4 warps through shared memory
@@ -295,7 +348,7 @@ namespace
         {
             double m = dtmin;
             #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            for (int o = 16; o > 0; o >>= 1) m = dmin(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) T.red[warp][NUM_SUMS] = m;
         }
         __syncthreads();
@@ -304,7 +357,7 @@ namespace
             const int k = threadIdx.x;
             double* row = partials + size_t(blockIdx.x) * ROW;
             double a = T.red[0][k], bq = T.red[1][k], cq = T.red[2][k], d = T.red[3][k];
-            row[k] = k == NUM_SUMS ? fmin(fmin(a, bq), fmin(cq, d)) : ((a + bq) + (cq + d)) * (h * h);
+            row[k] = k == NUM_SUMS ? dmin(dmin(a, bq), dmin(cq, d)) : ((a + bq) + (cq + d)) * (h * h);
         }
     }
 }

@@ -1,7 +1,5 @@
-set -x
-python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log; grep -E "^(FAILED|ERROR)|^E  " gpurun_out/pytest_gpu.log | head -40
-CMD="python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e"
-$CMD > gpurun_out/bench3.json 2> gpurun_out/bench3.err; cat gpurun_out/bench3.json
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
-$CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:stage_strip -s 6 -c 2 -o gpurun_out/prof_strip2 $CMD > gpurun_out/ncu2.log 2>&1
+for m in 4 3 2; do
+  echo "== M3B_STRIP_MIN_CTAS=$m"
+  M3B_STRIP_MIN_CTAS=$m python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value', d['value'], 'ms_per_step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'])"
+  M3B_STRIP_MIN_CTAS=$m python bench.py --workload c3 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c3 value', d['value'], 'ms_per_step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'])"
+done
