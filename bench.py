@@ -174,12 +174,35 @@ def main():
     import torch
     import mara3_b200
 
-    if world > 1:
-        raise SystemExit("multi-GPU bench: see bench_multi path (not wired in this build)")
-
     torch.cuda.set_device(local_rank)
-    wl = WORKLOADS[args.workload or "c2"]
-    solver = mara3_b200.Solver(wl["config"], device=local_rank)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [mara3_b200.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    wl = WORKLOADS[args.workload or ("c2" if world == 1 else "c3")]
+    scaling_reference = None
+    if world > 1 and rank == 0:
+        # the same workload on ONE GPU, measured in this run, so that strong-scaling efficiency can be
+        # computed against the same problem (the N=1 default of this script is the smaller config 2)
+        ref = mara3_b200.Solver(wl["config"], device=local_rank)
+        ref_u = ref.create_solution()
+        ref.run_steps(ref_u, 3)
+        ref.synchronize()
+        t0 = time.perf_counter()
+        ref.run_steps(ref_u, 10)
+        ref.synchronize()
+        scaling_reference = {"n_gpus": 1, "value": ref.num_cells * 10 / (time.perf_counter() - t0) * 1e-6, "unit": "Mzps",
+                             "how": "10 steps of the same workload on rank 0's GPU alone, host clock, no L2 flush"}
+        del ref_u, ref
+    if world > 1:
+        dist.barrier()
+
+    solver = mara3_b200.Solver(wl["config"], device=local_rank, rank=rank, nranks=world, nccl_unique_id=uid)
     solution = solver.create_solution()
     cells = solver.num_cells
     flush = None if args.no_flush else torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -194,6 +217,8 @@ def main():
         solver.next_solution(solution)
     solver.synchronize()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -220,22 +245,26 @@ def main():
     launches = solver.kernel_launches - launches0
     clocks = sampler.stop()
 
-    step_ms = [a.elapsed_time(b) for a, b in events]
-    total_ms = sum(step_ms)
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in events], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)      # a step is as slow as its slowest rank
+    total_ms = float(step_ms.sum())
     ms_per_step = total_ms / args.steps
     value = cells * args.steps / (total_ms * 1e-3) * 1e-6
 
     peak, peak_how = measured_hbm_peak()
     kernel_ms = stage_ms / max(1, stage_launches)
-    achieved = cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH / (kernel_ms * 1e-3) * 1e-9 if stage_launches else None
+    local_cells = solver.num_owned_cells
+    achieved = local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH / (kernel_ms * 1e-3) * 1e-9 if stage_launches else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "kernel": "stage_fused", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
-                "algorithmic_bytes_per_launch": cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH, "peak_source": peak_how,
+                "algorithmic_bytes_per_launch": local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH, "per": "GPU (rank 0)", "peak_source": peak_how,
                 "step_frac_of_hbm_roofline": value * 1e6 * ALGORITHMIC_BYTES_PER_CELL_STEP / (peak * 1e9)}
 
     # ---- end to end through the C ABI with host buffers (H2D + step + D2H inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         shape = (solver.num_blocks, 3, solver.block_size, solver.block_size)
         u_in = torch.empty(shape, dtype=torch.float64).pin_memory()
         u_out = torch.empty(shape, dtype=torch.float64).pin_memory()
@@ -254,8 +283,17 @@ def main():
         e2e = {"value": cells * n_e2e / dt_e2e * 1e-6, "unit": "Mzps", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": n_e2e, "api": "m3b_next_solution_host (pinned host buffers)"}
 
+    exchange = None
+    if world > 1:
+        # NVLink side of the step: two guard-zone exchanges (one per RK stage) + one result all-gather
+        exchange = {"halo_bytes_sent_per_exchange_rank0": solver.halo_bytes_per_exchange, "exchanges_per_step": 2,
+                    "transport": "NCCL send/recv, grouped per stage, on the compute stream"}
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sample_steps = max(1, int(12e6 / cells))
         mzps, kind, cores, how = time_reference(wl["config"], sample_steps, 1, threads)
@@ -263,14 +301,17 @@ def main():
                         "sample": f"{sample_steps} timed steps after 1 warm-up of the same workload; {how}"}
 
     print(json.dumps({
-        "metric": "iso2d zone-updates/sec", "value": value, "unit": "Mzps", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "metric": "iso2d zone-updates/sec", "value": value, "unit": "Mzps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "keys": wl["config"], "cells": cells, "blocks": solver.num_blocks,
                    "l2": "not flushed" if args.no_flush else "flushed between steps (512 MiB fill, outside the per-step timing)",
                    "timing": "CUDA events on the launch stream around each step (a step ends with the host reading dt and the validation flag)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "safe_mode_retries": fallbacks, "wall_s": wall,
+        "safe_mode_retries": fallbacks, "wall_s": wall, "exchange": exchange, "scaling_reference": scaling_reference,
     }))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -58,11 +58,31 @@ const char* m3b_global_error(void);                     /* message of the last f
  *        bit 1 = host only: solver_data queries without a device context;
  *        bit 2 = use the tiled stage kernel even where the warp-strip kernel applies (testing). */
 m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, int flags);
+/* Multi-GPU: one process per GPU.  Rank 0 draws an NCCL unique id (128 bytes), hands it to the other
+ * ranks by any means (bench.py uses torch.distributed), and every rank creates its solver.  The leaf
+ * blocks are cut into `nranks` Morton-contiguous ranges; each rank owns one range and keeps ghost
+ * copies of the remote blocks its range touches.  Per-block queries below then refer to the OWNED
+ * blocks of the calling rank.  Uniform-level trees only in this build. */
+int         m3b_nccl_unique_id(unsigned char* out128);
+m3b_solver_t* m3b_solver_create_distributed(int argc, const char* const* argv, int device, int flags,
+                                            int rank, int nranks, const unsigned char* nccl_unique_id);
 void        m3b_solver_destroy(m3b_solver_t* s);
 const char* m3b_last_error(const m3b_solver_t* s);
 
 /* solver_data_t queries (subprog_binary.hpp:74-104) */
-int         m3b_num_blocks(const m3b_solver_t* s);
+int         m3b_num_blocks(const m3b_solver_t* s);              /* blocks owned by this rank (all of them on one rank) */
+int         m3b_num_global_blocks(const m3b_solver_t* s);       /* leaves of the whole tree */
+int         m3b_first_block(const m3b_solver_t* s);             /* global (Morton) id of the first owned block */
+int         m3b_num_local_blocks(const m3b_solver_t* s);        /* owned + ghost blocks stored on this rank */
+int64_t     m3b_num_owned_cells(const m3b_solver_t* s);
+/* guard-zone exchange plan (host side; available without a device): local -> global block ids,
+ * per peer the ordered (local block, di, dj) strips sent / received, and the 3x3 same-level
+ * neighbour table [owned][9] in local ids that the stage kernel reads its halo through */
+void        m3b_local_to_global(const m3b_solver_t* s, int* out);
+int         m3b_halo_plan_size(const m3b_solver_t* s, int peer, int send);
+void        m3b_halo_plan(const m3b_solver_t* s, int peer, int send, int* out);
+void        m3b_neighbor_table(const m3b_solver_t* s, int* out);
+uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
 int         m3b_block_size(const m3b_solver_t* s);
 int64_t     m3b_num_cells(const m3b_solver_t* s);
 int         m3b_num_regular_blocks(const m3b_solver_t* s);   /* blocks served by the fused kernel */

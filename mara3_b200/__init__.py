@@ -74,6 +74,19 @@ def load_library():
     L.m3b_global_error.restype = C.c_char_p
     L.m3b_solver_create.restype = vp
     L.m3b_solver_create.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    L.m3b_solver_create_distributed.restype = vp
+    L.m3b_solver_create_distributed.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.m3b_nccl_unique_id.argtypes = [C.c_char_p]
+    for name in ("num_global_blocks", "first_block", "num_local_blocks"):
+        getattr(L, "m3b_" + name).argtypes = [vp]
+    L.m3b_num_owned_cells.argtypes = [vp]
+    L.m3b_num_owned_cells.restype = C.c_int64
+    L.m3b_local_to_global.argtypes = [vp, ip]
+    L.m3b_halo_plan_size.argtypes = [vp, C.c_int, C.c_int]
+    L.m3b_halo_plan.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.m3b_neighbor_table.argtypes = [vp, ip]
+    L.m3b_halo_bytes_per_exchange.argtypes = [vp]
+    L.m3b_halo_bytes_per_exchange.restype = C.c_uint64
     L.m3b_solver_destroy.argtypes = [vp]
     L.m3b_last_error.restype = C.c_char_p
     L.m3b_last_error.argtypes = [vp]
@@ -186,18 +199,27 @@ class Solution:
 class Solver:
     """run_config + solver_data_t + the device context (one GPU)."""
 
-    def __init__(self, config=None, device=0, general_only=False, host_only=False, tiled_kernel=False, quiet=True, argv=None, **keys):
+    def __init__(self, config=None, device=0, general_only=False, host_only=False, tiled_kernel=False, quiet=True, argv=None,
+                 rank=0, nranks=1, nccl_unique_id=None, **keys):
+        """rank / nranks / nccl_unique_id: one process per GPU (see nccl_unique_id()); per-block arrays and
+        conserved_u then cover the blocks this rank owns, global ids first_block .. first_block + num_blocks."""
         L = load_library()
         items = dict(config or {})
         items.update(keys)
         tokens = list(argv or []) + [f"{k}={_format(v)}" for k, v in items.items()]
         arr = (C.c_char_p * max(1, len(tokens)))(*[t.encode() for t in tokens])
         flags = (FLAG_GENERAL_ONLY if general_only else 0) | (FLAG_HOST_ONLY if host_only else 0) | (FLAG_TILED_KERNEL if tiled_kernel else 0)
-        self._h = L.m3b_solver_create(len(tokens), arr, int(device), flags)
+        uid = bytes(nccl_unique_id) if nccl_unique_id is not None else None
+        self._h = L.m3b_solver_create_distributed(len(tokens), arr, int(device), flags, int(rank), int(nranks), uid)
         if not self._h:
             raise Mara3Error(L.m3b_global_error().decode())
         self.host_only = host_only
+        self.rank, self.nranks = int(rank), int(nranks)
         self.num_blocks = L.m3b_num_blocks(self._h)
+        self.num_global_blocks = L.m3b_num_global_blocks(self._h)
+        self.first_block = L.m3b_first_block(self._h)
+        self.num_local_blocks = L.m3b_num_local_blocks(self._h)
+        self.num_owned_cells = L.m3b_num_owned_cells(self._h)
         self.block_size = L.m3b_block_size(self._h)
         self.num_cells = L.m3b_num_cells(self._h)
         L.m3b_set_quiet(self._h, int(quiet))
@@ -239,6 +261,29 @@ class Solver:
     density_floor = property(lambda s: _lib.m3b_density_floor(s._h))
     num_regular_blocks = property(lambda s: _lib.m3b_num_regular_blocks(s._h))
     kernel_launches = property(lambda s: int(_lib.m3b_kernel_launches(s._h)))
+
+    halo_bytes_per_exchange = property(lambda s: int(_lib.m3b_halo_bytes_per_exchange(s._h)))
+
+    @property
+    def local_to_global(self):
+        a = np.empty(self.num_local_blocks, dtype=np.int32)
+        _lib.m3b_local_to_global(self._h, a.ctypes.data_as(C.POINTER(C.c_int)))
+        return a
+
+    @property
+    def neighbor_table(self):
+        """[owned][3][3] local ids of the same-level neighbours (-1: none), the table the stage kernel reads its halo through."""
+        a = np.empty((self.num_blocks, 3, 3), dtype=np.int32)
+        _lib.m3b_neighbor_table(self._h, a.ctypes.data_as(C.POINTER(C.c_int)))
+        return a
+
+    def halo_plan(self, peer, send):
+        """Ordered (local block, di, dj) strips sent to / received from `peer` before each stage."""
+        n = _lib.m3b_halo_plan_size(self._h, int(peer), int(send))
+        a = np.empty((n, 3), dtype=np.int32)
+        if n:
+            _lib.m3b_halo_plan(self._h, int(peer), int(send), a.ctypes.data_as(C.POINTER(C.c_int)))
+        return a
 
     def config(self, key):
         buf = C.create_string_buffer(1024)
@@ -351,3 +396,12 @@ def orbital_elements(bodies, t):
     if L.m3b_orbital_elements(_dptr(b), float(t), _dptr(out)):
         raise ValueError("mara::compute_orbital_elements (two_body_state does not correspond to a bound orbit)")
     return out
+
+
+def nccl_unique_id():
+    """A fresh 128-byte NCCL unique id (rank 0 creates it and sends it to the other ranks)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.m3b_nccl_unique_id(buf):
+        raise Mara3Error(L.m3b_global_error().decode())
+    return buf.raw

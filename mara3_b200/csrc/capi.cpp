@@ -60,12 +60,23 @@ const char* m3b_global_error(void) { return global_error.c_str(); }
 
 m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, int flags)
 {
+    return m3b_solver_create_distributed(argc, argv, device, flags, 0, 1, nullptr);
+}
+
+int m3b_nccl_unique_id(unsigned char* out128)
+{
+    try { communicator_t::make_unique_id(out128); return M3B_OK; }
+    catch (const std::exception& e) { global_error = e.what(); return M3B_ERROR; }
+}
+
+m3b_solver_t* m3b_solver_create_distributed(int argc, const char* const* argv, int device, int flags, int rank, int nranks, const unsigned char* nccl_unique_id)
+{
     try {
         auto s = std::make_unique<m3b_solver>();
         auto config = config_t::from_argv(argc, argv);
         if (! config.get_string("restart").empty())
             throw std::invalid_argument("restart= is handled by the checkpoint reader, not by m3b_solver_create");
-        s->solver = std::make_unique<binary_solver_t>(config, (flags & 2) ? -1 : device, (flags & 1) != 0, (flags & 4) != 0);
+        s->solver = std::make_unique<binary_solver_t>(config, (flags & 2) ? -1 : device, (flags & 1) != 0, (flags & 4) != 0, rank, nranks, nccl_unique_id);
         return s.release();
     }
     catch (const std::exception& e)
@@ -83,7 +94,50 @@ const char* m3b_last_error(const m3b_solver_t* s)
     return s->error.empty() ? s->solver->last_error().c_str() : s->error.c_str();
 }
 
-int m3b_num_blocks(const m3b_solver_t* s) { return s->solver->solver_data().num_blocks; }
+int m3b_num_blocks(const m3b_solver_t* s) { return s->solver->solver_data().num_owned; }
+int m3b_num_global_blocks(const m3b_solver_t* s) { return s->solver->solver_data().num_blocks; }
+int m3b_first_block(const m3b_solver_t* s) { return s->solver->solver_data().partition.first_owned; }
+int m3b_num_local_blocks(const m3b_solver_t* s) { return s->solver->solver_data().num_local; }
+int64_t m3b_num_owned_cells(const m3b_solver_t* s) { return int64_t(s->solver->solver_data().num_owned_cells()); }
+
+void m3b_local_to_global(const m3b_solver_t* s, int* out)
+{
+    const auto& v = s->solver->solver_data().partition.local_to_global;
+    std::memcpy(out, v.data(), v.size() * sizeof(int));
+}
+
+int m3b_halo_plan_size(const m3b_solver_t* s, int peer, int send)
+{
+    const auto& p = s->solver->solver_data().partition;
+    if (peer < 0 || peer >= p.nranks) return 0;
+    return int((send ? p.send : p.recv)[peer].size());
+}
+
+void m3b_halo_plan(const m3b_solver_t* s, int peer, int send, int* out)
+{
+    const auto& p = s->solver->solver_data().partition;
+    const auto& list = (send ? p.send : p.recv)[peer];
+    for (std::size_t k = 0; k < list.size(); ++k)
+    {
+        out[3 * k + 0] = list[k].block;
+        out[3 * k + 1] = list[k].di;
+        out[3 * k + 2] = list[k].dj;
+    }
+}
+
+void m3b_neighbor_table(const m3b_solver_t* s, int* out)
+{
+    const auto& d = s->solver->solver_data();
+    for (int b = 0; b < d.num_owned; ++b)
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj)
+            {
+                int g = d.tree->same_level_neighbor(d.global_block(b), di, dj);
+                out[b * 9 + (di + 1) * 3 + (dj + 1)] = g < 0 ? -1 : d.partition.global_to_local[g];
+            }
+}
+
+uint64_t m3b_halo_bytes_per_exchange(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().halo_bytes_per_exchange() : 0; }
 int m3b_block_size(const m3b_solver_t* s) { return s->solver->solver_data().block_size; }
 int64_t m3b_num_cells(const m3b_solver_t* s) { return int64_t(s->solver->solver_data().num_cells()); }
 int m3b_num_regular_blocks(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().num_regular_blocks() : -1; }
@@ -91,25 +145,30 @@ int m3b_num_regular_blocks(const m3b_solver_t* s) { return s->solver->has_device
 void m3b_tree_index(const m3b_solver_t* s, int64_t* out)
 {
     const auto& d = s->solver->solver_data();
-    for (int b = 0; b < d.num_blocks; ++b)
+    for (int b = 0; b < d.num_owned; ++b)
     {
-        out[3 * b + 0] = d.tree->index(b).level;
-        out[3 * b + 1] = d.tree->index(b).i;
-        out[3 * b + 2] = d.tree->index(b).j;
+        const auto& idx = d.tree->index(d.global_block(b));
+        out[3 * b + 0] = idx.level;
+        out[3 * b + 1] = idx.i;
+        out[3 * b + 2] = idx.j;
     }
 }
 
 void m3b_vertices(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().vertices(), out); }
 void m3b_cell_centers(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().cell_centers(), out); }
 void m3b_cell_areas(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().cell_areas(), out); }
-void m3b_buffer_rate_field(const m3b_solver_t* s, double* out) { copy_out(s->solver->solver_data().buffer_rate_field, out); }
+void m3b_buffer_rate_field(const m3b_solver_t* s, double* out)
+{
+    const auto& d = s->solver->solver_data();
+    std::memcpy(out, d.buffer_rate_field.data(), d.num_owned_cells() * sizeof(double));     // owned blocks come first
+}
 
 void m3b_initial_conserved_u(const m3b_solver_t* s, double* out)
 {
     // stored field-major [3][B][NN]; the ABI layout is block-major [B][3][NN]
     const auto& d = s->solver->solver_data();
-    const std::size_t NN = d.cells_per_block(), FS = d.num_cells();
-    for (int b = 0; b < d.num_blocks; ++b)
+    const std::size_t NN = d.cells_per_block(), FS = d.num_local_cells();
+    for (int b = 0; b < d.num_owned; ++b)
         for (int q = 0; q < 3; ++q)
             std::memcpy(out + (std::size_t(b) * 3 + q) * NN, &d.initial_conserved_u[q * FS + b * NN], NN * sizeof(double));
 }

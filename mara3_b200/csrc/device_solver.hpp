@@ -26,7 +26,8 @@ namespace m3b
         unsigned int pad;
     };
 
-    struct offender_t { int block, cell; double sigma; };
+    struct offender_t { int block, cell; double sigma; };     // block: local id on the reporting rank
+    class communicator_t;
 
     struct stage_inputs_t
     {
@@ -82,8 +83,20 @@ namespace m3b
         /** binary::maximum_timestep (scheme.cpp:1107-1126) of a state; result in slot.dt_min. */
         void launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot);
 
+        // ---- multi-GPU (no-ops / identities on one rank)
+        void set_communicator(communicator_t* comm);
+        /** Fill the ghost blocks of `field` with the neighbours' edge strips (NCCL send / recv). */
+        void exchange_halos(device_field_t& field);
+        /** All-gather every slot's stage result; after sync(), stage_result() folds the ranks. */
+        void gather_results();
+        /** One double from every rank, in rank order (blocking). */
+        std::vector<double> all_gather_scalar(double value);
+        std::uint64_t halo_bytes_per_exchange() const;
+        unsigned int local_num_negative(int slot) const;
+
         void sync();
-        const stage_result_t& stage_result(int slot) const { return host_results[slot]; }
+        /** Result of the stage launched with this slot, summed / minimised over all ranks. */
+        stage_result_t stage_result(int slot) const;
         std::vector<offender_t> offenders(int slot);
 
         /** Number of kernel launches issued so far (bench.py reports it as gpu_launches). */
@@ -104,7 +117,8 @@ namespace m3b
         struct impl_t;
         std::unique_ptr<impl_t> impl;
         int device_id = 0;
-        int N = 0, B = 0;
+        int N = 0, B = 0, BO = 0;       // block size, blocks stored here, blocks owned (updated) here
+        int num_ranks = 1, rank_ = 0;
         std::size_t cells = 0;
         void* stream_ = nullptr;
         void* own_stream = nullptr;

@@ -22,10 +22,12 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include "comm.hpp"
 #include "device_solver.hpp"
 #include "iso2d_device.cuh"
 
@@ -626,14 +628,40 @@ namespace
         }
     }
 
+    /** One strip / corner of a block in the guard-zone exchange between ranks (partition.hpp). */
+    struct halo_entry_dev_t
+    {
+        int block;              // local block id
+        int i0, ni, j0, nj;     // cells [i0, i0 + ni) x [j0, j0 + nj)
+        int pad;
+        size_t offset;          // first double of this entry in the packed buffer (3 fields x ni x nj)
+    };
+
+    /** Gather (pack = 1) the listed strips of U into the send buffer, or scatter (pack = 0) the receive
+     *  buffer into the ghost blocks: the device side of extend() across GPUs (scheme.cpp:132-142). */
+    __global__ void __launch_bounds__(128) halo_copy(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
+        double* __restrict__ buffer, int pack)
+    {
+        const halo_entry_dev_t e = entries[blockIdx.x];
+        const int cells = e.ni * e.nj;
+
+        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
+        {
+            int q = k / cells, c = k % cells;
+            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
+            size_t u = q * FS + (size_t(e.block) * N + i) * N + j;
+            if (pack) buffer[e.offset + k] = U[u]; else U[u] = buffer[e.offset + k];
+        }
+    }
+
     /** [B][3][NN] (host, block major) <-> [3][B][NN] (device, field major) */
-    __global__ void permute_state(const double* __restrict__ src, double* __restrict__ dst, int B, int NN, int to_device)
+    __global__ void permute_state(const double* __restrict__ src, double* __restrict__ dst, int B, int NN, size_t FS, int to_device)
     {
         size_t n = size_t(B) * 3 * NN;
         for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
         {
             size_t cell = k % NN, q = (k / NN) % 3, b = k / (size_t(3) * NN);
-            size_t field_major = (q * B + b) * NN + cell;
+            size_t field_major = q * FS + b * NN + cell;
             if (to_device) dst[field_major] = src[k]; else dst[k] = src[field_major];
         }
     }
@@ -700,6 +728,21 @@ struct device_solver_t::impl_t
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     size_t fused_smem = 0;
     int sm_count = 148;
+
+    // multi-GPU: guard-zone exchange plan and cross-rank reduction of the stage results
+    communicator_t* comm = nullptr;
+    int num_send_entries = 0, num_recv_entries = 0;
+    halo_entry_dev_t* d_send_entries = nullptr;
+    halo_entry_dev_t* d_recv_entries = nullptr;
+    double* d_send_buffer = nullptr;
+    double* d_recv_buffer = nullptr;
+    std::vector<const double*> send_ptr;
+    std::vector<double*> recv_ptr;
+    std::vector<size_t> send_count, recv_count;
+    stage_result_t* d_results_local = nullptr;      // [num_slots] device copy that NCCL can read
+    stage_result_t* d_results_all = nullptr;        // [nranks][num_slots]
+    stage_result_t* h_results_all = nullptr;        // pinned
+    std::uint64_t halo_bytes_per_exchange = 0;
 };
 
 device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool general_only, bool tiled_kernel) : impl(new impl_t), device_id(device), force_general(general_only)
@@ -713,9 +756,12 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->sm_count = prop.multiProcessorCount;
 
     N = sd.block_size;
-    B = sd.num_blocks;
-    cells = sd.num_cells();
+    B = sd.num_local;               // blocks stored on this rank: owned, then ghosts
+    BO = sd.num_owned;
+    cells = sd.num_local_cells();
     const auto& tree = *sd.tree;
+    const auto& part = sd.partition;
+    auto local = [&part] (int global) { return global < 0 ? -1 : part.global_to_local[global]; };
 
     cudaStream_t s;
     M3B_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -729,21 +775,23 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
 
     for (int b = 0; b < B; ++b)
     {
-        spacing[b] = sd.spacing(tree.index(b).level);
+        const int g = sd.global_block(b);
+        spacing[b] = sd.spacing(tree.index(g).level);
+        if (b >= BO) continue;          // ghost blocks are only read from
         bool regular = true;
 
         for (int side = 0; side < 4; ++side)
         {
-            auto fn = tree.face_neighbor(b, side);
+            auto fn = tree.face_neighbor(g, side);
             auto& d = nbr[size_t(b) * 4 + side];
             d.kind = int(fn.kind);
-            for (int q = 0; q < 4; ++q) d.leaf[q] = fn.leaf[q];
+            for (int q = 0; q < 4; ++q) d.leaf[q] = local(fn.leaf[q]);
             d.bx = fn.bx; d.by = fn.by; d.pad = 0;
         }
         for (int di = -1; di <= 1; ++di)
             for (int dj = -1; dj <= 1; ++dj)
             {
-                int l = tree.same_level_neighbor(b, di, dj);
+                int l = local(tree.same_level_neighbor(g, di, dj));
                 nbr9[size_t(b) * 9 + (di + 1) * 3 + (dj + 1)] = l;
                 if (l < 0) regular = false;
             }
@@ -771,7 +819,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         mark(b);
         for (int side = 0; side < 4; ++side) for (int q = 0; q < 4; ++q) mark(nbr[size_t(b) * 4 + side].leaf[q]);
     }
-    if (force_general) for (int b = 0; b < B; ++b) mark(b);
+    if (force_general) for (int b = 0; b < BO; ++b) mark(b);
     for (int b = 0; b < B; ++b) if (in_gradient_set[b]) { gslot[b] = int(impl->gradient_blocks.size()); impl->gradient_blocks.push_back(b); }
 
     impl->mesh.B = B;
@@ -806,8 +854,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->d_irregular = device_upload(impl->irregular);
     impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
 
-    auto all_blocks = std::vector<int>(B);
-    for (int b = 0; b < B; ++b) all_blocks[b] = b;
+    auto all_blocks = std::vector<int>(BO);
+    for (int b = 0; b < BO; ++b) all_blocks[b] = b;
     impl->owned.push_back(device_upload(all_blocks));
 
     impl->model.softening_radius2   = sd.softening_radius * sd.softening_radius;
@@ -822,15 +870,65 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->model.axisymmetric_cs2    = sd.axisymmetric_cs2;
 
     // ---- scratch
-    size_t max_rows = size_t(B) * std::max(1, (N / std::max(1, impl->tile_x)) * (N / std::max(1, impl->tile_y))) + B;
+    size_t max_rows = size_t(BO) * std::max(1, (N / std::max(1, impl->tile_x)) * (N / std::max(1, impl->tile_y))) + B;
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
-    M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * cells * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * sd.num_owned_cells() * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_fail, num_slots * sizeof(fail_dev_t)));
     // stage results live in mapped pinned host memory: finish_stage writes them straight to the host
     M3B_CUDA(cudaHostAlloc(&host_results, num_slots * sizeof(stage_result_t), cudaHostAllocMapped));
     M3B_CUDA(cudaHostGetDevicePointer(&impl->d_results, host_results, 0));
     M3B_CUDA(cudaMemset(impl->d_fail, 0, num_slots * sizeof(fail_dev_t)));
     M3B_CUDA(cudaMalloc(&impl->d_gradients, std::max<size_t>(1, 6 * impl->mesh.GS) * sizeof(double)));
+
+    // ---- multi-GPU exchange plan (partition.hpp): per peer, the strips in the order both sides agree on
+    if (part.is_distributed())
+    {
+        auto build = [&] (const std::vector<std::vector<halo_region_t>>& lists, std::vector<size_t>& counts, std::vector<size_t>& starts)
+        {
+            auto entries = std::vector<halo_entry_dev_t>();
+            size_t offset = 0;
+            counts.assign(part.nranks, 0);
+            starts.assign(part.nranks, 0);
+            for (int p = 0; p < part.nranks; ++p)
+            {
+                starts[p] = offset;
+                for (const auto& r : lists[p])
+                {
+                    halo_entry_dev_t e;
+                    e.block = r.block;
+                    e.i0 = r.di < 0 ? N - 2 : 0; e.ni = r.di ? 2 : N;
+                    e.j0 = r.dj < 0 ? N - 2 : 0; e.nj = r.dj ? 2 : N;
+                    e.pad = 0;
+                    e.offset = offset;
+                    offset += size_t(3) * e.ni * e.nj;
+                    entries.push_back(e);
+                }
+                counts[p] = offset - starts[p];
+            }
+            return std::make_pair(entries, offset);
+        };
+        auto send_starts = std::vector<size_t>(), recv_starts = std::vector<size_t>();
+        auto [send_entries, send_total] = build(part.send, impl->send_count, send_starts);
+        auto [recv_entries, recv_total] = build(part.recv, impl->recv_count, recv_starts);
+        impl->num_send_entries = int(send_entries.size());
+        impl->num_recv_entries = int(recv_entries.size());
+        impl->d_send_entries = device_upload(send_entries);
+        impl->d_recv_entries = device_upload(recv_entries);
+        M3B_CUDA(cudaMalloc(&impl->d_send_buffer, std::max<size_t>(1, send_total) * sizeof(double)));
+        M3B_CUDA(cudaMalloc(&impl->d_recv_buffer, std::max<size_t>(1, recv_total) * sizeof(double)));
+        for (int p = 0; p < part.nranks; ++p)
+        {
+            impl->send_ptr.push_back(impl->d_send_buffer + send_starts[p]);
+            impl->recv_ptr.push_back(impl->d_recv_buffer + recv_starts[p]);
+        }
+        impl->halo_bytes_per_exchange = send_total * sizeof(double);
+        M3B_CUDA(cudaMalloc(&impl->d_results_local, num_slots * sizeof(stage_result_t)));
+        M3B_CUDA(cudaMalloc(&impl->d_results_all, size_t(part.nranks) * num_slots * sizeof(stage_result_t)));
+        M3B_CUDA(cudaMallocHost(&impl->h_results_all, size_t(part.nranks) * num_slots * sizeof(stage_result_t)));
+        std::memset(impl->h_results_all, 0, size_t(part.nranks) * num_slots * sizeof(stage_result_t));
+    }
+    num_ranks = part.nranks;
+    rank_ = part.rank;
 
     auto set_smem = [&] (auto kernel, size_t bytes)
     {
@@ -862,6 +960,10 @@ device_solver_t::~device_solver_t()
                    (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail})
         if (p) cudaFree(p);
     for (auto p : impl->owned) cudaFree(p);
+    for (auto p : {(void*) impl->d_send_entries, (void*) impl->d_recv_entries, (void*) impl->d_send_buffer, (void*) impl->d_recv_buffer,
+                   (void*) impl->d_results_local, (void*) impl->d_results_all})
+        if (p) cudaFree(p);
+    if (impl->h_results_all) cudaFreeHost(impl->h_results_all);
     for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (host_results) cudaFreeHost(host_results);
     cudaStreamDestroy(cudaStream_t(own_stream));
@@ -877,8 +979,8 @@ void device_solver_t::upload(const double* host, device_field_t& dst)
 {
     auto s = cudaStream_t(stream_);
     M3B_CUDA(cudaSetDevice(device_id));
-    M3B_CUDA(cudaMemcpyAsync(impl->d_staging, host, 3 * cells * sizeof(double), cudaMemcpyHostToDevice, s));
-    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(impl->d_staging, dst.data, B, N * N, 1);
+    M3B_CUDA(cudaMemcpyAsync(impl->d_staging, host, 3 * size_t(BO) * N * N * sizeof(double), cudaMemcpyHostToDevice, s));
+    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(impl->d_staging, dst.data, BO, N * N, cells, 1);
     ++launches;
     M3B_CUDA(cudaGetLastError());
 }
@@ -887,10 +989,10 @@ void device_solver_t::download(const device_field_t& src, double* host)
 {
     auto s = cudaStream_t(stream_);
     M3B_CUDA(cudaSetDevice(device_id));
-    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(src.data, impl->d_staging, B, N * N, 0);
+    permute_state<<<impl->sm_count * 4, 256, 0, s>>>(src.data, impl->d_staging, BO, N * N, cells, 0);
     ++launches;
     M3B_CUDA(cudaGetLastError());
-    M3B_CUDA(cudaMemcpyAsync(host, impl->d_staging, 3 * cells * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaMemcpyAsync(host, impl->d_staging, 3 * size_t(BO) * N * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     M3B_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -955,7 +1057,7 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
 
     const double* un_data = un ? un->data : nullptr;
     int num_fused = force_general ? 0 : int(impl->regular.size());
-    int num_general = force_general ? B : int(impl->irregular.size());
+    int num_general = force_general ? BO : int(impl->irregular.size());
     const int* d_general = force_general ? static_cast<const int*>(impl->owned[0]) : impl->d_irregular;
     int fused_ctas = num_fused * (impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0);
 
@@ -1006,7 +1108,8 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
     W.rows_per_fused_block = num_fused ? fused_ctas / num_fused : 1;
     W.num_fused_blocks = num_fused;
     W.num_general_blocks = num_general;
-    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot, impl->d_results + slot);
+    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot,
+        (num_ranks == 1 ? impl->d_results : impl->d_results_local) + slot);
     ++launches;
     M3B_CUDA(cudaGetLastError());
 }
@@ -1019,11 +1122,90 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     st.time = time;
     st.x1 = bodies.body1.x; st.y1 = bodies.body1.y; st.m1 = bodies.body1.mass;
     st.x2 = bodies.body2.x; st.y2 = bodies.body2.y; st.m2 = bodies.body2.mass;
-    max_timestep_kernel<<<B, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
+    max_timestep_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
     work_inputs_t W = {};
-    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, B, W, impl->d_fail + slot, impl->d_results + slot);
+    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, BO, W, impl->d_fail + slot,
+        (num_ranks == 1 ? impl->d_results : impl->d_results_local) + slot);
     launches += 2;
     M3B_CUDA(cudaGetLastError());
+}
+
+void device_solver_t::set_communicator(communicator_t* comm)
+{
+    impl->comm = comm;
+}
+
+std::uint64_t device_solver_t::halo_bytes_per_exchange() const
+{
+    return impl->halo_bytes_per_exchange;
+}
+
+void device_solver_t::exchange_halos(device_field_t& field)
+{
+    if (num_ranks == 1) return;
+    if (! impl->comm) throw std::logic_error("exchange_halos: no communicator set");
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+
+    if (impl->num_send_entries)
+    {
+        halo_copy<<<impl->num_send_entries, 128, 0, s>>>(impl->d_send_entries, field.data, cells, N, impl->d_send_buffer, 1);
+        ++launches;
+    }
+    impl->comm->exchange(impl->send_ptr, impl->send_count, impl->recv_ptr, impl->recv_count, stream_);
+
+    if (impl->num_recv_entries)
+    {
+        halo_copy<<<impl->num_recv_entries, 128, 0, s>>>(impl->d_recv_entries, field.data, cells, N, impl->d_recv_buffer, 0);
+        ++launches;
+    }
+    M3B_CUDA(cudaGetLastError());
+}
+
+std::vector<double> device_solver_t::all_gather_scalar(double value)
+{
+    auto out = std::vector<double>(num_ranks, value);
+    if (num_ranks == 1) return out;
+    auto s = cudaStream_t(stream_);
+    double* d = reinterpret_cast<double*>(impl->d_results_all);     // scratch: large enough, idle between steps
+    M3B_CUDA(cudaMemcpyAsync(d + num_ranks, &value, sizeof(double), cudaMemcpyHostToDevice, s));
+    impl->comm->all_gather(d + num_ranks, d, 1, stream_);
+    M3B_CUDA(cudaMemcpyAsync(out.data(), d, num_ranks * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaStreamSynchronize(s));
+    return out;
+}
+
+void device_solver_t::gather_results()
+{
+    if (num_ranks == 1) return;
+    auto s = cudaStream_t(stream_);
+    const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
+    impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
+    M3B_CUDA(cudaMemcpyAsync(impl->h_results_all, impl->d_results_all, size_t(num_ranks) * num_slots * sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
+}
+
+stage_result_t device_solver_t::stage_result(int slot) const
+{
+    if (num_ranks == 1) return host_results[slot];
+
+    // fold the ranks in rank order: every rank computes the same bits
+    auto r = stage_result_t();
+    r.dt_min = 1e300;
+    for (int p = 0; p < num_ranks; ++p)
+    {
+        const auto& q = impl->h_results_all[size_t(p) * num_slots + slot];
+        for (int k = 0; k < 16; ++k) r.sums[k] += q.sums[k];
+        r.work[0] += q.work[0];
+        r.work[1] += q.work[1];
+        r.dt_min = std::min(r.dt_min, q.dt_min);
+        r.num_negative += q.num_negative;
+    }
+    return r;
+}
+
+unsigned int device_solver_t::local_num_negative(int slot) const
+{
+    return num_ranks == 1 ? host_results[slot].num_negative : impl->h_results_all[size_t(rank_) * num_slots + slot].num_negative;
 }
 
 void device_solver_t::sync()
@@ -1038,7 +1220,7 @@ std::vector<offender_t> device_solver_t::offenders(int slot)
     M3B_CUDA(cudaSetDevice(device_id));
     M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
     M3B_CUDA(cudaMemcpy(&f, impl->d_fail + slot, sizeof(fail_dev_t), cudaMemcpyDeviceToHost));
-    auto n = std::min<unsigned>(host_results[slot].num_negative, max_offenders);
+    auto n = std::min<unsigned>(local_num_negative(slot), max_offenders);
     auto v = std::vector<offender_t>(f.list, f.list + n);
     std::sort(v.begin(), v.end(), [] (const offender_t& a, const offender_t& b) { return a.block != b.block ? a.block < b.block : a.cell < b.cell; });
     return v;

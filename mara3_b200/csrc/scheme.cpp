@@ -1,4 +1,5 @@
 #include "scheme.hpp"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <iostream>
@@ -51,9 +52,10 @@ void solution_t::set_scalars(const double o[num_scalars])
     orbital_elements = get(33);
 }
 
-binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool general_only, bool tiled_kernel)
+binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool general_only, bool tiled_kernel,
+                                 int rank, int nranks, const unsigned char* nccl_unique_id)
 : config(run_config)
-, data(create_solver_data(run_config))
+, data(create_solver_data(run_config, rank, nranks))
 {
     // set_scheme_globals (scheme.cpp:42-49) rejects threaded <= 0; the key is otherwise unused here
     if (config.get_int("threaded") <= 0)
@@ -63,6 +65,14 @@ binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool ge
     if (device >= 0)
     {
         gpu = std::make_unique<device_solver_t>(data, device, general_only, tiled_kernel);
+        if (nranks > 1)
+        {
+            if (! nccl_unique_id) throw std::invalid_argument("a multi-rank solver needs the NCCL unique id of the job");
+            comm = std::make_unique<communicator_t>(rank, nranks, nccl_unique_id);      // on the device the solver selected
+            gpu->set_communicator(comm.get());
+            auto maxima = gpu->all_gather_scalar(data.max_velocity_local);
+            data.set_max_velocity(*std::max_element(maxima.begin(), maxima.end()));
+        }
         scratch1 = new_field();
         scratch2 = new_field();
     }
@@ -101,6 +111,7 @@ double binary_solver_t::maximum_timestep(const solution_t& s)
 {
     auto bodies = two_body_state(s.orbital_elements, s.time);
     device().launch_max_timestep(*s.conserved_u, s.time, bodies, 7);
+    device().gather_results();
     device().sync();
     return device().stage_result(7).dt_min;
 }
@@ -191,7 +202,7 @@ void binary_solver_t::record_offenders(int slot)
 {
     messages.clear();
     const int N = data.block_size;
-    auto n = device().stage_result(slot).num_negative;
+    auto n = device().local_num_negative(slot);
 
     for (const auto& o : device().offenders(slot))
     {
@@ -217,9 +228,11 @@ status_t binary_solver_t::advance(const solution_t& in, double dt, bool safe_mod
     if (! out.conserved_u || out.conserved_u == in.conserved_u) out.conserved_u = new_field();
 
     auto inputs = stage_inputs(in, dt, safe_mode);
+    device().exchange_halos(*in.conserved_u);       // ghost blocks are a cache of the neighbours' edges
     device().launch_stage(*in.conserved_u, nullptr, *out.conserved_u, inputs, 0);
+    device().gather_results();
     device().sync();
-    const auto& r = device().stage_result(0);
+    const auto r = device().stage_result(0);
     auto st = bookkeeping(in, r, inputs.bodies, dt, out);
     if (st != status_ok) return st;
 
@@ -287,7 +300,9 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     if (data.rk_order == 1)
     {
         inputs1.compute_dt = ! data.fixed_dt && ! live_possible;
+        device().exchange_halos(*A);
         device().launch_stage(*A, nullptr, *scratch1, inputs1, 0);
+        device().gather_results();
         device().sync();
         s1.conserved_u = scratch1;
         auto st = bookkeeping(s, device().stage_result(0), inputs1.bodies, dt, s1);
@@ -302,11 +317,13 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     }
 
     // stage 1: A -> scratch1
+    device().exchange_halos(*A);
     device().launch_stage(*A, nullptr, *scratch1, inputs1, 0);
     s1.conserved_u = scratch1;
 
     if (live_possible)
     {
+        device().gather_results();
         device().sync();
         auto st = bookkeeping(s, device().stage_result(0), inputs1.bodies, dt, s1);
         if (st != status_ok) return st;
@@ -323,7 +340,9 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     inputs2.combine = true;
     inputs2.rk_b0 = 0.5;
     inputs2.compute_dt = ! data.fixed_dt && ! live_possible;
+    device().exchange_halos(*scratch1);
     device().launch_stage(*scratch1, A.get(), *scratch2, inputs2, 1);
+    device().gather_results();
     device().sync();
 
     if (! live_possible)

@@ -11,6 +11,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include "comm.hpp"
 #include "config.hpp"
 #include "device_solver.hpp"
 #include "solver_data.hpp"
@@ -51,7 +52,10 @@ namespace m3b
     class binary_solver_t
     {
     public:
-        binary_solver_t(const config_t& run_config, int device, bool general_only = false, bool tiled_kernel = false);
+        /** rank / nranks / nccl_unique_id: one process per GPU; the leaf blocks are cut into Morton-contiguous
+         *  ranges (partition.hpp).  nccl_unique_id may be null for host-only use (device < 0). */
+        binary_solver_t(const config_t& run_config, int device, bool general_only = false, bool tiled_kernel = false,
+                        int rank = 0, int nranks = 1, const unsigned char* nccl_unique_id = nullptr);
 
         const config_t& run_config() const { return config; }
         const solver_data_t& solver_data() const { return data; }
@@ -89,6 +93,7 @@ namespace m3b
         config_t config;
         solver_data_t data;
         std::unique_ptr<device_solver_t> gpu;
+        std::unique_ptr<communicator_t> comm;
         std::shared_ptr<device_field_t> scratch1, scratch2;
         std::vector<std::string> messages;
         std::string error;

@@ -51,7 +51,7 @@ void m3b::disk_profile(const config_t& run_config, double x, double y, double pr
     disk_model_t(run_config).evaluate(x, y, prim);
 }
 
-solver_data_t m3b::create_solver_data(const config_t& cfg)
+solver_data_t m3b::create_solver_data(const config_t& cfg, int rank, int nranks)
 {
     auto d = solver_data_t();
     d.domain_radius       = cfg.get_double("domain_radius");
@@ -84,33 +84,41 @@ solver_data_t m3b::create_solver_data(const config_t& cfg)
     d.initial_elements.eccentricity = cfg.get_double("eccentricity");
 
     d.tree = std::make_shared<quadtree_t>(d.block_size, cfg.get_int("depth"), cfg.get_double("focus_factor"), cfg.get_double("focus_index"));
+    d.partition = make_partition(*d.tree, rank, nranks);
     d.num_blocks = d.tree->num_leaves();
+    d.num_owned = d.partition.num_owned;
+    d.num_local = d.partition.num_local();
 
-    const int N = d.block_size, B = d.num_blocks;
+    const int N = d.block_size, L = d.num_local;
     const auto disk = disk_model_t(cfg);
     const double buffer_rate = cfg.get_double("buffer_damping_rate");
     double min_dx = std::numeric_limits<double>::infinity(), min_dy = min_dx, max_v = 0.0;
 
-    d.xv.resize(std::size_t(B) * (N + 1));
-    d.yv.resize(std::size_t(B) * (N + 1));
-    d.buffer_rate_field.resize(d.num_cells());
-    d.initial_conserved_u.resize(3 * d.num_cells());
+    // the smallest vertex spacing is a property of the whole tree (solver_data.cpp:41-55); 1-d work per block
+    for (int g = 0; g < d.num_blocks; ++g)
+    {
+        const auto& leaf = d.tree->leaf_node(g);
+        for (int k = 0; k < N; ++k)
+        {
+            min_dx = std::min(min_dx, leaf.xv[k + 1] * d.domain_radius - leaf.xv[k] * d.domain_radius);
+            min_dy = std::min(min_dy, leaf.yv[k + 1] * d.domain_radius - leaf.yv[k] * d.domain_radius);
+        }
+    }
+    d.xv.resize(std::size_t(L) * (N + 1));
+    d.yv.resize(std::size_t(L) * (N + 1));
+    d.buffer_rate_field.resize(d.num_local_cells());
+    d.initial_conserved_u.resize(3 * d.num_local_cells());
 
-    for (int b = 0; b < B; ++b)
+    for (int b = 0; b < L; ++b)
     {
         double* xv = &d.xv[std::size_t(b) * (N + 1)];
         double* yv = &d.yv[std::size_t(b) * (N + 1)];
-        const auto& leaf = d.tree->leaf_node(b);
+        const auto& leaf = d.tree->leaf_node(d.global_block(b));
 
         for (int k = 0; k <= N; ++k)    // (block * domain_radius): subprog_binary.cpp:180-183
         {
             xv[k] = leaf.xv[k] * d.domain_radius;
             yv[k] = leaf.yv[k] * d.domain_radius;
-        }
-        for (int k = 0; k < N; ++k)
-        {
-            min_dx = std::min(min_dx, xv[k + 1] - xv[k]);
-            min_dy = std::min(min_dy, yv[k + 1] - yv[k]);
         }
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j)
@@ -122,27 +130,33 @@ solver_data_t m3b::create_solver_data(const config_t& cfg)
                 disk.evaluate(x, y, prim);
                 std::size_t k = (std::size_t(b) * N + i) * N + j;
 
-                d.initial_conserved_u[0 * d.num_cells() + k] = prim[0];
-                d.initial_conserved_u[1 * d.num_cells() + k] = prim[0] * prim[1];
-                d.initial_conserved_u[2 * d.num_cells() + k] = prim[0] * prim[2];
-                max_v = std::max(max_v, std::sqrt(prim[1] * prim[1] + prim[2] * prim[2]));
+                d.initial_conserved_u[0 * d.num_local_cells() + k] = prim[0];
+                d.initial_conserved_u[1 * d.num_local_cells() + k] = prim[0] * prim[1];
+                d.initial_conserved_u[2 * d.num_local_cells() + k] = prim[0] * prim[2];
+                if (b < d.num_owned) max_v = std::max(max_v, std::sqrt(prim[1] * prim[1] + prim[2] * prim[2]));
 
                 // buffer zone: rate * (1 + tanh(3 (r - domain_radius))) (solver_data.cpp:64-78)
                 double r = std::pow(x * x + y * y, 0.5);
                 d.buffer_rate_field[k] = buffer_rate * (1.0 + std::tanh(3.0 * (r - d.domain_radius)));
             }
     }
-    double min_spacing = std::min(min_dx, min_dy);
-    d.gst_suppr_radius      = cfg.get_double("source_term_softening") * min_spacing;
-    d.recommended_time_step = min_spacing / std::max(1.0, max_v) * d.cfl_number;
+    d.min_spacing = std::min(min_dx, min_dy);
+    d.gst_suppr_radius = cfg.get_double("source_term_softening") * d.min_spacing;
+    d.max_velocity_local = max_v;
+    d.set_max_velocity(max_v);      // exact on one rank; a distributed solver re-does this with the global maximum
     return d;
+}
+
+void solver_data_t::set_max_velocity(double global_max)
+{
+    recommended_time_step = min_spacing / std::max(1.0, global_max) * cfl_number;
 }
 
 std::vector<double> solver_data_t::vertices() const
 {
     const int N = block_size, V = N + 1;
-    auto out = std::vector<double>(std::size_t(num_blocks) * 2 * V * V);
-    for (int b = 0; b < num_blocks; ++b)
+    auto out = std::vector<double>(std::size_t(num_owned) * 2 * V * V);
+    for (int b = 0; b < num_owned; ++b)
         for (int i = 0; i < V; ++i)
             for (int j = 0; j < V; ++j)
             {
@@ -155,8 +169,8 @@ std::vector<double> solver_data_t::vertices() const
 std::vector<double> solver_data_t::cell_centers() const
 {
     const int N = block_size, V = N + 1;
-    auto out = std::vector<double>(std::size_t(num_blocks) * 2 * N * N);
-    for (int b = 0; b < num_blocks; ++b)
+    auto out = std::vector<double>(std::size_t(num_owned) * 2 * N * N);
+    for (int b = 0; b < num_owned; ++b)
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j)
             {
@@ -169,8 +183,8 @@ std::vector<double> solver_data_t::cell_centers() const
 std::vector<double> solver_data_t::cell_areas() const
 {
     const int N = block_size, V = N + 1;
-    auto out = std::vector<double>(std::size_t(num_blocks) * N * N);
-    for (int b = 0; b < num_blocks; ++b)
+    auto out = std::vector<double>(std::size_t(num_owned) * N * N);
+    for (int b = 0; b < num_owned; ++b)
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j)
                 out[(std::size_t(b) * N + i) * N + j] =

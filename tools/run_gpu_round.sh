@@ -1,5 +1,2 @@
-for m in 4 3 2; do
-  echo "== M3B_STRIP_MIN_CTAS=$m"
-  M3B_STRIP_MIN_CTAS=$m python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value', d['value'], 'ms_per_step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'])"
-  M3B_STRIP_MIN_CTAS=$m python bench.py --workload c3 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c3 value', d['value'], 'ms_per_step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'])"
-done
+set -x
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py > gpurun_out/multi_check.log 2>&1; tail -60 gpurun_out/multi_check.log
