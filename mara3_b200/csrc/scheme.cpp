@@ -87,7 +87,23 @@ device_solver_t& binary_solver_t::device()
 
 std::shared_ptr<device_field_t> binary_solver_t::new_field()
 {
-    return std::make_shared<device_field_t>(device().state_doubles(), device().device());
+    // fields released by solutions go back to a small pool instead of cudaFree: value-semantics callers
+    // (m3b_advance_host, clone) would otherwise pay a cudaMalloc + cudaFree per call
+    device_field_t* raw = nullptr;
+    if (! pool->free.empty())
+    {
+        raw = pool->free.back().release();
+        pool->free.pop_back();
+    }
+    else
+    {
+        raw = new device_field_t(device().state_doubles(), device().device());
+    }
+    auto keep = pool;
+    return std::shared_ptr<device_field_t>(raw, [keep] (device_field_t* f)
+    {
+        if (keep->free.size() < 8) keep->free.emplace_back(f); else delete f;
+    });
 }
 
 solution_t binary_solver_t::create_solution()

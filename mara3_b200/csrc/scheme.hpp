@@ -95,6 +95,8 @@ namespace m3b
         std::unique_ptr<device_solver_t> gpu;
         std::unique_ptr<communicator_t> comm;
         std::shared_ptr<device_field_t> scratch1, scratch2;
+        struct field_pool_t { std::vector<std::unique_ptr<device_field_t>> free; };
+        std::shared_ptr<field_pool_t> pool = std::make_shared<field_pool_t>();     // recycled state buffers (cudaMalloc is slow)
         std::vector<std::string> messages;
         std::string error;
         bool quiet = false;
