@@ -208,6 +208,8 @@ def main():
     flush = None if args.no_flush else torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def flush_l2():
+        # the step queued ahead by next_solution must have drained first, or the fill would run beside it
+        torch.cuda.synchronize()
         if flush is not None:
             flush.fill_(1)
             torch.cuda.synchronize()

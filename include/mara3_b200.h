@@ -136,6 +136,10 @@ int         m3b_orbital_elements(const double* bodies10, double t, double* eleme
 int         m3b_num_messages(const m3b_solver_t* s);
 const char* m3b_message(const m3b_solver_t* s, int n);
 void        m3b_set_quiet(m3b_solver_t* s, int quiet);                /* 1: do not print those lines to stdout */
+/* m3b_next_solution queues the FOLLOWING step on the GPU (dt and body positions computed on the device)
+ * before it waits for the current one, so that a stepping loop never idles the GPU on the host.
+ * 0 switches this off (every call then starts and finishes exactly one step). Default 1. */
+void        m3b_set_pipelining(m3b_solver_t* s, int on);
 uint64_t    m3b_kernel_launches(const m3b_solver_t* s);               /* kernels launched so far */
 /* CUDA-event timing of the fused stage kernel on its own stream (for the roofline) */
 void        m3b_stage_timing(m3b_solver_t* s, int enable);

@@ -121,6 +121,7 @@ def load_library():
     L.m3b_message.argtypes = [vp, C.c_int]
     L.m3b_message.restype = C.c_char_p
     L.m3b_set_quiet.argtypes = [vp, C.c_int]
+    L.m3b_set_pipelining.argtypes = [vp, C.c_int]
     L.m3b_kernel_launches.argtypes = [vp]
     L.m3b_kernel_launches.restype = C.c_uint64
     L.m3b_stage_timing.argtypes = [vp, C.c_int]
@@ -361,6 +362,10 @@ class Solver:
     def set_stream(self, cuda_stream):
         """Launch on a caller-owned CUDA stream (an integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
         self._check(_lib.m3b_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_pipelining(self, on):
+        """Queue the following step before waiting for the current one (default on)."""
+        _lib.m3b_set_pipelining(self._h, int(on))
 
     def synchronize(self):
         _lib.m3b_synchronize(self._h)

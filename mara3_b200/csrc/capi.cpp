@@ -213,7 +213,7 @@ void m3b_solution_destroy(m3b_solution_t* u) { delete u; }
 
 int m3b_solution_set_conserved(m3b_solver_t* s, m3b_solution_t* u, const double* host)
 {
-    return guarded(s, [&] { s->solver->device().upload(host, *u->solution.conserved_u); s->solver->device().sync(); return M3B_OK; });
+    return guarded(s, [&] { s->solver->invalidate(); s->solver->device().upload(host, *u->solution.conserved_u); s->solver->device().sync(); return M3B_OK; });
 }
 
 int m3b_solution_get_conserved(m3b_solver_t* s, const m3b_solution_t* u, double* host)
@@ -301,7 +301,7 @@ int m3b_next_solution_host(m3b_solver_t* s, const double* u_in, const double* sc
         u.conserved_u = solver.new_field();
         u.set_scalars(scalars_in);
         solver.device().upload(u_in, *u.conserved_u);
-        auto st = solver.next_solution(u, dt_used, &fb);
+        auto st = solver.next_solution(u, dt_used, &fb, /*speculate*/ false);   // a one-shot call: nothing to queue ahead
         if (fell_back) *fell_back = fb;
         if (st == status_ok)
         {
@@ -339,6 +339,7 @@ int m3b_orbital_elements(const double* b, double t, double* out)
 int m3b_num_messages(const m3b_solver_t* s) { return int(s->solver->last_messages().size()); }
 const char* m3b_message(const m3b_solver_t* s, int n) { return s->solver->last_messages().at(n).c_str(); }
 void m3b_set_quiet(m3b_solver_t* s, int quiet) { s->solver->set_quiet(quiet != 0); }
+void m3b_set_pipelining(m3b_solver_t* s, int on) { try { s->solver->set_pipelining(on != 0); } catch (...) {} }
 uint64_t m3b_kernel_launches(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().launch_count() : 0; }
 void m3b_stage_timing(m3b_solver_t* s, int enable) { if (s->solver->has_device()) s->solver->device().set_stage_timing(enable != 0); }
 

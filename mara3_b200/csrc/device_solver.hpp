@@ -80,6 +80,20 @@ namespace m3b
          */
         void launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot);
 
+        /**
+         * A whole RK2 step queued without host involvement: exchange, stage 1 (in -> scratch), exchange,
+         * stage 2 (scratch, in -> out, RK combination and CFL estimate fused), result folding, and the
+         * stage inputs of the FOLLOWING step computed on the device (prepare_next).  The inputs of THIS
+         * step must already be in the device slots of `parity` (upload_step_inputs, or the previous
+         * step's prepare_next).  Only valid while the binary's orbital elements are constant.
+         */
+        void launch_step_async(device_field_t& in, device_field_t& scratch, device_field_t& out, int parity,
+                               const elements_t& elements, double cfl_number, double recommended_time_step, double theta, bool fixed_dt);
+        void upload_step_inputs(int parity, const stage_inputs_t& first, const stage_inputs_t& second);
+        void wait_step(int parity);
+        stage_result_t async_result(int parity, int stage) const;
+        int async_slot(int parity, int stage) const;
+
         /** binary::maximum_timestep (scheme.cpp:1107-1126) of a state; result in slot.dt_min. */
         void launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot);
 
@@ -111,9 +125,14 @@ namespace m3b
         void collect_stage_timing();
 
         static constexpr int num_slots = 8;
+        static constexpr int first_async_slot = 2;      // slots 2..5: two steps in flight x two stages
         static constexpr int max_offenders = 64;
 
     private:
+        void upload_stage(const stage_inputs_t& inputs, int slot);
+        void launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot);
+        stage_result_t* result_target(int slot);
+        void launch_finish(const double* block_rows, int num_rows, int slot);
         struct impl_t;
         std::unique_ptr<impl_t> impl;
         int device_id = 0;

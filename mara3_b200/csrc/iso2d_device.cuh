@@ -38,6 +38,7 @@ struct stage_t
     double theta;       // plm_theta, or 0 in safe mode (scheme.cpp:792)
     double x1, y1, m1;  // body 1 position, mass
     double x2, y2, m2;  // body 2
+    double vx1, vy1, vx2, vy2;  // body velocities (work integral, scheme.cpp:363-374)
     double rk_b0;       // if combine: out = Un * b0 + updated * (1 - b0)   (subprog_binary.cpp:272-275)
     int combine;
     int compute_dt;     // also reduce spacing / max wavespeed of the OUTPUT state (scheme.cpp:1107-1126)

@@ -41,7 +41,9 @@ namespace
 {
     constexpr int THREADS = 256;
     constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
-    constexpr int FINISH_THREADS = 1024;
+    constexpr int FINISH_THREADS = 256;
+    constexpr int FINISH_ROWS_PER_CTA = 32;     // at most 4 rows per thread group; <= 2 * FINISH_THREADS / ROW CTAs are folded at the end
+    constexpr int stage_ring_size = 64;
 
     struct face_nbr_dev_t
     {
@@ -128,6 +130,37 @@ namespace
     }
 
 
+    /**
+     * The last tile CTA of a block to finish folds the block's tile rows, in tile order (so the result
+     * does not depend on which CTA came last), into one row per block: the reference's per-block
+     * source_term_total_t (scheme.cpp:390-408).  Standard threadfence + ticket pattern.
+     */
+    __device__ void fold_tiles_of_block(const double* tile_rows, double* __restrict__ block_rows, int* counters, int ordinal, int tiles_per_block)
+    {
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(&counters[ordinal], 1) == tiles_per_block - 1;
+        __syncthreads();
+        if (! is_last) return;
+        __threadfence();
+
+        if (threadIdx.x <= NUM_SUMS)
+        {
+            const int k = threadIdx.x;
+            const double* rows = tile_rows + size_t(ordinal) * tiles_per_block * ROW + k;
+            double v = k == NUM_SUMS ? 1e300 : 0.0;
+            for (int t = 0; t < tiles_per_block; ++t)
+            {
+                double p = __ldcg(rows + size_t(t) * ROW);
+                v = k == NUM_SUMS ? dmin(v, p) : v + p;
+            }
+            block_rows[size_t(ordinal) * ROW + k] = v;
+        }
+        if (threadIdx.x == 0) counters[ordinal] = 0;       // re-armed for the next launch
+    }
+
+
     // =======================================================================
     // Fused stage kernel for regular blocks
     // =======================================================================
@@ -147,13 +180,14 @@ namespace
 
     template<int TX, int TY>
     __global__ void __launch_bounds__(THREADS, 2) stage_fused(
-        mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ regular_list,
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* __restrict__ partials, fail_dev_t* fail)
+        double* partials, double* __restrict__ block_rows, int* counters, fail_dev_t* fail)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
 
+        const stage_t S = *stage_ptr;
         const int N = mesh.N;
         const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
         const int b  = regular_list[blockIdx.x / tiles_per_block];
@@ -268,6 +302,7 @@ namespace
             if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
         }
         reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
+        fold_tiles_of_block(partials, block_rows, counters, blockIdx.x / tiles_per_block, tiles_per_block);
     }
 
 
@@ -370,9 +405,10 @@ namespace
 
     /** P2 + P3 for the listed blocks: physical PLM gradients at the block's own spacing. */
     __global__ void __launch_bounds__(THREADS) general_gradients(
-        mesh_dev_t mesh, const stage_t S, const int* __restrict__ list,
+        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
         const double* __restrict__ Uin, double* __restrict__ G)
     {
+        const stage_t S = *stage_ptr;
         const int N = mesh.N, b = list[blockIdx.x];
         const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
         const size_t base = size_t(mesh.gslot[b]) * N * N;
@@ -445,11 +481,12 @@ namespace
 
     /** P6-P8 + P11 for the listed blocks, one CTA per block. */
     __global__ void __launch_bounds__(THREADS) general_update(
-        mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ list,
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
         const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
         double* __restrict__ partials, fail_dev_t* fail)
     {
         __shared__ double red[(THREADS / 32) * (NUM_SUMS + 1)];
+        const stage_t S = *stage_ptr;
         const int N = mesh.N, b = list[blockIdx.x];
         const size_t FS = mesh.FS;
         const double* xv = mesh.xv + size_t(b) * (N + 1);
@@ -506,9 +543,10 @@ namespace
 
     /** maximum_timestep (scheme.cpp:1107-1126): per-CTA min of spacing / max wavespeed. */
     __global__ void __launch_bounds__(THREADS) max_timestep_kernel(
-        mesh_dev_t mesh, model_t model, const stage_t S, const double* __restrict__ U, double* __restrict__ partials)
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const double* __restrict__ U, double* __restrict__ partials)
     {
         __shared__ double red[THREADS / 32];
+        const stage_t S = *stage_ptr;
         const int N = mesh.N, b = blockIdx.x;
         const double* xv = mesh.xv + size_t(b) * (N + 1);
         const double* yv = mesh.yv + size_t(b) * (N + 1);
@@ -536,68 +574,50 @@ namespace
         }
     }
 
-    /** Inputs of the per-block `work` integral (scheme.cpp:363-374, 407-408). */
-    struct work_inputs_t
-    {
-        double mass[2], vx[2], vy[2];   // the two bodies at the stage time
-        double dt;
-        int rows_per_fused_block;       // CTA rows per block written by the fused kernel
-        int num_fused_blocks;
-        int num_general_blocks;         // one row each, after the fused rows
-    };
-
     /**
      * Fold the per-CTA rows in a fixed order (deterministic) and publish the stage result.
      * The reference evaluates the work done on each body PER BLOCK from that block's accreted
      * mass and momentum -- a non-linear function -- and then sums over blocks
      * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
      */
-    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* __restrict__ partials, int num_rows, work_inputs_t W,
-        fail_dev_t* fail, stage_result_t* result)
+    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* rows, int num_rows, int rows_per_cta,
+        double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr, fail_dev_t* fail, stage_result_t* result)
     {
-        __shared__ double red[FINISH_THREADS];
+        // one row per block (rows); CTA c folds rows [c * rows_per_cta, ...) and the block-wise work integrals,
+        // the last CTA to finish folds the CTA rows in CTA order
+        __shared__ double red[FINISH_THREADS / 32][32];
         __shared__ double wred[2][FINISH_THREADS];
+        __shared__ int is_last;
+        const stage_t S = *stage_ptr;
+        const double body_mass[2] = {S.m1, S.m2}, body_vx[2] = {S.vx1, S.vx2}, body_vy[2] = {S.vy1, S.vy2};
         const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = FINISH_THREADS / 32;
         const bool is_min = col == NUM_SUMS;
-        double v = is_min ? 1e300 : 0.0;
+        const int r0 = blockIdx.x * rows_per_cta, r1 = min(num_rows, r0 + rows_per_cta);
 
+        double v = is_min ? 1e300 : 0.0;
         if (col <= NUM_SUMS)
         {
-            int r = grp;
-            for (; r + 3 * ngrp < num_rows; r += 4 * ngrp)      // four rows in flight per thread
+            for (int r = r0 + grp; r < r1; r += ngrp)          // rows_per_cta <= 4 * ngrp: at most 4 independent loads
             {
-                double p0 = partials[size_t(r) * ROW + col], p1 = partials[size_t(r + ngrp) * ROW + col];
-                double p2 = partials[size_t(r + 2 * ngrp) * ROW + col], p3 = partials[size_t(r + 3 * ngrp) * ROW + col];
-                v = is_min ? dmin(dmin(v, p0), dmin(dmin(p1, p2), p3)) : (((v + p0) + p1) + p2) + p3;
-            }
-            for (; r < num_rows; r += ngrp)
-            {
-                double p = partials[size_t(r) * ROW + col];
+                double p = __ldcg(rows + size_t(r) * ROW + col);
                 v = is_min ? dmin(v, p) : v + p;
             }
         }
-        red[threadIdx.x] = v;
+        red[grp][col] = v;
 
         double work[2] = {0.0, 0.0};
-        for (int blk = threadIdx.x; blk < W.num_fused_blocks + W.num_general_blocks; blk += FINISH_THREADS)
+        for (int r = r0 + threadIdx.x; r < r1; r += FINISH_THREADS)
         {
-            const bool fused = blk < W.num_fused_blocks;
-            const int r0 = fused ? blk * W.rows_per_fused_block : W.num_fused_blocks * W.rows_per_fused_block + (blk - W.num_fused_blocks);
-            const int nr = fused ? W.rows_per_fused_block : 1;
-
+            #pragma unroll
             for (int k = 0; k < 2; ++k)
             {
-                double dm = 0.0, dpx = 0.0, dpy = 0.0;
-                for (int r = r0; r < r0 + nr; ++r)
-                {
-                    dm  += partials[size_t(r) * ROW + ACC_MASS + k];
-                    dpx += partials[size_t(r) * ROW + ACC_PX + k];
-                    dpy += partials[size_t(r) * ROW + ACC_PY + k];
-                }
+                double dm  = __ldcg(rows + size_t(r) * ROW + ACC_MASS + k);
+                double dpx = __ldcg(rows + size_t(r) * ROW + ACC_PX + k);
+                double dpy = __ldcg(rows + size_t(r) * ROW + ACC_PY + k);
                 if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
                 {
-                    double M0 = W.mass[k], px0 = W.vx[k] * M0, py0 = W.vy[k] * M0;
-                    double M1 = M0 + dm * W.dt, px1 = px0 + dpx * W.dt, py1 = py0 + dpy * W.dt;
+                    double M0 = body_mass[k], px0 = body_vx[k] * M0, py0 = body_vy[k] * M0;
+                    double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
                     work[k] += ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
                 }
             }
@@ -606,26 +626,104 @@ namespace
         wred[1][threadIdx.x] = work[1];
         __syncthreads();
 
+        double* mine = cta_rows + size_t(blockIdx.x) * ROW;
         if (grp == 0 && col <= NUM_SUMS)
         {
             for (int g = 1; g < ngrp; ++g)
             {
-                double p = red[g * 32 + col];
+                double p = red[g][col];
                 v = is_min ? dmin(v, p) : v + p;
             }
-            if (col < NUM_SUMS) result->sums[col] = v; else result->dt_min = v;
+            mine[col] = v;
         }
         if (grp == 1 && col < 2)
         {
             double w = 0.0;
-            for (int t = 0; t < FINISH_THREADS; ++t) w += wred[col][t];
-            result->work[col] = w;
+            const int n = min(FINISH_THREADS, r1 - r0);
+            for (int t = 0; t < n; ++t) w += wred[col][t];
+            mine[NUM_SUMS + 1 + col] = w;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
+        __syncthreads();
+        if (! is_last) return;
+        __threadfence();
+
+        // all CTA rows at once into shared memory, then a fixed-order fold
+        double* all = &wred[0][0];              // gridDim.x * ROW <= 2 * FINISH_THREADS doubles
+        for (int k = threadIdx.x; k < int(gridDim.x) * ROW; k += FINISH_THREADS) all[k] = __ldcg(cta_rows + k);
+        __syncthreads();
+        if (threadIdx.x < ROW - 1)
+        {
+            const int k = threadIdx.x;
+            double f = k == NUM_SUMS ? 1e300 : 0.0;
+            for (int c = 0; c < int(gridDim.x); ++c) f = k == NUM_SUMS ? dmin(f, all[c * ROW + k]) : f + all[c * ROW + k];
+            if (k < NUM_SUMS) result->sums[k] = f;
+            else if (k == NUM_SUMS) result->dt_min = f;
+            else result->work[k - NUM_SUMS - 1] = f;
         }
         if (threadIdx.x == 64)
         {
             result->num_negative = fail->count;
+            fail->pad = fail->count;    // how many entries of the list belong to this launch
             fail->count = 0;            // ready for the next launch that uses this slot
+            *ticket = 0;
         }
+    }
+
+    /** What prepare_next needs to set up the following step without the host (constant while the binary is not live). */
+    struct step_config_t
+    {
+        elements_t elements;
+        double cfl_number, recommended_time_step, theta;
+        int fixed_dt;
+    };
+
+    __device__ void fill_stage(stage_t& st, double time, double dt, double theta, const two_body_t& b, double rk_b0, int combine, int compute_dt)
+    {
+        st.time = time; st.dt = dt; st.theta = theta;
+        st.x1 = b.body1.x; st.y1 = b.body1.y; st.m1 = b.body1.mass; st.vx1 = b.body1.vx; st.vy1 = b.body1.vy;
+        st.x2 = b.body2.x; st.y2 = b.body2.y; st.m2 = b.body2.mass; st.vx2 = b.body2.vx; st.vy2 = b.body2.vy;
+        st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
+    }
+
+    /**
+     * End of an RK2 step, on the device: fold the two stage results over the ranks (rank order, so every
+     * rank gets the same bits), publish them to the host, and write the stage inputs of the NEXT step --
+     * dt = cfl * min(spacing / wavespeed) (subprog_binary.cpp:281-283), time = t/2 + ((t + dt) + dt)/2
+     * (scheme.cpp:1036, 1055), body positions from compute_two_body_state (scheme.cpp:814) -- so that
+     * the host can queue the next step without waiting for this one.
+     */
+    __global__ void prepare_next(const stage_result_t* __restrict__ gathered, int nranks, int slot_stride, int slot_a, int slot_b,
+        step_config_t cfg, const stage_t* __restrict__ current, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
+    {
+        // two threads: one per stage result / per stage of the next step
+        __shared__ double dt_min_b;
+        const int k = threadIdx.x;
+        if (k >= 2) return;
+        const int slot = k == 0 ? slot_a : slot_b;
+        stage_result_t r = stage_result_t();
+        r.dt_min = 1e300;
+
+        for (int p = 0; p < nranks; ++p)
+        {
+            const stage_result_t& q = gathered[size_t(p) * slot_stride + slot];
+            for (int c = 0; c < 16; ++c) r.sums[c] += q.sums[c];
+            r.work[0] += q.work[0];
+            r.work[1] += q.work[1];
+            r.dt_min = dmin(r.dt_min, q.dt_min);
+            r.num_negative += q.num_negative;
+        }
+        host_results[slot] = r;
+        if (k == 1) dt_min_b = r.dt_min;
+        __syncwarp(0x3);
+
+        const double t = current[slot_a].time, dt = current[slot_a].dt;
+        const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
+        const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
+        if (k == 0) fill_stage(*next_a, t_next, dt_next, cfg.theta, two_body_state(cfg.elements, t_next), 0.0, 0, 0);
+        else        fill_stage(*next_b, t_next + dt_next, dt_next, cfg.theta, two_body_state(cfg.elements, t_next + dt_next), 0.5, 1, ! cfg.fixed_dt);
     }
 
     /** One strip / corner of a block in the guard-zone exchange between ranks (partition.hpp). */
@@ -726,8 +824,21 @@ struct device_solver_t::impl_t
     stage_result_t* d_results = nullptr;    // [num_slots]
     std::vector<void*> owned;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    std::vector<cudaEvent_t> event_pool;
     size_t fused_smem = 0;
     int sm_count = 148;
+
+    // stage inputs live in device memory (one per result slot): uploaded by the host, or written by prepare_next
+    stage_t* d_stage = nullptr;                 // [num_slots]
+    stage_t* h_stage_ring = nullptr;            // pinned staging ring for the uploads
+    int ring_next = 0;
+    double* d_partials2 = nullptr;              // second row buffer: the two stages of a step stay separate
+    double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
+    double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows
+    int* d_counters = nullptr;                  // per-block tile tickets, then the finish ticket
+    int finish_ctas_max = 0;
+    size_t partial_rows = 0;
+    cudaEvent_t step_done[2] = {nullptr, nullptr};
 
     // multi-GPU: guard-zone exchange plan and cross-rank reduction of the stage results
     communicator_t* comm = nullptr;
@@ -872,6 +983,18 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     // ---- scratch
     size_t max_rows = size_t(BO) * std::max(1, (N / std::max(1, impl->tile_x)) * (N / std::max(1, impl->tile_y))) + B;
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_partials2, max_rows * ROW * sizeof(double)));
+    for (auto& p : impl->d_block_rows) M3B_CUDA(cudaMalloc(&p, size_t(BO + 1) * ROW * sizeof(double)));
+    impl->finish_ctas_max = 2 * FINISH_THREADS / ROW;
+    M3B_CUDA(cudaMalloc(&impl->d_cta_rows, size_t(impl->finish_ctas_max) * ROW * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_counters, size_t(BO + 2) * sizeof(int)));
+    M3B_CUDA(cudaMemset(impl->d_counters, 0, size_t(BO + 2) * sizeof(int)));
+    impl->partial_rows = max_rows;
+    M3B_CUDA(cudaMalloc(&impl->d_stage, num_slots * sizeof(stage_t)));
+    M3B_CUDA(cudaMallocHost(&impl->h_stage_ring, stage_ring_size * sizeof(stage_t)));
+    M3B_CUDA(cudaMalloc(&impl->d_results_local, num_slots * sizeof(stage_result_t)));
+    M3B_CUDA(cudaMemset(impl->d_results_local, 0, num_slots * sizeof(stage_result_t)));
+    for (auto& e : impl->step_done) M3B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * sd.num_owned_cells() * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_fail, num_slots * sizeof(fail_dev_t)));
     // stage results live in mapped pinned host memory: finish_stage writes them straight to the host
@@ -922,7 +1045,6 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             impl->recv_ptr.push_back(impl->d_recv_buffer + recv_starts[p]);
         }
         impl->halo_bytes_per_exchange = send_total * sizeof(double);
-        M3B_CUDA(cudaMalloc(&impl->d_results_local, num_slots * sizeof(stage_result_t)));
         M3B_CUDA(cudaMalloc(&impl->d_results_all, size_t(part.nranks) * num_slots * sizeof(stage_result_t)));
         M3B_CUDA(cudaMallocHost(&impl->h_results_all, size_t(part.nranks) * num_slots * sizeof(stage_result_t)));
         std::memset(impl->h_results_all, 0, size_t(part.nranks) * num_slots * sizeof(stage_result_t));
@@ -964,7 +1086,12 @@ device_solver_t::~device_solver_t()
                    (void*) impl->d_results_local, (void*) impl->d_results_all})
         if (p) cudaFree(p);
     if (impl->h_results_all) cudaFreeHost(impl->h_results_all);
+    if (impl->h_stage_ring) cudaFreeHost(impl->h_stage_ring);
+    for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
+                   (void*) impl->d_cta_rows, (void*) impl->d_counters}) if (p) cudaFree(p);
+    for (auto e : impl->step_done) if (e) cudaEventDestroy(e);
     for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto e : impl->event_pool) cudaEventDestroy(e);
     if (host_results) cudaFreeHost(host_results);
     cudaStreamDestroy(cudaStream_t(own_stream));
 }
@@ -1018,6 +1145,10 @@ void device_solver_t::combine(const device_field_t& a, double wa, const device_f
 
 void device_solver_t::set_stage_timing(bool on)
 {
+    if (on && impl->event_pool.size() < 512)
+    {
+        for (int k = 0; k < 512; ++k) { cudaEvent_t e; M3B_CUDA(cudaEventCreate(&e)); impl->event_pool.push_back(e); }
+    }
     stage_timing = on;
 }
 
@@ -1030,31 +1161,39 @@ void device_solver_t::collect_stage_timing()
         M3B_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
         stage_ms_total += ms;
         ++stage_timed_launches;
-        cudaEventDestroy(ev.first);
-        cudaEventDestroy(ev.second);
+        impl->event_pool.push_back(ev.first);
+        impl->event_pool.push_back(ev.second);
     }
     impl->timing_events.clear();
 }
 
-void device_solver_t::launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot)
+void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
 {
     auto s = cudaStream_t(stream_);
-    M3B_CUDA(cudaSetDevice(device_id));
-
-    if (inputs.combine && ! un) throw std::invalid_argument("launch_stage: combine requires the step-start state");
-    if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
-
-    stage_t st;
+    stage_t& st = impl->h_stage_ring[impl->ring_next];      // the ring is far longer than the launches in flight
+    impl->ring_next = (impl->ring_next + 1) % stage_ring_size;
     st.time = inputs.time;
     st.dt = inputs.dt;
     st.theta = inputs.theta;
     st.x1 = inputs.bodies.body1.x; st.y1 = inputs.bodies.body1.y; st.m1 = inputs.bodies.body1.mass;
     st.x2 = inputs.bodies.body2.x; st.y2 = inputs.bodies.body2.y; st.m2 = inputs.bodies.body2.mass;
+    st.vx1 = inputs.bodies.body1.vx; st.vy1 = inputs.bodies.body1.vy;
+    st.vx2 = inputs.bodies.body2.vx; st.vy2 = inputs.bodies.body2.vy;
     st.rk_b0 = inputs.rk_b0;
     st.combine = inputs.combine;
     st.compute_dt = inputs.compute_dt;
+    M3B_CUDA(cudaMemcpyAsync(impl->d_stage + slot, &st, sizeof(stage_t), cudaMemcpyHostToDevice, s));
+}
 
+/** The stage kernels + finish_stage for the inputs already in d_stage[slot]. */
+void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot)
+{
+    auto s = cudaStream_t(stream_);
+    if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
 
+    const stage_t* st = impl->d_stage + slot;
+    double* partials = (slot & 1) ? impl->d_partials2 : impl->d_partials;
+    double* block_rows = impl->d_block_rows[slot & 1];
     const double* un_data = un ? un->data : nullptr;
     int num_fused = force_general ? 0 : int(impl->regular.size());
     int num_general = force_general ? BO : int(impl->irregular.size());
@@ -1066,17 +1205,22 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (stage_timing)
         {
-            M3B_CUDA(cudaEventCreate(&e0));
-            M3B_CUDA(cudaEventCreate(&e1));
+            // events come from a pool: creating them here would delay the launches behind this one
+            if (impl->event_pool.size() < 2)
+            {
+                for (int k = 0; k < 64; ++k) { cudaEvent_t e; M3B_CUDA(cudaEventCreate(&e)); impl->event_pool.push_back(e); }
+            }
+            e0 = impl->event_pool.back(); impl->event_pool.pop_back();
+            e1 = impl->event_pool.back(); impl->event_pool.pop_back();
             M3B_CUDA(cudaEventRecord(e0, s));
         }
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<fused_ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
-            impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot)
+            impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, partials, block_rows, impl->d_counters, impl->d_fail + slot)
         if (impl->strip)
         {
             auto kernel = impl->strip_min_ctas == 2 ? stage_strip<2> : (impl->strip_min_ctas == 3 ? stage_strip<3> : stage_strip<4>);
             kernel<<<fused_ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_regular, impl->d_tile_flags,
-                in.data, un_data, out.data, impl->d_partials, impl->d_fail + slot);
+                in.data, un_data, out.data, partials, block_rows, impl->d_counters, impl->d_fail + slot);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
@@ -1097,37 +1241,110 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
         int ng = int(impl->gradient_blocks.size());
         general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
         general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
-            in.data, impl->d_gradients, un_data, out.data, impl->d_partials + size_t(fused_ctas) * ROW, impl->d_fail + slot);
+            in.data, impl->d_gradients, un_data, out.data, block_rows + size_t(num_fused) * ROW, impl->d_fail + slot);
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
-    work_inputs_t W;
-    W.mass[0] = inputs.bodies.body1.mass; W.vx[0] = inputs.bodies.body1.vx; W.vy[0] = inputs.bodies.body1.vy;
-    W.mass[1] = inputs.bodies.body2.mass; W.vx[1] = inputs.bodies.body2.vx; W.vy[1] = inputs.bodies.body2.vy;
-    W.dt = inputs.dt;
-    W.rows_per_fused_block = num_fused ? fused_ctas / num_fused : 1;
-    W.num_fused_blocks = num_fused;
-    W.num_general_blocks = num_general;
-    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, fused_ctas + num_general, W, impl->d_fail + slot,
-        (num_ranks == 1 ? impl->d_results : impl->d_results_local) + slot);
+    launch_finish(block_rows, num_fused + num_general, slot);
+    M3B_CUDA(cudaGetLastError());
+}
+
+void device_solver_t::launch_finish(const double* block_rows, int num_rows, int slot)
+{
+    // enough CTAs to keep every load independent, few enough for the final fold to fit shared memory
+    int rows_per_cta = FINISH_ROWS_PER_CTA;
+    while ((num_rows + rows_per_cta - 1) / rows_per_cta > impl->finish_ctas_max) rows_per_cta *= 2;
+    int ctas = std::max(1, (num_rows + rows_per_cta - 1) / rows_per_cta);
+    finish_stage<<<ctas, FINISH_THREADS, 0, cudaStream_t(stream_)>>>(block_rows, num_rows, rows_per_cta, impl->d_cta_rows,
+        impl->d_counters + BO + 1, impl->d_stage + slot, impl->d_fail + slot, result_target(slot));
     ++launches;
     M3B_CUDA(cudaGetLastError());
+}
+
+/** Where finish_stage writes: host-mapped memory for synchronous single-rank use, device memory when the
+ *  result still has to be folded over ranks or consumed by prepare_next. */
+stage_result_t* device_solver_t::result_target(int slot)
+{
+    bool on_device = num_ranks > 1 || (slot >= first_async_slot && slot < first_async_slot + 4);
+    return (on_device ? impl->d_results_local : impl->d_results) + slot;
+}
+
+void device_solver_t::launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    if (inputs.combine && ! un) throw std::invalid_argument("launch_stage: combine requires the step-start state");
+    upload_stage(inputs, slot);
+    launch_stage_kernels(in, un, out, slot);
+}
+
+void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scratch, device_field_t& out, int parity,
+                                        const elements_t& elements, double cfl_number, double recommended_time_step, double theta, bool fixed_dt)
+{
+    auto s = cudaStream_t(stream_);
+    M3B_CUDA(cudaSetDevice(device_id));
+    const int a = first_async_slot + 2 * parity, b = a + 1;
+    const int na = first_async_slot + 2 * (1 - parity), nb = na + 1;
+
+    exchange_halos(in);
+    launch_stage_kernels(in, nullptr, scratch, a);
+    exchange_halos(scratch);
+    launch_stage_kernels(scratch, &in, out, b);
+
+    const stage_result_t* gathered = impl->d_results_local;
+    if (num_ranks > 1)
+    {
+        const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
+        impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
+        gathered = impl->d_results_all;
+    }
+    step_config_t cfg;
+    cfg.elements = elements;
+    cfg.cfl_number = cfl_number;
+    cfg.recommended_time_step = recommended_time_step;
+    cfg.theta = theta;
+    cfg.fixed_dt = fixed_dt;
+    prepare_next<<<1, 32, 0, s>>>(gathered, num_ranks, num_slots, a, b, cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);
+    ++launches;
+    M3B_CUDA(cudaGetLastError());
+    M3B_CUDA(cudaEventRecord(impl->step_done[parity], s));
+}
+
+void device_solver_t::upload_step_inputs(int parity, const stage_inputs_t& first, const stage_inputs_t& second)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    upload_stage(first, first_async_slot + 2 * parity);
+    upload_stage(second, first_async_slot + 2 * parity + 1);
+}
+
+void device_solver_t::wait_step(int parity)
+{
+    M3B_CUDA(cudaEventSynchronize(impl->step_done[parity]));
+}
+
+stage_result_t device_solver_t::async_result(int parity, int stage) const
+{
+    return host_results[first_async_slot + 2 * parity + stage];     // already folded over ranks by prepare_next
+}
+
+int device_solver_t::async_slot(int parity, int stage) const
+{
+    return first_async_slot + 2 * parity + stage;
 }
 
 void device_solver_t::launch_max_timestep(const device_field_t& in, double time, const two_body_t& bodies, int slot)
 {
     auto s = cudaStream_t(stream_);
     M3B_CUDA(cudaSetDevice(device_id));
-    stage_t st = stage_t();
-    st.time = time;
-    st.x1 = bodies.body1.x; st.y1 = bodies.body1.y; st.m1 = bodies.body1.mass;
-    st.x2 = bodies.body2.x; st.y2 = bodies.body2.y; st.m2 = bodies.body2.mass;
-    max_timestep_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, impl->model, st, in.data, impl->d_partials);
-    work_inputs_t W = {};
-    finish_stage<<<1, FINISH_THREADS, 0, s>>>(impl->d_partials, BO, W, impl->d_fail + slot,
-        (num_ranks == 1 ? impl->d_results : impl->d_results_local) + slot);
-    launches += 2;
-    M3B_CUDA(cudaGetLastError());
+    auto inputs = stage_inputs_t();
+    inputs.time = time;
+    inputs.dt = 0.0;
+    inputs.theta = 0.0;
+    inputs.bodies = bodies;
+    upload_stage(inputs, slot);
+    double* block_rows = impl->d_block_rows[slot & 1];
+    max_timestep_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, impl->model, impl->d_stage + slot, in.data, block_rows);
+    ++launches;
+    launch_finish(block_rows, BO, slot);
 }
 
 void device_solver_t::set_communicator(communicator_t* comm)
@@ -1220,7 +1437,7 @@ std::vector<offender_t> device_solver_t::offenders(int slot)
     M3B_CUDA(cudaSetDevice(device_id));
     M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
     M3B_CUDA(cudaMemcpy(&f, impl->d_fail + slot, sizeof(fail_dev_t), cudaMemcpyDeviceToHost));
-    auto n = std::min<unsigned>(local_num_negative(slot), max_offenders);
+    auto n = std::min<unsigned>(f.pad, max_offenders);
     auto v = std::vector<offender_t>(f.list, f.list + n);
     std::sort(v.begin(), v.end(), [] (const offender_t& a, const offender_t& b) { return a.block != b.block ? a.block < b.block : a.cell < b.cell; });
     return v;

@@ -388,16 +388,82 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     return status_ok;
 }
 
-status_t binary_solver_t::next_solution(solution_t& s, double* dt_used, bool* fell_back)
+bool binary_solver_t::can_pipeline(const solution_t& s, double dt) const
+{
+    // the device computes the next step's inputs from constant orbital elements: stay well clear of the
+    // time at which the binary goes live (scheme.cpp:882)
+    return pipelining && data.rk_order == 2 && s.time + 1000.0 * dt < data.begin_live_binary;
+}
+
+void binary_solver_t::drop_speculation()
+{
+    if (speculation.valid)
+    {
+        device().sync();            // its kernels may still be running on the buffers we are about to release
+        speculation = speculation_t();
+    }
+}
+
+static bool same_elements(const elements_t& a, const elements_t& b)
+{
+    return a.pomega == b.pomega && a.tau == b.tau && a.cm_position_x == b.cm_position_x && a.cm_position_y == b.cm_position_y
+        && a.cm_velocity_x == b.cm_velocity_x && a.cm_velocity_y == b.cm_velocity_y && a.separation == b.separation
+        && a.total_mass == b.total_mass && a.mass_ratio == b.mass_ratio && a.eccentricity == b.eccentricity;
+}
+
+void binary_solver_t::launch_pipelined(const std::shared_ptr<device_field_t>& in, const std::shared_ptr<device_field_t>& out, int parity, const elements_t& elements)
+{
+    device().launch_step_async(*in, *scratch1, *out, parity, elements, data.cfl_number, data.recommended_time_step,
+                               data.plm_theta, data.fixed_dt);
+}
+
+/** Wait for a queued step, do the host bookkeeping of its two stages, and commit it to `s`. */
+status_t binary_solver_t::finish_pipelined(solution_t& s, const speculation_t& step)
+{
+    device().wait_step(step.parity);
+    const auto r1 = device().async_result(step.parity, 0);
+    const auto r2 = device().async_result(step.parity, 1);
+    const double dt = step.dt;
+
+    auto inputs1 = stage_inputs(s, dt, false);
+    auto s1 = solution_t(), s2 = solution_t();
+    auto st = bookkeeping(s, r1, inputs1.bodies, dt, s1);
+    if (st != status_ok) return st;
+    if (r1.num_negative) { record_offenders(device().async_slot(step.parity, 0)); return status_negative_density; }
+    auto inputs2 = stage_inputs(s1, dt, false);
+    st = bookkeeping(s1, r2, inputs2.bodies, dt, s2);
+    if (st != status_ok) return st;
+    if (r2.num_negative) { record_offenders(device().async_slot(step.parity, 1)); return status_negative_density; }
+
+    auto result = combine_scalars(s, s2, 0.5);
+    result.conserved_u = step.out;
+    s = result;
+    dt_cache_field = s.conserved_u.get();
+    dt_cache_time = s.time;
+    dt_cache_value = r2.dt_min;
+    return status_ok;
+}
+
+status_t binary_solver_t::next_solution(solution_t& s, double* dt_used, bool* fell_back, bool speculate)
 {
     if (! data.conserve_linear_p)
     {
         error = "conserve_linear_p=0 (advance_q) is not implemented by the B200 path";
         return status_unsupported;
     }
-    double dt;
+    if (fell_back) *fell_back = false;
 
-    if (data.fixed_dt)
+    // ---- a step queued earlier for exactly this state?
+    bool queued = speculation.valid && speculation.in == s.conserved_u && speculation.time == s.time
+        && same_elements(speculation.elements, s.orbital_elements);
+    if (speculation.valid && ! queued) drop_speculation();
+
+    double dt;
+    if (queued)
+    {
+        dt = speculation.dt;
+    }
+    else if (data.fixed_dt)
     {
         dt = data.recommended_time_step;
     }
@@ -410,16 +476,62 @@ status_t binary_solver_t::next_solution(solution_t& s, double* dt_used, bool* fe
         dt = data.cfl_number * maximum_timestep(s);
     }
     dt_cache_field = nullptr;
+    auto st = status_ok;
 
-    if (fell_back) *fell_back = false;
-    auto st = try_step(s, dt, false);
+    if (queued || can_pipeline(s, dt))
+    {
+        auto step = speculation;
+        speculation = speculation_t();
+
+        if (! queued)
+        {
+            // start of a pipeline: the host provides the inputs of this step
+            step.valid = true;
+            step.in = s.conserved_u;
+            step.out = new_field();
+            step.time = s.time;
+            step.dt = dt;
+            step.parity = 0;
+            auto inputs1 = stage_inputs(s, dt, false);
+            auto after1 = s;
+            after1.time = s.time + dt;
+            auto inputs2 = stage_inputs(after1, dt, false);
+            inputs2.combine = true;
+            inputs2.rk_b0 = 0.5;
+            inputs2.compute_dt = ! data.fixed_dt;
+            device().upload_step_inputs(step.parity, inputs1, inputs2);
+            launch_pipelined(step.in, step.out, step.parity, s.orbital_elements);
+        }
+        // queue the step after this one before waiting: its dt and body positions are already on the device
+        if (speculate && can_pipeline(s, dt))
+        {
+            speculation.valid = true;
+            speculation.in = step.out;
+            speculation.out = new_field();
+            speculation.parity = 1 - step.parity;
+            speculation.elements = s.orbital_elements;      // constant while the binary is not live
+            launch_pipelined(speculation.in, speculation.out, speculation.parity, s.orbital_elements);
+        }
+        st = finish_pipelined(s, step);
+
+        if (st == status_ok && speculation.valid)
+        {
+            speculation.time = s.time;
+            speculation.dt = data.fixed_dt ? data.recommended_time_step : data.cfl_number * dt_cache_value;
+        }
+        if (st != status_ok) drop_speculation();        // it started from a state that is being thrown away
+    }
+    else
+    {
+        st = try_step(s, dt, false);
+    }
 
     if (st == status_negative_density || st == status_unbound_orbit)
     {
         // the reference catches any std::exception, prints it, and redoes the step in safe mode
         // (subprog_binary.cpp:285-292)
-        if (! quiet) std::cout << error << std::endl;
         if (st == status_negative_density) error = "negative density in updated state";
+        if (! quiet) std::cout << error << std::endl;
         dt *= 0.1;
         if (fell_back) *fell_back = true;
         dt_cache_field = nullptr;

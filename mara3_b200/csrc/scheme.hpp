@@ -77,12 +77,16 @@ namespace m3b
         void combine(const solution_t& s0, const solution_t& s2, double b0, solution_t& out);
 
         /** binary::next_solution (subprog_binary.cpp:258-293), in place. */
-        status_t next_solution(solution_t& s, double* dt_used, bool* fell_back);
+        status_t next_solution(solution_t& s, double* dt_used, bool* fell_back, bool speculate = true);
+        /** Forget a step queued ahead of the caller (after the caller changed a state in place). */
+        void invalidate() { drop_speculation(); dt_cache_field = nullptr; }
 
         /** Messages the reference would have printed for the last negative-density failure. */
         const std::vector<std::string>& last_messages() const { return messages; }
         const std::string& last_error() const { return error; }
         void set_quiet(bool q) { quiet = q; }
+        /** Queue the following step before waiting for the current one (default on). */
+        void set_pipelining(bool on) { drop_speculation(); pipelining = on; }
 
     private:
         status_t try_step(solution_t& s, double dt, bool safe_mode);
@@ -100,6 +104,27 @@ namespace m3b
         std::vector<std::string> messages;
         std::string error;
         bool quiet = false;
+
+        /**
+         * A step that has been queued on the GPU for a state the caller has not asked to advance yet:
+         * next_solution() queues step n + 1 (from the output of step n, with dt and body positions
+         * computed on the device) before it waits for step n, so the GPU never idles on the host.
+         */
+        struct speculation_t
+        {
+            bool valid = false;
+            std::shared_ptr<device_field_t> in, out;    // the state it starts from / produces
+            double time = 0.0;                          // ... and that state's time
+            double dt = 0.0;                            // known once the step before has been consumed
+            elements_t elements;                        // orbital elements its body positions were computed from
+            int parity = 0;
+        };
+        speculation_t speculation;
+        bool pipelining = true;
+        bool can_pipeline(const solution_t& s, double dt) const;
+        void launch_pipelined(const std::shared_ptr<device_field_t>& in, const std::shared_ptr<device_field_t>& out, int parity, const elements_t& elements);
+        status_t finish_pipelined(solution_t& s, const speculation_t& step);
+        void drop_speculation();
 
         // CFL estimate produced by the last fused step, valid for exactly one state
         const device_field_t* dt_cache_field = nullptr;

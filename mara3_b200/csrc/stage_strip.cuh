@@ -69,14 +69,15 @@ namespace
 
     template<int MIN_CTAS>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
-        mesh_dev_t mesh, model_t model, const stage_t S, const int* __restrict__ regular_list,
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
         const unsigned char* __restrict__ tile_flags,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* __restrict__ partials, fail_dev_t* fail)
+        double* partials, double* __restrict__ block_rows, int* counters, fail_dev_t* fail)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         strip_smem_t& T = *reinterpret_cast<strip_smem_t*>(smem_raw);
 
+        const stage_t S = *stage_ptr;       // written by the host or by prepare_next of the step before
         const int N = mesh.N;
         const int tiles_y = N / SY, tiles_per_block = (N / SX) * tiles_y;
         const int r_index = blockIdx.x / tiles_per_block;
@@ -359,5 +360,6 @@ namespace
             double a = T.red[0][k], bq = T.red[1][k], cq = T.red[2][k], d = T.red[3][k];
             row[k] = k == NUM_SUMS ? dmin(dmin(a, bq), dmin(cq, d)) : ((a + bq) + (cq + d)) * (h * h);
         }
+        fold_tiles_of_block(partials, block_rows, counters, r_index, tiles_per_block);
     }
 }

@@ -291,3 +291,30 @@ def test_fused_and_general_kernels_agree_at_size():
             b.next_solution(ub)
         assert block_rel_err(ua.conserved_u, ub.conserved_u) <= 1e-13
         assert np.allclose(ua.scalars, ub.scalars, rtol=1e-10, atol=1e-16)
+
+
+def test_pipelined_stepping_equals_step_by_step():
+    """next_solution queues the following step ahead of the host; with that switched off every call
+    starts and finishes one step.  Same fields to rounding of the device-side sin/cos, same retries."""
+    cfg = dict(depth=2, block_size=64)
+    a, b = m3.Solver(cfg), m3.Solver(cfg)
+    b.set_pipelining(False)
+    ua, ub = a.create_solution(), b.create_solution()
+    fa, fb = [], []
+    for n in range(30):
+        dta, ra = a.next_solution(ua)
+        dtb, rb = b.next_solution(ub)
+        fa.append(ra)
+        fb.append(rb)
+        assert abs(dta - dtb) <= 1e-13 * dtb
+    assert fa == fb and any(fa)
+    assert block_rel_err(ua.conserved_u, ub.conserved_u) <= 1e-12
+    assert_scalars(ua.scalars, ub.scalars, 1e-11, ub.time)
+    # changing a state in place invalidates the step queued from it
+    U = ua.conserved_u
+    U[:, 0] *= 1.01
+    ua.conserved_u = U
+    ub.conserved_u = U
+    a.next_solution(ua)
+    b.next_solution(ub)
+    assert block_rel_err(ua.conserved_u, ub.conserved_u) <= 1e-12
