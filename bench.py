@@ -32,6 +32,8 @@ WORKLOADS = {
                config=dict(depth=4, block_size=64, focus_factor=1e3, mach_number=10.0)),
     "c3": dict(name="binary iso2d uniform 4096^2 (depth=6, 4096 blocks of 64^2), PLM+HLLE, RK2",
                config=dict(depth=6, block_size=64, focus_factor=1e3, mach_number=10.0)),
+    "c5": dict(name="binary iso2d uniform 16384^2 (depth=8, 65536 blocks of 64^2), PLM+HLLE, RK2",
+               config=dict(depth=8, block_size=64, focus_factor=1e3, mach_number=10.0)),
 }
 ALGORITHMIC_BYTES_PER_CELL_STEP = 120.0     # RK2 = 2 x (24 read + 24 write) + 24 re-read of U^n
 ALGORITHMIC_BYTES_PER_CELL_LAUNCH = 60.0    # mean over the two stage launches of a step (48 and 72)
@@ -158,6 +160,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-scaling-reference", action="store_true", help="N>1: skip the single-GPU run of the same workload on rank 0")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,7 +189,7 @@ def main():
 
     wl = WORKLOADS[args.workload or ("c2" if world == 1 else "c3")]
     scaling_reference = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and not args.no_scaling_reference:
         # the same workload on ONE GPU, measured in this run, so that strong-scaling efficiency can be
         # computed against the same problem (the N=1 default of this script is the smaller config 2)
         ref = mara3_b200.Solver(wl["config"], device=local_rank)

@@ -75,7 +75,8 @@ namespace m3b
 
         /**
          * One RK stage, binary::advance_u phases P1-P8 + P11 (scheme.cpp:790-904):
-         * out = update(in) [optionally RK-combined with un].  Asynchronous; results
+         * out = update(in) [optionally RK-combined with un].  On several ranks the guard zones of `in`
+         * are exchanged first, overlapped with the update of the interior blocks.  Asynchronous; results
          * land in the slot returned by stage_result() after sync().
          */
         void launch_stage(const device_field_t& in, const device_field_t* un, device_field_t& out, const stage_inputs_t& inputs, int slot);
@@ -130,7 +131,8 @@ namespace m3b
 
     private:
         void upload_stage(const stage_inputs_t& inputs, int slot);
-        void launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot);
+        void launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange);
+        void exchange_on(void* cuda_stream, device_field_t& field);
         stage_result_t* result_target(int slot);
         void launch_finish(const double* block_rows, int num_rows, int slot);
         struct impl_t;

@@ -811,6 +811,10 @@ struct device_solver_t::impl_t
     model_t model {};
     int tile_x = 0, tile_y = 0;
     int strip_min_ctas = 4;
+    int num_interior = 0;                   // leading entries of `regular` that touch no ghost block
+    bool overlap_exchange = false;          // M3B_OVERLAP_EXCHANGE=1: exchange on its own stream beside the interior update
+    cudaStream_t comm_stream = nullptr;     // guard-zone exchange runs here, beside the interior update
+    cudaEvent_t input_ready = nullptr, halo_ready = nullptr;
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     unsigned char* d_tile_flags = nullptr;
     std::vector<int> regular, irregular, gradient_blocks;
@@ -919,6 +923,20 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         std::sort(impl->irregular.begin(), impl->irregular.end());
         impl->regular.clear();
     }
+    // interior blocks (every neighbour owned by this rank) first: they can be updated while the guard zones
+    // of the boundary blocks are still in flight
+    std::stable_partition(impl->regular.begin(), impl->regular.end(), [&] (int b)
+    {
+        for (int k = 0; k < 9; ++k) if (nbr9[size_t(b) * 9 + k] >= BO) return false;
+        return true;
+    });
+    impl->num_interior = 0;
+    for (int b : impl->regular)
+    {
+        bool interior = true;
+        for (int k = 0; k < 9; ++k) if (nbr9[size_t(b) * 9 + k] >= BO) interior = false;
+        impl->num_interior += interior;
+    }
     num_regular = int(impl->regular.size());
 
     auto gslot = std::vector<int>(B, -1);
@@ -995,6 +1013,17 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaMalloc(&impl->d_results_local, num_slots * sizeof(stage_result_t)));
     M3B_CUDA(cudaMemset(impl->d_results_local, 0, num_slots * sizeof(stage_result_t)));
     for (auto& e : impl->step_done) M3B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        // highest priority: the exchange's small kernels must not queue behind the interior update's CTAs
+        int least = 0, greatest = 0;
+        M3B_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        M3B_CUDA(cudaStreamCreateWithPriority(&impl->comm_stream, cudaStreamNonBlocking, greatest));
+    }
+    // Measured on 4096^2 (profiles/): +4 % at 4 GPUs but -27 % at 8 GPUs, where the NCCL kernel spins on SMs until
+    // the slowest peer arrives and the boundary launch adds a partial wave; off unless asked for.
+    if (const char* e = std::getenv("M3B_OVERLAP_EXCHANGE")) impl->overlap_exchange = std::atoi(e) != 0;
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->input_ready, cudaEventDisableTiming));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->halo_ready, cudaEventDisableTiming));
     M3B_CUDA(cudaMalloc(&impl->d_staging, 3 * sd.num_owned_cells() * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_fail, num_slots * sizeof(fail_dev_t)));
     // stage results live in mapped pinned host memory: finish_stage writes them straight to the host
@@ -1090,6 +1119,9 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
                    (void*) impl->d_cta_rows, (void*) impl->d_counters}) if (p) cudaFree(p);
     for (auto e : impl->step_done) if (e) cudaEventDestroy(e);
+    if (impl->input_ready) cudaEventDestroy(impl->input_ready);
+    if (impl->halo_ready) cudaEventDestroy(impl->halo_ready);
+    if (impl->comm_stream) cudaStreamDestroy(impl->comm_stream);
     for (auto& ev : impl->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto e : impl->event_pool) cudaEventDestroy(e);
     if (host_results) cudaFreeHost(host_results);
@@ -1185,8 +1217,9 @@ void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
     M3B_CUDA(cudaMemcpyAsync(impl->d_stage + slot, &st, sizeof(stage_t), cudaMemcpyHostToDevice, s));
 }
 
-/** The stage kernels + finish_stage for the inputs already in d_stage[slot]. */
-void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot)
+/** The stage kernels + finish_stage for the inputs already in d_stage[slot].  With `exchange` the guard
+ *  zones of `in` are refreshed from the other ranks first, overlapped with the update of the interior blocks. */
+void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange)
 {
     auto s = cudaStream_t(stream_);
     if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
@@ -1198,29 +1231,31 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     int num_fused = force_general ? 0 : int(impl->regular.size());
     int num_general = force_general ? BO : int(impl->irregular.size());
     const int* d_general = force_general ? static_cast<const int*>(impl->owned[0]) : impl->d_irregular;
-    int fused_ctas = num_fused * (impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0);
-
-    if (fused_ctas > 0)
+    const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
+    int fused_ctas = num_fused * tpb;
+    exchange = exchange && num_ranks > 1;
+    if (exchange && ! impl->overlap_exchange)
     {
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (stage_timing)
-        {
-            // events come from a pool: creating them here would delay the launches behind this one
-            if (impl->event_pool.size() < 2)
-            {
-                for (int k = 0; k < 64; ++k) { cudaEvent_t e; M3B_CUDA(cudaEventCreate(&e)); impl->event_pool.push_back(e); }
-            }
-            e0 = impl->event_pool.back(); impl->event_pool.pop_back();
-            e1 = impl->event_pool.back(); impl->event_pool.pop_back();
-            M3B_CUDA(cudaEventRecord(e0, s));
-        }
-        #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<fused_ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
-            impl->mesh, impl->model, st, impl->d_regular, in.data, un_data, out.data, partials, block_rows, impl->d_counters, impl->d_fail + slot)
+        exchange_on(stream_, const_cast<device_field_t&>(in));     // plain ordering: exchange, then every block
+        exchange = false;
+    }
+
+    // blocks [first, first + count) of the regular list: tile rows, block rows and tickets are indexed by list position
+    auto launch_fused = [&] (int first, int count)
+    {
+        if (count <= 0) return;
+        const int ctas = count * tpb;
+        const int* list = impl->d_regular + first;
+        double* tiles = partials + size_t(first) * tpb * ROW;
+        double* rows = block_rows + size_t(first) * ROW;
+        int* tickets = impl->d_counters + first;
+        #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
+            impl->mesh, impl->model, st, list, in.data, un_data, out.data, tiles, rows, tickets, impl->d_fail + slot)
         if (impl->strip)
         {
             auto kernel = impl->strip_min_ctas == 2 ? stage_strip<2> : (impl->strip_min_ctas == 3 ? stage_strip<3> : stage_strip<4>);
-            kernel<<<fused_ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_regular, impl->d_tile_flags,
-                in.data, un_data, out.data, partials, block_rows, impl->d_counters, impl->d_fail + slot);
+            kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, list, impl->d_tile_flags,
+                in.data, un_data, out.data, tiles, rows, tickets, impl->d_fail + slot);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
@@ -1229,11 +1264,42 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         #undef M3B_LAUNCH_FUSED
         ++launches;
         M3B_CUDA(cudaGetLastError());
-        if (stage_timing)
+    };
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stage_timing && fused_ctas > 0)
+    {
+        // events come from a pool: creating them here would delay the launches behind this one
+        if (impl->event_pool.size() < 2)
         {
-            M3B_CUDA(cudaEventRecord(e1, s));
-            impl->timing_events.emplace_back(e0, e1);
+            for (int k = 0; k < 64; ++k) { cudaEvent_t e; M3B_CUDA(cudaEventCreate(&e)); impl->event_pool.push_back(e); }
         }
+        e0 = impl->event_pool.back(); impl->event_pool.pop_back();
+        e1 = impl->event_pool.back(); impl->event_pool.pop_back();
+    }
+    if (exchange)
+    {
+        // guard zones travel on their own stream while the interior blocks are updated
+        auto& field = const_cast<device_field_t&>(in);
+        M3B_CUDA(cudaEventRecord(impl->input_ready, s));
+        M3B_CUDA(cudaStreamWaitEvent(impl->comm_stream, impl->input_ready, 0));
+        exchange_on(impl->comm_stream, field);
+        M3B_CUDA(cudaEventRecord(impl->halo_ready, impl->comm_stream));
+        if (e0) M3B_CUDA(cudaEventRecord(e0, s));
+        launch_fused(0, impl->num_interior);
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));
+        launch_fused(impl->num_interior, num_fused - impl->num_interior);
+        if (num_fused == 0) {}      // (general blocks below run after the wait as well)
+    }
+    else
+    {
+        if (e0) M3B_CUDA(cudaEventRecord(e0, s));
+        launch_fused(0, num_fused);
+    }
+    if (e0)
+    {
+        M3B_CUDA(cudaEventRecord(e1, s));
+        impl->timing_events.emplace_back(e0, e1);
     }
     if (num_general > 0)
     {
@@ -1274,7 +1340,7 @@ void device_solver_t::launch_stage(const device_field_t& in, const device_field_
     M3B_CUDA(cudaSetDevice(device_id));
     if (inputs.combine && ! un) throw std::invalid_argument("launch_stage: combine requires the step-start state");
     upload_stage(inputs, slot);
-    launch_stage_kernels(in, un, out, slot);
+    launch_stage_kernels(in, un, out, slot, /*exchange*/ true);
 }
 
 void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scratch, device_field_t& out, int parity,
@@ -1285,10 +1351,8 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
     const int a = first_async_slot + 2 * parity, b = a + 1;
     const int na = first_async_slot + 2 * (1 - parity), nb = na + 1;
 
-    exchange_halos(in);
-    launch_stage_kernels(in, nullptr, scratch, a);
-    exchange_halos(scratch);
-    launch_stage_kernels(scratch, &in, out, b);
+    launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true);
+    launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true);
 
     const stage_result_t* gathered = impl->d_results_local;
     if (num_ranks > 1)
@@ -1360,8 +1424,13 @@ std::uint64_t device_solver_t::halo_bytes_per_exchange() const
 void device_solver_t::exchange_halos(device_field_t& field)
 {
     if (num_ranks == 1) return;
+    exchange_on(stream_, field);
+}
+
+void device_solver_t::exchange_on(void* cuda_stream, device_field_t& field)
+{
     if (! impl->comm) throw std::logic_error("exchange_halos: no communicator set");
-    auto s = cudaStream_t(stream_);
+    auto s = cudaStream_t(cuda_stream);
     M3B_CUDA(cudaSetDevice(device_id));
 
     if (impl->num_send_entries)
@@ -1369,7 +1438,7 @@ void device_solver_t::exchange_halos(device_field_t& field)
         halo_copy<<<impl->num_send_entries, 128, 0, s>>>(impl->d_send_entries, field.data, cells, N, impl->d_send_buffer, 1);
         ++launches;
     }
-    impl->comm->exchange(impl->send_ptr, impl->send_count, impl->recv_ptr, impl->recv_count, stream_);
+    impl->comm->exchange(impl->send_ptr, impl->send_count, impl->recv_ptr, impl->recv_count, cuda_stream);
 
     if (impl->num_recv_entries)
     {

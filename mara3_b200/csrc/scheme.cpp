@@ -244,7 +244,6 @@ status_t binary_solver_t::advance(const solution_t& in, double dt, bool safe_mod
     if (! out.conserved_u || out.conserved_u == in.conserved_u) out.conserved_u = new_field();
 
     auto inputs = stage_inputs(in, dt, safe_mode);
-    device().exchange_halos(*in.conserved_u);       // ghost blocks are a cache of the neighbours' edges
     device().launch_stage(*in.conserved_u, nullptr, *out.conserved_u, inputs, 0);
     device().gather_results();
     device().sync();
@@ -316,7 +315,6 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     if (data.rk_order == 1)
     {
         inputs1.compute_dt = ! data.fixed_dt && ! live_possible;
-        device().exchange_halos(*A);
         device().launch_stage(*A, nullptr, *scratch1, inputs1, 0);
         device().gather_results();
         device().sync();
@@ -333,7 +331,6 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     }
 
     // stage 1: A -> scratch1
-    device().exchange_halos(*A);
     device().launch_stage(*A, nullptr, *scratch1, inputs1, 0);
     s1.conserved_u = scratch1;
 
@@ -356,7 +353,6 @@ status_t binary_solver_t::try_step(solution_t& s, double dt, bool safe_mode)
     inputs2.combine = true;
     inputs2.rk_b0 = 0.5;
     inputs2.compute_dt = ! data.fixed_dt && ! live_possible;
-    device().exchange_halos(*scratch1);
     device().launch_stage(*scratch1, A.get(), *scratch2, inputs2, 1);
     device().gather_results();
     device().sync();
