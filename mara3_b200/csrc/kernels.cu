@@ -42,7 +42,7 @@ namespace
     constexpr int THREADS = 256;
     constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
     constexpr int FINISH_THREADS = 256;
-    constexpr int FINISH_ROWS_PER_CTA = 32;     // at most 4 rows per thread group; <= 2 * FINISH_THREADS / ROW CTAs are folded at the end
+    constexpr int FINISH_ROWS_PER_CTA = 32;     // block rows folded by one finish_stage CTA
     constexpr int stage_ring_size = 64;
 
     struct face_nbr_dev_t
@@ -66,6 +66,7 @@ namespace
         const double* U0;               // [3][FS]
         const double* br;               // [FS]
         size_t GS;                      // gradient scratch stride
+        int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
     };
 
     struct fail_dev_t
@@ -130,37 +131,6 @@ namespace
     }
 
 
-    /**
-     * The last tile CTA of a block to finish folds the block's tile rows, in tile order (so the result
-     * does not depend on which CTA came last), into one row per block: the reference's per-block
-     * source_term_total_t (scheme.cpp:390-408).  Standard threadfence + ticket pattern.
-     */
-    __device__ void fold_tiles_of_block(const double* tile_rows, double* __restrict__ block_rows, int* counters, int ordinal, int tiles_per_block)
-    {
-        __shared__ int is_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(&counters[ordinal], 1) == tiles_per_block - 1;
-        __syncthreads();
-        if (! is_last) return;
-        __threadfence();
-
-        if (threadIdx.x <= NUM_SUMS)
-        {
-            const int k = threadIdx.x;
-            const double* rows = tile_rows + size_t(ordinal) * tiles_per_block * ROW + k;
-            double v = k == NUM_SUMS ? 1e300 : 0.0;
-            for (int t = 0; t < tiles_per_block; ++t)
-            {
-                double p = __ldcg(rows + size_t(t) * ROW);
-                v = k == NUM_SUMS ? dmin(v, p) : v + p;
-            }
-            block_rows[size_t(ordinal) * ROW + k] = v;
-        }
-        if (threadIdx.x == 0) counters[ordinal] = 0;       // re-armed for the next launch
-    }
-
-
     // =======================================================================
     // Fused stage kernel for regular blocks
     // =======================================================================
@@ -182,7 +152,7 @@ namespace
     __global__ void __launch_bounds__(THREADS, 2) stage_fused(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* partials, double* __restrict__ block_rows, int* counters, fail_dev_t* fail)
+        double* partials, fail_dev_t* fail)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
@@ -302,7 +272,6 @@ namespace
             if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
         }
         reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
-        fold_tiles_of_block(partials, block_rows, counters, blockIdx.x / tiles_per_block, tiles_per_block);
     }
 
 
@@ -574,104 +543,6 @@ namespace
         }
     }
 
-    /**
-     * Fold the per-CTA rows in a fixed order (deterministic) and publish the stage result.
-     * The reference evaluates the work done on each body PER BLOCK from that block's accreted
-     * mass and momentum -- a non-linear function -- and then sums over blocks
-     * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
-     */
-    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* rows, int num_rows, int rows_per_cta,
-        double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr, fail_dev_t* fail, stage_result_t* result)
-    {
-        // one row per block (rows); CTA c folds rows [c * rows_per_cta, ...) and the block-wise work integrals,
-        // the last CTA to finish folds the CTA rows in CTA order
-        __shared__ double red[FINISH_THREADS / 32][32];
-        __shared__ double wred[2][FINISH_THREADS];
-        __shared__ int is_last;
-        const stage_t S = *stage_ptr;
-        const double body_mass[2] = {S.m1, S.m2}, body_vx[2] = {S.vx1, S.vx2}, body_vy[2] = {S.vy1, S.vy2};
-        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = FINISH_THREADS / 32;
-        const bool is_min = col == NUM_SUMS;
-        const int r0 = blockIdx.x * rows_per_cta, r1 = min(num_rows, r0 + rows_per_cta);
-
-        double v = is_min ? 1e300 : 0.0;
-        if (col <= NUM_SUMS)
-        {
-            for (int r = r0 + grp; r < r1; r += ngrp)          // rows_per_cta <= 4 * ngrp: at most 4 independent loads
-            {
-                double p = __ldcg(rows + size_t(r) * ROW + col);
-                v = is_min ? dmin(v, p) : v + p;
-            }
-        }
-        red[grp][col] = v;
-
-        double work[2] = {0.0, 0.0};
-        for (int r = r0 + threadIdx.x; r < r1; r += FINISH_THREADS)
-        {
-            #pragma unroll
-            for (int k = 0; k < 2; ++k)
-            {
-                double dm  = __ldcg(rows + size_t(r) * ROW + ACC_MASS + k);
-                double dpx = __ldcg(rows + size_t(r) * ROW + ACC_PX + k);
-                double dpy = __ldcg(rows + size_t(r) * ROW + ACC_PY + k);
-                if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
-                {
-                    double M0 = body_mass[k], px0 = body_vx[k] * M0, py0 = body_vy[k] * M0;
-                    double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
-                    work[k] += ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
-                }
-            }
-        }
-        wred[0][threadIdx.x] = work[0];
-        wred[1][threadIdx.x] = work[1];
-        __syncthreads();
-
-        double* mine = cta_rows + size_t(blockIdx.x) * ROW;
-        if (grp == 0 && col <= NUM_SUMS)
-        {
-            for (int g = 1; g < ngrp; ++g)
-            {
-                double p = red[g][col];
-                v = is_min ? dmin(v, p) : v + p;
-            }
-            mine[col] = v;
-        }
-        if (grp == 1 && col < 2)
-        {
-            double w = 0.0;
-            const int n = min(FINISH_THREADS, r1 - r0);
-            for (int t = 0; t < n; ++t) w += wred[col][t];
-            mine[NUM_SUMS + 1 + col] = w;
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
-        __syncthreads();
-        if (! is_last) return;
-        __threadfence();
-
-        // all CTA rows at once into shared memory, then a fixed-order fold
-        double* all = &wred[0][0];              // gridDim.x * ROW <= 2 * FINISH_THREADS doubles
-        for (int k = threadIdx.x; k < int(gridDim.x) * ROW; k += FINISH_THREADS) all[k] = __ldcg(cta_rows + k);
-        __syncthreads();
-        if (threadIdx.x < ROW - 1)
-        {
-            const int k = threadIdx.x;
-            double f = k == NUM_SUMS ? 1e300 : 0.0;
-            for (int c = 0; c < int(gridDim.x); ++c) f = k == NUM_SUMS ? dmin(f, all[c * ROW + k]) : f + all[c * ROW + k];
-            if (k < NUM_SUMS) result->sums[k] = f;
-            else if (k == NUM_SUMS) result->dt_min = f;
-            else result->work[k - NUM_SUMS - 1] = f;
-        }
-        if (threadIdx.x == 64)
-        {
-            result->num_negative = fail->count;
-            fail->pad = fail->count;    // how many entries of the list belong to this launch
-            fail->count = 0;            // ready for the next launch that uses this slot
-            *ticket = 0;
-        }
-    }
-
     /** What prepare_next needs to set up the following step without the host (constant while the binary is not live). */
     struct step_config_t
     {
@@ -686,6 +557,142 @@ namespace
         st.x1 = b.body1.x; st.y1 = b.body1.y; st.m1 = b.body1.mass; st.vx1 = b.body1.vx; st.vy1 = b.body1.vy;
         st.x2 = b.body2.x; st.y2 = b.body2.y; st.m2 = b.body2.mass; st.vx2 = b.body2.vx; st.vy2 = b.body2.vy;
         st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
+    }
+
+    /** Optional epilogue of finish_stage (single rank): what prepare_next does, in the last CTA of the step's last stage. */
+    struct prepare_args_t
+    {
+        int enabled;
+        step_config_t cfg;
+        const stage_t* current_a;       // first stage of the step that is ending (its time and dt)
+        stage_t* next_a;
+        stage_t* next_b;
+    };
+
+    /**
+     * Fold the stage kernels' rows in a fixed order (deterministic) and publish the stage result.
+     * Rows [0, num_fused) are regular blocks: their `tpb` tile rows (written by stage_strip / stage_fused,
+     * no fences or tickets in those kernels) are first folded, in tile order, into one row per block;
+     * rows [num_fused, num_rows) come one per block from the general path.
+     * The reference evaluates the work done on each body PER BLOCK from that block's accreted
+     * mass and momentum -- a non-linear function -- and then sums over blocks
+     * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
+     * CTA c handles FINISH_ROWS_PER_CTA block rows; the last CTA to finish folds the CTA rows in CTA order.
+     */
+    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* tile_rows, int num_fused, int tpb,
+        const double* general_rows, int num_rows, double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr,
+        fail_dev_t* fail, stage_result_t* result, prepare_args_t prep)
+    {
+        __shared__ double dt_min_all;
+        __shared__ double srow[FINISH_ROWS_PER_CTA][ROW];
+        __shared__ double wred[2][FINISH_ROWS_PER_CTA];
+        __shared__ double fin[FINISH_THREADS / 32][32];
+        __shared__ int is_last;
+        const stage_t S = *stage_ptr;
+        const int r0 = blockIdx.x * FINISH_ROWS_PER_CTA, n = min(FINISH_ROWS_PER_CTA, num_rows - r0);
+
+        // (A) one row per block
+        for (int idx = threadIdx.x; idx < n * ROW; idx += FINISH_THREADS)
+        {
+            const int r = idx / ROW, k = idx % ROW, R = r0 + r;
+            if (k > NUM_SUMS) continue;
+            double v;
+            if (R < num_fused)
+            {
+                const double* rows = tile_rows + size_t(R) * tpb * ROW + k;
+                v = k == NUM_SUMS ? 1e300 : 0.0;
+                for (int t = 0; t < tpb; ++t)
+                {
+                    double p = __ldcg(rows + size_t(t) * ROW);
+                    v = k == NUM_SUMS ? dmin(v, p) : v + p;
+                }
+            }
+            else v = __ldcg(general_rows + size_t(R - num_fused) * ROW + k);
+            srow[r][k] = v;
+        }
+        __syncthreads();
+
+        // (B) fold the CTA's rows in row order; block-wise work integrals
+        double* mine = cta_rows + size_t(blockIdx.x) * ROW;
+        if (threadIdx.x <= NUM_SUMS)
+        {
+            const int k = threadIdx.x;
+            double v = k == NUM_SUMS ? 1e300 : 0.0;
+            for (int r = 0; r < n; ++r) v = k == NUM_SUMS ? dmin(v, srow[r][k]) : v + srow[r][k];
+            mine[k] = v;
+        }
+        else if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * FINISH_ROWS_PER_CTA)
+        {
+            const int r = (threadIdx.x - 32) >> 1, k = threadIdx.x & 1;
+            double w = 0.0;
+            if (r < n)
+            {
+                const double dm = srow[r][ACC_MASS + k], dpx = srow[r][ACC_PX + k], dpy = srow[r][ACC_PY + k];
+                if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
+                {
+                    const double M0 = k ? S.m2 : S.m1, px0 = (k ? S.vx2 : S.vx1) * M0, py0 = (k ? S.vy2 : S.vy1) * M0;
+                    const double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
+                    w = ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
+                }
+            }
+            wred[k][r] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2)
+        {
+            double w = 0.0;
+            for (int r = 0; r < n; ++r) w += wred[threadIdx.x][r];
+            mine[NUM_SUMS + 1 + threadIdx.x] = w;
+        }
+        if (threadIdx.x < 32) __threadfence();      // the writers of `mine` all sit in warp 0
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
+        __syncthreads();
+        if (! is_last) return;
+        __threadfence();
+
+        // (C) CTA rows: group g folds rows g, g + 8, ... in order, then the eight groups are folded in order
+        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = FINISH_THREADS / 32;
+        const bool is_min = col == NUM_SUMS;
+        double v = is_min ? 1e300 : 0.0;
+        if (col < ROW - 1)
+        {
+            for (int c = grp; c < int(gridDim.x); c += ngrp)
+            {
+                double p = __ldcg(cta_rows + size_t(c) * ROW + col);
+                v = is_min ? dmin(v, p) : v + p;
+            }
+        }
+        fin[grp][col] = v;
+        __syncthreads();
+        if (threadIdx.x < ROW - 1)
+        {
+            const int k = threadIdx.x;
+            double f = fin[0][k];
+            for (int g = 1; g < ngrp; ++g) f = k == NUM_SUMS ? dmin(f, fin[g][k]) : f + fin[g][k];
+            if (k < NUM_SUMS) result->sums[k] = f;
+            else if (k == NUM_SUMS) { result->dt_min = f; dt_min_all = f; }
+            else result->work[k - NUM_SUMS - 1] = f;
+        }
+        if (threadIdx.x == 64)
+        {
+            result->num_negative = fail->count;
+            fail->pad = fail->count;    // how many entries of the list belong to this launch
+            fail->count = 0;            // ready for the next launch that uses this slot
+            *ticket = 0;
+        }
+        if (! prep.enabled) return;
+
+        // stage inputs of the next step (see prepare_next): one thread per stage
+        __syncthreads();
+        if (threadIdx.x == 96 || threadIdx.x == 128)
+        {
+            const double t = prep.current_a->time, dt = prep.current_a->dt;
+            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
+            const double dt_next = prep.cfg.fixed_dt ? prep.cfg.recommended_time_step : prep.cfg.cfl_number * dt_min_all;
+            if (threadIdx.x == 96) fill_stage(*prep.next_a, t_next, dt_next, prep.cfg.theta, two_body_state(prep.cfg.elements, t_next), 0.0, 0, 0);
+            else fill_stage(*prep.next_b, t_next + dt_next, dt_next, prep.cfg.theta, two_body_state(prep.cfg.elements, t_next + dt_next), 0.5, 1, ! prep.cfg.fixed_dt);
+        }
     }
 
     /**
@@ -838,9 +845,12 @@ struct device_solver_t::impl_t
     int ring_next = 0;
     double* d_partials2 = nullptr;              // second row buffer: the two stages of a step stay separate
     double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
-    double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows
+    double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows, one set per slot parity
+    size_t cta_rows_stride = 0;
+    cudaStream_t finish_stream = nullptr;       // finish_stage of a step's first stage runs here, beside the second stage
+    cudaEvent_t stage_done = nullptr, side_finish_done = nullptr;
+    prepare_args_t pending_prepare = prepare_args_t();
     int* d_counters = nullptr;                  // per-block tile tickets, then the finish ticket
-    int finish_ctas_max = 0;
     size_t partial_rows = 0;
     cudaEvent_t step_done[2] = {nullptr, nullptr};
 
@@ -1003,10 +1013,13 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_partials2, max_rows * ROW * sizeof(double)));
     for (auto& p : impl->d_block_rows) M3B_CUDA(cudaMalloc(&p, size_t(BO + 1) * ROW * sizeof(double)));
-    impl->finish_ctas_max = 2 * FINISH_THREADS / ROW;
-    M3B_CUDA(cudaMalloc(&impl->d_cta_rows, size_t(impl->finish_ctas_max) * ROW * sizeof(double)));
-    M3B_CUDA(cudaMalloc(&impl->d_counters, size_t(BO + 2) * sizeof(int)));
-    M3B_CUDA(cudaMemset(impl->d_counters, 0, size_t(BO + 2) * sizeof(int)));
+    impl->cta_rows_stride = size_t(BO / FINISH_ROWS_PER_CTA + 1) * ROW;
+    M3B_CUDA(cudaMalloc(&impl->d_cta_rows, 2 * impl->cta_rows_stride * sizeof(double)));
+    M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->stage_done, cudaEventDisableTiming));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->side_finish_done, cudaEventDisableTiming));
+    M3B_CUDA(cudaMalloc(&impl->d_counters, 2 * sizeof(int)));
+    M3B_CUDA(cudaMemset(impl->d_counters, 0, 2 * sizeof(int)));
     impl->partial_rows = max_rows;
     M3B_CUDA(cudaMalloc(&impl->d_stage, num_slots * sizeof(stage_t)));
     M3B_CUDA(cudaMallocHost(&impl->h_stage_ring, stage_ring_size * sizeof(stage_t)));
@@ -1092,9 +1105,13 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         // experiment knob: registers per thread vs resident CTAs (default 4 CTAs x 128 threads, 128 registers)
         const char* e = std::getenv("M3B_STRIP_MIN_CTAS");
         impl->strip_min_ctas = e ? std::atoi(e) : 4;
-        set_smem(stage_strip<4>, sizeof(strip_smem_t));
-        set_smem(stage_strip<3>, sizeof(strip_smem_t));
-        set_smem(stage_strip<2>, sizeof(strip_smem_t));
+        const char* pa = std::getenv("M3B_PREFETCH_AHEAD");
+        impl->mesh.prefetch_ahead = pa ? std::atoi(pa) : impl->sm_count * 4;
+        set_smem(stage_strip<4, 0>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 32>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64>, sizeof(strip_smem_t));
+        set_smem(stage_strip<3, 64>, sizeof(strip_smem_t));
+        set_smem(stage_strip<2, 64>, sizeof(strip_smem_t));
     }
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
     if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
@@ -1119,6 +1136,9 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
                    (void*) impl->d_cta_rows, (void*) impl->d_counters}) if (p) cudaFree(p);
     for (auto e : impl->step_done) if (e) cudaEventDestroy(e);
+    if (impl->stage_done) cudaEventDestroy(impl->stage_done);
+    if (impl->side_finish_done) cudaEventDestroy(impl->side_finish_done);
+    if (impl->finish_stream) cudaStreamDestroy(impl->finish_stream);
     if (impl->input_ready) cudaEventDestroy(impl->input_ready);
     if (impl->halo_ready) cudaEventDestroy(impl->halo_ready);
     if (impl->comm_stream) cudaStreamDestroy(impl->comm_stream);
@@ -1219,7 +1239,7 @@ void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
 
 /** The stage kernels + finish_stage for the inputs already in d_stage[slot].  With `exchange` the guard
  *  zones of `in` are refreshed from the other ranks first, overlapped with the update of the interior blocks. */
-void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange)
+void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange, int finish_mode)
 {
     auto s = cudaStream_t(stream_);
     if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
@@ -1247,15 +1267,15 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         const int ctas = count * tpb;
         const int* list = impl->d_regular + first;
         double* tiles = partials + size_t(first) * tpb * ROW;
-        double* rows = block_rows + size_t(first) * ROW;
-        int* tickets = impl->d_counters + first;
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
-            impl->mesh, impl->model, st, list, in.data, un_data, out.data, tiles, rows, tickets, impl->d_fail + slot)
+            impl->mesh, impl->model, st, list, in.data, un_data, out.data, tiles, impl->d_fail + slot)
         if (impl->strip)
         {
-            auto kernel = impl->strip_min_ctas == 2 ? stage_strip<2> : (impl->strip_min_ctas == 3 ? stage_strip<3> : stage_strip<4>);
+            auto kernel = N == 64 ? stage_strip<4, 64> : (N == 32 ? stage_strip<4, 32> : stage_strip<4, 0>);
+            if (N == 64 && impl->strip_min_ctas == 3) kernel = stage_strip<3, 64>;
+            if (N == 64 && impl->strip_min_ctas == 2) kernel = stage_strip<2, 64>;
             kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, list, impl->d_tile_flags,
-                in.data, un_data, out.data, tiles, rows, tickets, impl->d_fail + slot);
+                in.data, un_data, out.data, tiles, impl->d_fail + slot);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
@@ -1307,31 +1327,46 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         int ng = int(impl->gradient_blocks.size());
         general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
         general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
-            in.data, impl->d_gradients, un_data, out.data, block_rows + size_t(num_fused) * ROW, impl->d_fail + slot);
+            in.data, impl->d_gradients, un_data, out.data, block_rows, impl->d_fail + slot);
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
-    launch_finish(block_rows, num_fused + num_general, slot);
+    launch_finish(partials, num_fused, tpb, block_rows, num_fused + num_general, slot, finish_mode);
     M3B_CUDA(cudaGetLastError());
 }
 
-void device_solver_t::launch_finish(const double* block_rows, int num_rows, int slot)
+/** finish_mode 0: on the compute stream.  1: on the side stream, beside the next stage (its result is only read at the end of
+ *  the step).  2: on the compute stream after the side stream's finish, with the next step's stage inputs written by the last CTA. */
+void device_solver_t::launch_finish(const double* tile_rows, int num_fused, int tpb, const double* general_rows, int num_rows, int slot, int finish_mode)
 {
-    // enough CTAs to keep every load independent, few enough for the final fold to fit shared memory
-    int rows_per_cta = FINISH_ROWS_PER_CTA;
-    while ((num_rows + rows_per_cta - 1) / rows_per_cta > impl->finish_ctas_max) rows_per_cta *= 2;
-    int ctas = std::max(1, (num_rows + rows_per_cta - 1) / rows_per_cta);
-    finish_stage<<<ctas, FINISH_THREADS, 0, cudaStream_t(stream_)>>>(block_rows, num_rows, rows_per_cta, impl->d_cta_rows,
-        impl->d_counters + BO + 1, impl->d_stage + slot, impl->d_fail + slot, result_target(slot));
+    auto s = cudaStream_t(stream_);
+    int ctas = std::max(1, (num_rows + FINISH_ROWS_PER_CTA - 1) / FINISH_ROWS_PER_CTA);
+    double* cta_rows = impl->d_cta_rows + size_t(slot & 1) * impl->cta_rows_stride;
+    prepare_args_t prep = prepare_args_t();
+
+    if (finish_mode == 1)
+    {
+        M3B_CUDA(cudaEventRecord(impl->stage_done, s));
+        M3B_CUDA(cudaStreamWaitEvent(impl->finish_stream, impl->stage_done, 0));
+        s = impl->finish_stream;
+    }
+    if (finish_mode == 2)
+    {
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->side_finish_done, 0));
+        prep = impl->pending_prepare;
+    }
+    finish_stage<<<ctas, FINISH_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, num_rows, cta_rows,
+        impl->d_counters + (slot & 1), impl->d_stage + slot, impl->d_fail + slot, result_target(slot), prep);
     ++launches;
     M3B_CUDA(cudaGetLastError());
+    if (finish_mode == 1) M3B_CUDA(cudaEventRecord(impl->side_finish_done, impl->finish_stream));
 }
 
 /** Where finish_stage writes: host-mapped memory for synchronous single-rank use, device memory when the
  *  result still has to be folded over ranks or consumed by prepare_next. */
 stage_result_t* device_solver_t::result_target(int slot)
 {
-    bool on_device = num_ranks > 1 || (slot >= first_async_slot && slot < first_async_slot + 4);
+    bool on_device = num_ranks > 1;     // a single rank publishes straight to the host (finish_stage also prepares the next step)
     return (on_device ? impl->d_results_local : impl->d_results) + slot;
 }
 
@@ -1351,25 +1386,35 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
     const int a = first_async_slot + 2 * parity, b = a + 1;
     const int na = first_async_slot + 2 * (1 - parity), nb = na + 1;
 
-    launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true);
-    launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true);
-
-    const stage_result_t* gathered = impl->d_results_local;
-    if (num_ranks > 1)
-    {
-        const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
-        impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
-        gathered = impl->d_results_all;
-    }
     step_config_t cfg;
     cfg.elements = elements;
     cfg.cfl_number = cfl_number;
     cfg.recommended_time_step = recommended_time_step;
     cfg.theta = theta;
     cfg.fixed_dt = fixed_dt;
-    prepare_next<<<1, 32, 0, s>>>(gathered, num_ranks, num_slots, a, b, cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);
-    ++launches;
-    M3B_CUDA(cudaGetLastError());
+
+    if (num_ranks == 1)
+    {
+        // the first stage's rows are folded on the side stream while the second stage runs; the second
+        // stage's finish_stage also writes the stage inputs of the next step (no separate prepare_next)
+        impl->pending_prepare.enabled = 1;
+        impl->pending_prepare.cfg = cfg;
+        impl->pending_prepare.current_a = impl->d_stage + a;
+        impl->pending_prepare.next_a = impl->d_stage + na;
+        impl->pending_prepare.next_b = impl->d_stage + nb;
+        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1);
+        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2);
+    }
+    else
+    {
+        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 0);
+        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 0);
+        const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
+        impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
+        prepare_next<<<1, 32, 0, s>>>(impl->d_results_all, num_ranks, num_slots, a, b, cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);
+        ++launches;
+        M3B_CUDA(cudaGetLastError());
+    }
     M3B_CUDA(cudaEventRecord(impl->step_done[parity], s));
 }
 
@@ -1408,7 +1453,7 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     double* block_rows = impl->d_block_rows[slot & 1];
     max_timestep_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, impl->model, impl->d_stage + slot, in.data, block_rows);
     ++launches;
-    launch_finish(block_rows, BO, slot);
+    launch_finish(nullptr, 0, 1, block_rows, BO, slot, 0);
 }
 
 void device_solver_t::set_communicator(communicator_t* comm)

@@ -75,18 +75,18 @@ namespace
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
     }
 
-    template<int MIN_CTAS>
+    template<int MIN_CTAS, int NB>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
         const unsigned char* __restrict__ tile_flags,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* partials, double* __restrict__ block_rows, int* counters, fail_dev_t* fail)
+        double* partials, fail_dev_t* fail)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         strip_smem_t& T = *reinterpret_cast<strip_smem_t*>(smem_raw);
 
         const stage_t S = *stage_ptr;       // written by the host or by prepare_next of the step before
-        const int N = mesh.N;
+        const int N = NB ? NB : mesh.N;       // NB: block size known at compile time (addresses fold into immediates)
         const int tiles_y = N / SY, tiles_per_block = (N / SX) * tiles_y;
         const int r_index = blockIdx.x / tiles_per_block;
         const int b  = regular_list[r_index];
@@ -96,6 +96,17 @@ namespace
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const bool has_buffer = tile_flags[size_t(b) * tiles_per_block + t] & 1;
 
+        // one "generation" of resident CTAs ahead: pull the tile that a later CTA of this SM slot will load from HBM into L2
+        {
+            const int ahead = blockIdx.x + mesh.prefetch_ahead;
+            if (mesh.prefetch_ahead > 0 && ahead < gridDim.x && threadIdx.x < 96)
+            {
+                const int rb = regular_list[ahead / tiles_per_block], rt = ahead % tiles_per_block;
+                const int f = threadIdx.x >> 5, row = (threadIdx.x & 31) >> 1, half = threadIdx.x & 1;
+                const size_t c = (size_t(rb) * N + ((rt / tiles_y) * SX + row)) * N + (rt % tiles_y) * SY + 16 * half;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(Uin + f * FS + c));
+            }
+        }
         // the update phase's inputs are first touched ~10 us from now: pull their lines into L2 already
         if (lane < 2 * STRIP)
         {
@@ -371,6 +382,5 @@ namespace
             double a = T.red[0][k], bq = T.red[1][k], cq = T.red[2][k], d = T.red[3][k];
             row[k] = k == NUM_SUMS ? dmin(dmin(a, bq), dmin(cq, d)) : ((a + bq) + (cq + d)) * (h * h);
         }
-        fold_tiles_of_block(partials, block_rows, counters, r_index, tiles_per_block);
     }
 }
