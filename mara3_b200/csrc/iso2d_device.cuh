@@ -141,13 +141,15 @@ __device__ __noinline__ double sink_weight(double rate, double a2)
  * The same from the softened squared distances d_k = |x - x_k|^2 + rs^2 to the two bodies and
  * r2 = |x|^2 (the strip kernel tabulates their x- and y-parts per tile row / column).
  */
+template<bool FAST>
 __device__ __forceinline__ eos_t eos_from_distances(const model_t& M, const stage_t& S, double d1, double d2, double r2)
 {
+    // FAST: the caller has checked axisymmetric_cs2 == 0, nu == 0, alpha_cutoff_radius == 0 (the defaults): branch-free
     eos_t e;
-    e.cs2 = M.axisymmetric_cs2 ? fast_rsqrt(r2) * M.inv_mach2 : fma(S.m1, fast_rsqrt(d1), S.m2 * fast_rsqrt(d2)) * M.inv_mach2;
+    e.cs2 = ! FAST && M.axisymmetric_cs2 ? fast_rsqrt(r2) * M.inv_mach2 : fma(S.m1, fast_rsqrt(d1), S.m2 * fast_rsqrt(d2)) * M.inv_mach2;
     e.cs = e.cs2 * fast_rsqrt(e.cs2);
 
-    if (M.nu > 0.0 || M.alpha_cutoff_radius > 0.0)
+    if (! FAST && (M.nu > 0.0 || M.alpha_cutoff_radius > 0.0))
     {
         e.nu = viscosity_slow_path(M.nu, M.alpha, M.alpha_cutoff_radius, M.inv_mach, e.cs, r2);
     }
@@ -204,25 +206,9 @@ __device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, 
     double ap = dmax(0.0, dmax(vl, vr) + e.cs);     // max(0, vl + cs, vr + cs)
     double am = dmin(0.0, dmin(vl, vr) - e.cs);     // min(0, vl - cs, vr - cs)
     double f0, f1, f2;
-    const unsigned active = __activemask();
-
-    if (__all_sync(active, am == 0.0))
     {
-        // every face of the warp is supersonic towards +n: (Fl ap - Fr 0 - (Ul - Ur) ap 0) / ap = Fl
-        double pgl = L.s * e.cs2;
-        f0 = vl * L.s;
-        f1 = AXIS == 0 ? fma(f0, L.vx, pgl) : f0 * L.vx;
-        f2 = AXIS == 0 ? f0 * L.vy : fma(f0, L.vy, pgl);
-    }
-    else if (__all_sync(active, ap == 0.0))
-    {
-        double pgr = R.s * e.cs2;       // ... towards -n: the flux of the right state
-        f0 = vr * R.s;
-        f1 = AXIS == 0 ? fma(f0, R.vx, pgr) : f0 * R.vx;
-        f2 = AXIS == 0 ? f0 * R.vy : fma(f0, R.vy, pgr);
-    }
-    else
-    {
+        // (a warp-uniform short cut for all-supersonic faces was measured: the branches cost more than the
+        // arithmetic they save, 764 -> 719 us on the 4096^2 grid -- one straight-line block schedules better)
         double inv = fast_rcp(ap - am);
         double apam = ap * am;
         double Ul1 = L.s * L.vx, Ul2 = L.s * L.vy, Ur1 = R.s * R.vx, Ur2 = R.s * R.vy;
@@ -266,10 +252,13 @@ using namespace m3b::sums;
  * cell's contributions to sums[].  Returns y1, y2 (inverse softened distances)
  * for the fused time-step estimate.
  */
+template<bool FAST = false, bool WARP_SINKS = false>
 __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S, double x, double y,
     double s, double px, double py, double u0s, double u0x, double u0y, double br,
-    double src[3], double sums[NUM_SUMS], double& y1, double& y2)
+    double src[3], double sums[NUM_SUMS], double& y1, double& y2, double* warp_sinks = nullptr)
 {
+    // WARP_SINKS: called by all 32 lanes of a converged warp; the eight sink sums (rarely touched) are
+    // accumulated per warp in shared memory (warp_sinks[8]) instead of in 16 registers per thread
     double dx1 = x - S.x1, dy1 = y - S.y1, dx2 = x - S.x2, dy2 = y - S.y2;
     double r1 = fma(dx1, dx1, dy1 * dy1);
     double r2 = fma(dx2, dx2, dy2 * dy2);
@@ -290,20 +279,41 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
     // factor is < 4e-44: no representable effect on the state and < 1e-40 relative on the totals.
     double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
 
-    if (e1 < 100.0 || e2 < 100.0)
+    const bool near_sink = e1 < 100.0 || e2 < 100.0;
+
+    if (WARP_SINKS ? __any_sync(0xffffffffu, near_sink) : near_sink)
     {
         double w1 = sink_weight(M.sink_rate, e1);
         double w2 = sink_weight(M.sink_rate, e2);
         double lz = fma(x, py, -y * px);
-        sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
-        sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
-        sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
-        sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        if (WARP_SINKS)
+        {
+            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+            #pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+            }
+        }
+        else
+        {
+            sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
+            sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
+            sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
+            sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        }
         double w = -(w1 + w2) * S.dt;
         a0 = fma(s, w, a0);  a1 = fma(px, w, a1);  a2 = fma(py, w, a2);
     }
-    // buffer zone (scheme.cpp:384): (U0 - u) * rate * dt; rate is exactly 0 away from the edge
-    if (br != 0.0)
+    // buffer zone (scheme.cpp:384): (U0 - u) * rate * dt; rate is exactly 0 away from the edge, where
+    // these terms add exact zeros (FAST: no branch; the rate is non-zero on most of the default domain)
+    if (FAST || br != 0.0)
     {
         double b0 = (u0s - s) * br, b1 = (u0x - px) * br, b2 = (u0y - py) * br;
         sums[BUF_M] += b0;
@@ -311,7 +321,7 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
         a0 = fma(b0, S.dt, a0);  a1 = fma(b1, S.dt, a1);  a2 = fma(b2, S.dt, a2);
     }
     // density floor (scheme.cpp:385-388): u * 0.01 where sigma < floor
-    if (s < M.density_floor)
+    if (! FAST && s < M.density_floor)      // FAST: the caller has checked density_floor == 0
     {
         a0 = fma(s, 1e-2, a0);  a1 = fma(px, 1e-2, a1);  a2 = fma(py, 1e-2, a2);
     }
@@ -319,10 +329,11 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
 }
 
 /** max_wavespeed (physics_iso2d.hpp:330-337) with cs2 at the cell centre from y1, y2. */
+template<bool FAST = false>
 __device__ __forceinline__ double max_wavespeed(const model_t& M, const stage_t& S, double x, double y,
     double y1, double y2, double s, double px, double py)
 {
-    double cs2 = M.axisymmetric_cs2 ? fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2 : fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;
+    double cs2 = ! FAST && M.axisymmetric_cs2 ? fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2 : fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;
     double cs = cs2 * fast_rsqrt(cs2);
     double inv = fast_rcp(s);
     double vx = fabs(px * inv), vy = fabs(py * inv);

@@ -60,6 +60,7 @@ namespace
         const double* xv;               // [B][N+1]
         const double* yv;               // [B][N+1]
         const double* spacing;          // [B]
+        const double* inv_spacing;      // [B] 1 / spacing
         const face_nbr_dev_t* nbr;      // [B][4]
         const int* nbr9;                // [B][9] same-level neighbour leaf ids (regular blocks only)
         const int* gslot;               // [B] slot of the block in the gradient scratch, or -1
@@ -822,6 +823,7 @@ struct device_solver_t::impl_t
     bool overlap_exchange = false;          // M3B_OVERLAP_EXCHANGE=1: exchange on its own stream beside the interior update
     cudaStream_t comm_stream = nullptr;     // guard-zone exchange runs here, beside the interior update
     cudaEvent_t input_ready = nullptr, halo_ready = nullptr;
+    bool fast_eos = false;                  // default equation of state / viscosity: branch-free kernel variant
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     unsigned char* d_tile_flags = nullptr;
     std::vector<int> regular, irregular, gradient_blocks;
@@ -968,6 +970,11 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->mesh.xv = device_upload(sd.xv);
     impl->mesh.yv = device_upload(sd.yv);
     impl->mesh.spacing = device_upload(spacing);
+    {
+        std::vector<double> inv(spacing.size());
+        for (size_t k = 0; k < inv.size(); ++k) inv[k] = 1.0 / spacing[k];
+        impl->mesh.inv_spacing = device_upload(inv);
+    }
     impl->mesh.nbr = device_upload(nbr);
     impl->mesh.nbr9 = device_upload(nbr9);
     impl->mesh.gslot = device_upload(gslot);
@@ -1107,11 +1114,13 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         impl->strip_min_ctas = e ? std::atoi(e) : 4;
         const char* pa = std::getenv("M3B_PREFETCH_AHEAD");
         impl->mesh.prefetch_ahead = pa ? std::atoi(pa) : impl->sm_count * 4;
-        set_smem(stage_strip<4, 0>, sizeof(strip_smem_t));
-        set_smem(stage_strip<4, 32>, sizeof(strip_smem_t));
-        set_smem(stage_strip<4, 64>, sizeof(strip_smem_t));
-        set_smem(stage_strip<3, 64>, sizeof(strip_smem_t));
-        set_smem(stage_strip<2, 64>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, false, 0>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, true, 0>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, false, 0>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 0>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 1>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 2>, sizeof(strip_smem_t));
+        impl->fast_eos = ! sd.axisymmetric_cs2 && sd.nu == 0.0 && sd.alpha_cutoff_radius == 0.0 && sd.density_floor == 0.0;
     }
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
     if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
@@ -1122,7 +1131,7 @@ device_solver_t::~device_solver_t()
 {
     cudaSetDevice(device_id);
     cudaStreamSynchronize(cudaStream_t(stream_));
-    for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.nbr,
+    for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.inv_spacing, (void*) impl->mesh.nbr,
                    (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
                    (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
                    (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail})
@@ -1239,7 +1248,7 @@ void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
 
 /** The stage kernels + finish_stage for the inputs already in d_stage[slot].  With `exchange` the guard
  *  zones of `in` are refreshed from the other ranks first, overlapped with the update of the interior blocks. */
-void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange, int finish_mode)
+void device_solver_t::launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange, int finish_mode, int stage_mode)
 {
     auto s = cudaStream_t(stream_);
     if (in.data == out.data) throw std::invalid_argument("launch_stage: in-place stages are not supported");
@@ -1271,9 +1280,10 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             impl->mesh, impl->model, st, list, in.data, un_data, out.data, tiles, impl->d_fail + slot)
         if (impl->strip)
         {
-            auto kernel = N == 64 ? stage_strip<4, 64> : (N == 32 ? stage_strip<4, 32> : stage_strip<4, 0>);
-            if (N == 64 && impl->strip_min_ctas == 3) kernel = stage_strip<3, 64>;
-            if (N == 64 && impl->strip_min_ctas == 2) kernel = stage_strip<2, 64>;
+            auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0> : stage_strip<4, 64, false, 0>)
+                                  : (impl->fast_eos ? stage_strip<4, 0, true, 0> : stage_strip<4, 0, false, 0>);
+            if (N == 64 && impl->fast_eos && stage_mode == 1) kernel = stage_strip<4, 64, true, 1>;
+            if (N == 64 && impl->fast_eos && stage_mode == 2) kernel = stage_strip<4, 64, true, 2>;
             kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, list, impl->d_tile_flags,
                 in.data, un_data, out.data, tiles, impl->d_fail + slot);
         }
@@ -1402,13 +1412,13 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
         impl->pending_prepare.current_a = impl->d_stage + a;
         impl->pending_prepare.next_a = impl->d_stage + na;
         impl->pending_prepare.next_b = impl->d_stage + nb;
-        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1);
-        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2);
+        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1, 1);
+        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2, fixed_dt ? 0 : 2);
     }
     else
     {
-        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 0);
-        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 0);
+        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 0, 1);
+        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 0, fixed_dt ? 0 : 2);
         const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
         impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
         prepare_next<<<1, 32, 0, s>>>(impl->d_results_all, num_ranks, num_slots, a, b, cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);

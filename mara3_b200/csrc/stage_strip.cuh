@@ -38,6 +38,7 @@ namespace
         double x2v[3][SX + 1], x2c[3][SX];      // (xv - x_k)^2, (xc - x_k)^2
         double y2v[3][SY + 1], y2c[3][SY];      // (yv - y_k)^2 [+ rs^2], (yc - y_k)^2 [+ rs^2]
         double red[STRIP_THREADS / 32][NUM_SUMS + 1];
+        double sinks[STRIP_THREADS / 32][8];     // per-warp sink sums (ACC_MASS .. ACC_LZ), see source_terms<.., WARP_SINKS>
     };
 
     __device__ __forceinline__ double shfl_down1(double v)
@@ -45,14 +46,16 @@ namespace
         return __shfl_down_sync(0xffffffffu, v, 1);
     }
 
+    template<bool FAST>
     __device__ __forceinline__ eos_t strip_x_eos(const strip_smem_t& T, const model_t& model, const stage_t& S, int li, int lj)
     {
-        return eos_from_distances(model, S, T.x2v[0][li] + T.y2c[0][lj], T.x2v[1][li] + T.y2c[1][lj], T.x2v[2][li] + T.y2c[2][lj]);
+        return eos_from_distances<FAST>(model, S, T.x2v[0][li] + T.y2c[0][lj], T.x2v[1][li] + T.y2c[1][lj], T.x2v[2][li] + T.y2c[2][lj]);
     }
 
+    template<bool FAST>
     __device__ __forceinline__ eos_t strip_y_eos(const strip_smem_t& T, const model_t& model, const stage_t& S, int li, int lj)
     {
-        return eos_from_distances(model, S, T.x2c[0][li] + T.y2v[0][lj], T.x2c[1][li] + T.y2v[1][lj], T.x2c[2][li] + T.y2v[2][lj]);
+        return eos_from_distances<FAST>(model, S, T.x2c[0][li] + T.y2v[0][lj], T.x2c[1][li] + T.y2v[1][lj], T.x2c[2][li] + T.y2v[2][lj]);
     }
 
     /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX */
@@ -75,7 +78,7 @@ namespace
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
     }
 
-    template<int MIN_CTAS, int NB>
+    template<int MIN_CTAS, int NB, bool FAST, int MODE>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
         const unsigned char* __restrict__ tile_flags,
@@ -86,6 +89,8 @@ namespace
         strip_smem_t& T = *reinterpret_cast<strip_smem_t*>(smem_raw);
 
         const stage_t S = *stage_ptr;       // written by the host or by prepare_next of the step before
+        // MODE 1 / 2: first / last stage of an RK2 step with adaptive dt, flags known at compile time; 0: read them from S
+        const bool combine = MODE == 0 ? S.combine != 0 : MODE == 2, compute_dt = MODE == 0 ? S.compute_dt != 0 : MODE == 2;
         const int N = NB ? NB : mesh.N;       // NB: block size known at compile time (addresses fold into immediates)
         const int tiles_y = N / SY, tiles_per_block = (N / SX) * tiles_y;
         const int r_index = blockIdx.x / tiles_per_block;
@@ -118,13 +123,15 @@ namespace
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(mesh.U0 + FS + c));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(mesh.U0 + 2 * FS + c));
             }
-            if (S.combine)
+            if (combine)
             {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(Un + c));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(Un + FS + c));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(Un + 2 * FS + c));
             }
         }
+
+        if (lane < 8) T.sinks[warp][lane] = 0.0;
 
         // ------------------------------------------------------------------ phase 0: load + primitives
         {
@@ -252,7 +259,7 @@ namespace
         __syncthreads();
 
         // ------------------------------------------------------------------ phases 2 + 3
-        const double h = mesh.spacing[b], inv_h = 1.0 / h;
+        const double h = mesh.spacing[b], inv_h = mesh.inv_spacing[b];
         const int li0 = STRIP * warp, lj = lane;
         const double dt_over_h = S.dt * inv_h;
         const double yc = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
@@ -280,7 +287,7 @@ namespace
             }
             const double x = 0.5 * (T.xv[li] + T.xv[li + 1]);
             double src[3], y1, y2;
-            source_terms(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2);
+            source_terms<FAST, true>(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2, T.sinks[warp]);
 
             double n0 = u[0] - ((FxHi[0] - FxLo[0]) + (hy[0] - FyLo[0])) * dt_over_h + src[0];
             double n1 = u[1] - ((FxHi[1] - FxLo[1]) + (hy[1] - FyLo[1])) * dt_over_h + src[1];
@@ -288,7 +295,7 @@ namespace
 
             if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
 
-            if (S.combine)
+            if (combine)
             {
                 const double w = 1.0 - S.rk_b0;
                 n0 = un[0] * S.rk_b0 + n0 * w;
@@ -297,7 +304,7 @@ namespace
             }
             Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
 
-            if (S.compute_dt) amax = dmax(amax, max_wavespeed(model, S, x, yc, y1, y2, n0, n1, n2));
+            if (compute_dt) amax = dmax(amax, max_wavespeed<FAST>(model, S, x, yc, y1, y2, n0, n1, n2));
         };
         auto load_cell = [&] (int r, double* u, double* u0, double& br, double* un)
         {
@@ -305,7 +312,7 @@ namespace
             u[0] = Uin[c]; u[1] = Uin[FS + c]; u[2] = Uin[2 * FS + c];
             br = has_buffer ? BR[c] : 0.0;
             u0[0] = has_buffer ? U0[c] : 0.0; u0[1] = has_buffer ? U0[FS + c] : 0.0; u0[2] = has_buffer ? U0[2 * FS + c] : 0.0;
-            un[0] = S.combine ? Un[c] : 0.0; un[1] = S.combine ? Un[FS + c] : 0.0; un[2] = S.combine ? Un[2 * FS + c] : 0.0;
+            un[0] = combine ? Un[c] : 0.0; un[1] = combine ? Un[FS + c] : 0.0; un[2] = combine ? Un[2 * FS + c] : 0.0;
         };
 
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
@@ -313,18 +320,18 @@ namespace
         if (warp == 0)
         {
             double F[3];
-            strip_x_face(T, strip_x_eos(T, model, S, SX, lj), inv_h, SX, lj, F);
+            strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
             T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
         }
         else if (warp == 1 && lane < SX)
         {
             double F[3];
-            strip_y_face(T, strip_y_eos(T, model, S, lane, SY), inv_h, lane, SY, F);
+            strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
             T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
         }
         double FxLo[3], FyLo[3];
-        strip_x_face(T, strip_x_eos(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
-        strip_y_face(T, strip_y_eos(T, model, S, li0, lj), inv_h, li0, lj, FyLo);
+        strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
+        strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FyLo);
 
         if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
         __syncthreads();
@@ -337,8 +344,8 @@ namespace
             load_cell(r - 1, u, u0, br, un);
             // (computing the sound speed / viscosity of the next row one iteration ahead was tried: the extra
             // live registers cost more than the added instruction-level parallelism gained, 72 -> 77 us)
-            strip_x_face(T, strip_x_eos(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew);
-            strip_y_face(T, strip_y_eos(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew);
+            strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew);
+            strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew);
             update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
             #pragma unroll
             for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
@@ -350,17 +357,16 @@ namespace
             FxHi[0] = T.XB[0][warp + 1][lj]; FxHi[1] = T.XB[1][warp + 1][lj]; FxHi[2] = T.XB[2][warp + 1][lj];
             update_cell(STRIP - 1, u, u0, br, un, FxLo, FxHi, FyLo);
         }
-        const double dtmin = S.compute_dt ? h / amax : 1e300;
 
         // ------------------------------------------------------------------ fold the CTA's sums
         // per-warp shuffle tree over the groups that can be non-zero, then 4 warps through shared memory
-        const bool sinks_touched = __any_sync(0xffffffffu, sums[ACC_MASS] != 0.0 || sums[ACC_MASS + 1] != 0.0);
+        __syncwarp();
         #pragma unroll
-        for (int k = 0; k < NUM_SUMS; ++k)
+        for (int k = GRV_FX; k < NUM_SUMS; ++k)
         {
-            const bool sink_group = k < GRV_FX, buffer_group = k >= BUF_M;
+            const bool buffer_group = k >= BUF_M;
             double v = 0.0;
-            if ((! sink_group || sinks_touched) && (! buffer_group || has_buffer))      // warp-uniform
+            if (! buffer_group || has_buffer)      // warp-uniform
             {
                 v = sums[k];
                 #pragma unroll
@@ -368,10 +374,11 @@ namespace
             }
             if (lane == 0) T.red[warp][k] = v;
         }
+        if (lane < GRV_FX) T.red[warp][lane] = T.sinks[warp][lane];
         {
-            double m = dtmin;
+            double m = amax;
             #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = dmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            for (int o = 16; o > 0; o >>= 1) m = dmax(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) T.red[warp][NUM_SUMS] = m;
         }
         __syncthreads();
@@ -380,7 +387,8 @@ namespace
             const int k = threadIdx.x;
             double* row = partials + size_t(blockIdx.x) * ROW;
             double a = T.red[0][k], bq = T.red[1][k], cq = T.red[2][k], d = T.red[3][k];
-            row[k] = k == NUM_SUMS ? dmin(dmin(a, bq), dmin(cq, d)) : ((a + bq) + (cq + d)) * (h * h);
+            // min over cells of h / wavespeed = h / max wavespeed: one division per tile
+            row[k] = k == NUM_SUMS ? (compute_dt ? h / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (h * h);
         }
     }
 }
