@@ -88,12 +88,12 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
  */
 __device__ __forceinline__ double plm_from_differences(double dl, double dr, double theta)
 {
-    double al = fabs(dl), ar = fabs(dr);
-    double m = dmin(theta * dmin(al, ar), 0.5 * (al + ar));
-    int hl = __double2hiint(dl), hr = __double2hiint(dr);
-    int hi = (hl ^ hr) >= 0 ? (__double2hiint(m) | (hl & 0x80000000)) : 0;
-    int lo = (hl ^ hr) >= 0 ? __double2loint(m) : 0;
-    return __hiloint2double(hi, lo);
+    // signed throughout: t = theta * (the smaller of dl, dr in magnitude) and h = (dl + dr) / 2 carry the common
+    // sign, so the limited slope is whichever of them is smaller in magnitude -- no sign to re-insert
+    double h = 0.5 * (dl + dr);
+    double t = theta * (fabs(dl) < fabs(dr) ? dl : dr);
+    double r = fabs(t) < fabs(h) ? t : h;
+    return (__double2hiint(dl) ^ __double2hiint(dr)) >= 0 ? r : 0.0;
 }
 
 __device__ __forceinline__ double plm_diff(double yl, double y0, double yr, double theta)

@@ -70,6 +70,16 @@ namespace
         int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
     };
 
+    /** Everything a stage_strip CTA needs to find its data, in one 48-byte record per tile (one load instead of
+     *  the dependent chain regular list -> neighbour table / tile flags). */
+    struct __align__(16) tile_info_t
+    {
+        int b;                          // block
+        int n9[9];                      // same-level neighbour ids, (di + 1) * 3 + (dj + 1)
+        int flags;                      // bit 0: the buffer-zone rate is non-zero somewhere in the tile
+        int pad;
+    };
+
     struct fail_dev_t
     {
         unsigned int count;
@@ -826,6 +836,7 @@ struct device_solver_t::impl_t
     bool fast_eos = false;                  // default equation of state / viscosity: branch-free kernel variant
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     unsigned char* d_tile_flags = nullptr;
+    tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     std::vector<int> regular, irregular, gradient_blocks;
     int* d_regular = nullptr;
     int* d_irregular = nullptr;
@@ -980,6 +991,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->mesh.gslot = device_upload(gslot);
     impl->mesh.U0 = device_upload(sd.initial_conserved_u);
     impl->mesh.br = device_upload(sd.buffer_rate_field);
+    std::vector<unsigned char> tile_flags_host;
     if (impl->tile_x)
     {
         // static per-tile flags: bit 0 = the buffer-zone rate is non-zero somewhere in the tile
@@ -995,8 +1007,24 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
                 flags[size_t(b) * tpb + t] = any;
             }
         impl->d_tile_flags = device_upload(flags);
+        tile_flags_host = flags;
     }
     impl->d_regular = device_upload(impl->regular);
+    if (impl->tile_x)
+    {
+        const int tpb = (N / impl->tile_x) * (N / impl->tile_y);
+        auto info = std::vector<tile_info_t>(impl->regular.size() * tpb);
+        for (size_t r = 0; r < impl->regular.size(); ++r)
+            for (int t = 0; t < tpb; ++t)
+            {
+                auto& ti = info[r * tpb + t];
+                ti.b = impl->regular[r];
+                for (int k = 0; k < 9; ++k) ti.n9[k] = nbr9[size_t(ti.b) * 9 + k];
+                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t];
+                ti.pad = 0;
+            }
+        impl->d_tile_info = device_upload(info);
+    }
     impl->d_irregular = device_upload(impl->irregular);
     impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
 
@@ -1134,7 +1162,7 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.inv_spacing, (void*) impl->mesh.nbr,
                    (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
                    (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
-                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_fail})
+                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_tile_info, (void*) impl->d_fail})
         if (p) cudaFree(p);
     for (auto p : impl->owned) cudaFree(p);
     for (auto p : {(void*) impl->d_send_entries, (void*) impl->d_recv_entries, (void*) impl->d_send_buffer, (void*) impl->d_recv_buffer,
@@ -1284,7 +1312,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
                                   : (impl->fast_eos ? stage_strip<4, 0, true, 0> : stage_strip<4, 0, false, 0>);
             if (N == 64 && impl->fast_eos && stage_mode == 1) kernel = stage_strip<4, 64, true, 1>;
             if (N == 64 && impl->fast_eos && stage_mode == 2) kernel = stage_strip<4, 64, true, 2>;
-            kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, list, impl->d_tile_flags,
+            kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_tile_info + size_t(first) * tpb,
                 in.data, un_data, out.data, tiles, impl->d_fail + slot);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);

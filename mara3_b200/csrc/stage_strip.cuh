@@ -6,7 +6,7 @@
  *
  *   CTA  = 4 warps on a 16 x 32 tile; lane <-> column j (the contiguous direction), warp w owns the
  *          strip of rows 4w .. 4w+3.
- *   P0   tile + 2-cell halo: coalesced row loads (15-30 in flight per thread), conserved -> primitive,
+ *   P0   tile + 2-cell halo as 360 sixteen-byte chunks (9 LDG.128 per thread), conserved -> primitive,
  *        into shared memory.
  *   P1   PLM differences on tile + 1 halo, marching down the strip with the x-stencil in registers.
  *   P2/3 a software-pipelined loop down the strip: each iteration issues the loads for the update of
@@ -80,8 +80,7 @@ namespace
 
     template<int MIN_CTAS, int NB, bool FAST, int MODE>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
-        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
-        const unsigned char* __restrict__ tile_flags,
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
         double* partials, fail_dev_t* fail)
     {
@@ -93,20 +92,22 @@ namespace
         const bool combine = MODE == 0 ? S.combine != 0 : MODE == 2, compute_dt = MODE == 0 ? S.compute_dt != 0 : MODE == 2;
         const int N = NB ? NB : mesh.N;       // NB: block size known at compile time (addresses fold into immediates)
         const int tiles_y = N / SY, tiles_per_block = (N / SX) * tiles_y;
-        const int r_index = blockIdx.x / tiles_per_block;
-        const int b  = regular_list[r_index];
+        const int4* ti4 = reinterpret_cast<const int4*>(tile_info + blockIdx.x);
+        const int4 tiA = __ldg(ti4), tiB = __ldg(ti4 + 1), tiC = __ldg(ti4 + 2);
+        const int n9[9] = {tiA.y, tiA.z, tiA.w, tiB.x, tiB.y, tiB.z, tiB.w, tiC.x, tiC.y};
+        const int b  = tiA.x;
         const int t  = blockIdx.x % tiles_per_block;
         const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
         const size_t FS = mesh.FS;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const bool has_buffer = tile_flags[size_t(b) * tiles_per_block + t] & 1;
+        const bool has_buffer = tiC.z & 1;
 
         // one "generation" of resident CTAs ahead: pull the tile that a later CTA of this SM slot will load from HBM into L2
         {
             const int ahead = blockIdx.x + mesh.prefetch_ahead;
             if (mesh.prefetch_ahead > 0 && ahead < gridDim.x && threadIdx.x < 96)
             {
-                const int rb = regular_list[ahead / tiles_per_block], rt = ahead % tiles_per_block;
+                const int rb = __ldg(&tile_info[ahead].b), rt = ahead % tiles_per_block;
                 const int f = threadIdx.x >> 5, row = (threadIdx.x & 31) >> 1, half = threadIdx.x & 1;
                 const size_t c = (size_t(rb) * N + ((rt / tiles_y) * SX + row)) * N + (rt % tiles_y) * SY + 16 * half;
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(Uin + f * FS + c));
@@ -135,32 +136,34 @@ namespace
 
         // ------------------------------------------------------------------ phase 0: load + primitives
         {
-            // region column c <-> global column j0 - 2 + c; group A: c = lane, group B: c = 32 + lane (lane < 4);
-            // region row r = warp + 4 k <-> global row i0 - 2 + r.  Only rows 0, 1 (k = 0) can lie in the low-x
-            // neighbour and rows 18, 19 (k = 4) in the high-x neighbour.
-            const int gjA = j0 - 2 + lane, gjB = j0 + 30 + lane;
-            const int djA = gjA < 0 ? -1 : 0, djB = gjB >= N ? 1 : 0;
-            const long colA = gjA - djA * N, colB = gjB - djB * N;
-            const int* n9 = mesh.nbr9 + size_t(b) * 9;
-            const long NN = long(N) * N;
-            const bool low = i0 == 0 && warp < 2, high = i0 + SX == N && warp >= 2;
-            const long in_block = long(i0 - 2 + warp) * N, stride = 4L * N;
-            const long baseA = n9[3 + djA + 1] * NN + colA + in_block, baseB = n9[3 + djB + 1] * NN + colB + in_block;
-            const long lowA  = low  ? n9[0 + djA + 1] * NN + colA + long(N - 2 + warp) * N : baseA;
-            const long lowB  = low  ? n9[0 + djB + 1] * NN + colB + long(N - 2 + warp) * N : baseB;
-            const long highA = high ? n9[6 + djA + 1] * NN + colA + long(warp - 2) * N : baseA + 4 * stride;
-            const long highB = high ? n9[6 + djB + 1] * NN + colB + long(warp - 2) * N : baseB + 4 * stride;
+            // The (SX + 4) x (SY + 4) region is 20 rows of 18 sixteen-byte chunks (two cells in y); columns j0 - 2 and
+            // N are even, so a chunk never straddles two blocks.  Thread <-> (row rr + 7 k, chunk cc), k = 0, 1, 2:
+            // 9 LDG.128 per thread, conserved -> primitive for two cells at a time, 9 STS.128.
+            const int rr = threadIdx.x / 18, cc = threadIdx.x - 18 * rr;
+            const int gj = j0 - 2 + 2 * cc;
+            const int dj = gj < 0 ? -1 : (gj >= N ? 1 : 0);
+            const long col = gj - dj * N;
+            const int nlo  = dj < 0 ? n9[0] : (dj > 0 ? n9[2] : n9[1]);
+            const int nmid = dj < 0 ? n9[3] : (dj > 0 ? n9[5] : n9[4]);
+            const int nhi  = dj < 0 ? n9[6] : (dj > 0 ? n9[8] : n9[7]);
             const double* __restrict__ U1 = Uin + FS;
             const double* __restrict__ U2 = Uin + 2 * FS;
-            double uA[5][3], uB[5][3];
+            double2 uc[3][3];
 
             #pragma unroll
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < 3; ++k)
             {
-                const long cA = k == 0 ? lowA : (k == 4 ? highA : baseA + k * stride);
-                const long cB = k == 0 ? lowB : (k == 4 ? highB : baseB + k * stride);
-                uA[k][0] = Uin[cA]; uA[k][1] = U1[cA]; uA[k][2] = U2[cA];
-                if (lane < 4) { uB[k][0] = Uin[cB]; uB[k][1] = U1[cB]; uB[k][2] = U2[cB]; }
+                const int row = rr + 7 * k;
+                if (rr < 7 && row < SX + 4)
+                {
+                    const int gi = i0 - 2 + row;
+                    const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
+                    const int nb = di < 0 ? nlo : (di > 0 ? nhi : nmid);
+                    const long c = (long(nb) * N + (gi - di * N)) * N + col;
+                    uc[k][0] = *reinterpret_cast<const double2*>(Uin + c);
+                    uc[k][1] = *reinterpret_cast<const double2*>(U1 + c);
+                    uc[k][2] = *reinterpret_cast<const double2*>(U2 + c);
+                }
             }
             // coordinate tables while the loads are in flight
             {
@@ -204,15 +207,16 @@ namespace
                 }
             }
             #pragma unroll
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < 3; ++k)
             {
-                const int r = warp + 4 * k;
-                prim_t p = cons_to_prim(uA[k][0], uA[k][1], uA[k][2]);
-                T.P[0][r][lane] = p.s; T.P[1][r][lane] = p.vx; T.P[2][r][lane] = p.vy;
-                if (lane < 4)
+                const int row = rr + 7 * k;
+                if (rr < 7 && row < SX + 4)
                 {
-                    prim_t q = cons_to_prim(uB[k][0], uB[k][1], uB[k][2]);
-                    T.P[0][r][32 + lane] = q.s; T.P[1][r][32 + lane] = q.vx; T.P[2][r][32 + lane] = q.vy;
+                    // iso2d::recover_primitive (physics_iso2d.hpp:351-362) for the chunk's two cells
+                    const double ia = fast_rcp(uc[k][0].x), ib = fast_rcp(uc[k][0].y);
+                    *reinterpret_cast<double2*>(&T.P[0][row][2 * cc]) = uc[k][0];
+                    *reinterpret_cast<double2*>(&T.P[1][row][2 * cc]) = make_double2(uc[k][1].x * ia, uc[k][1].y * ib);
+                    *reinterpret_cast<double2*>(&T.P[2][row][2 * cc]) = make_double2(uc[k][2].x * ia, uc[k][2].y * ib);
                 }
             }
         }
