@@ -312,11 +312,14 @@ namespace
         };
         auto load_cell = [&] (int r, double* u, double* u0, double& br, double* un)
         {
+            // volatile: issued here, a whole iteration before their use (ptxas otherwise sinks them below the
+            // x-face to save registers, and the update then waits on L2)
             const size_t c = c0 + size_t(r) * N;
-            u[0] = Uin[c]; u[1] = Uin[FS + c]; u[2] = Uin[2 * FS + c];
-            br = has_buffer ? BR[c] : 0.0;
-            u0[0] = has_buffer ? U0[c] : 0.0; u0[1] = has_buffer ? U0[FS + c] : 0.0; u0[2] = has_buffer ? U0[2 * FS + c] : 0.0;
-            un[0] = combine ? Un[c] : 0.0; un[1] = combine ? Un[FS + c] : 0.0; un[2] = combine ? Un[2 * FS + c] : 0.0;
+            auto ldv = [] (const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; };
+            u[0] = ldv(Uin + c); u[1] = ldv(Uin + FS + c); u[2] = ldv(Uin + 2 * FS + c);
+            br = 0.0; u0[0] = u0[1] = u0[2] = 0.0; un[0] = un[1] = un[2] = 0.0;
+            if (has_buffer) { br = ldv(BR + c); u0[0] = ldv(U0 + c); u0[1] = ldv(U0 + FS + c); u0[2] = ldv(U0 + 2 * FS + c); }
+            if (combine) { un[0] = ldv(Un + c); un[1] = ldv(Un + FS + c); un[2] = ldv(Un + 2 * FS + c); }
         };
 
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
@@ -340,24 +343,24 @@ namespace
         if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
         __syncthreads();
 
-        // steady state: the loads for cell r - 1 are issued first and hidden behind the two faces of row r
+        // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
+        // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
+        double u[3], u0[3], un[3], br;
+        load_cell(0, u, u0, br, un);
         #pragma unroll 1
         for (int r = 1; r < STRIP; ++r)
         {
-            double u[3], u0[3], un[3], br, FxNew[3], FyNew[3];
-            load_cell(r - 1, u, u0, br, un);
-            // (computing the sound speed / viscosity of the next row one iteration ahead was tried: the extra
-            // live registers cost more than the added instruction-level parallelism gained, 72 -> 77 us)
+            double FxNew[3], FyNew[3];
             strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew);
             strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew);
             update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
+            load_cell(r, u, u0, br, un);
             #pragma unroll
             for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
         }
         // epilogue: the last row's high-x flux is the first face of the next strip (or the boundary row)
         {
-            double u[3], u0[3], un[3], br, FxHi[3];
-            load_cell(STRIP - 1, u, u0, br, un);
+            double FxHi[3];
             FxHi[0] = T.XB[0][warp + 1][lj]; FxHi[1] = T.XB[1][warp + 1][lj]; FxHi[2] = T.XB[2][warp + 1][lj];
             update_cell(STRIP - 1, u, u0, br, un, FxLo, FxHi, FyLo);
         }
