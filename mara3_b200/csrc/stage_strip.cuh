@@ -236,14 +236,17 @@ namespace
             #pragma unroll 1
             for (int g = g0; g < g1; ++g)
             {
+                // all nine loads first: behind a store to T.G the compiler will not hoist a load from T.P
+                double pp[3], yl[3], yr[3];
+                #pragma unroll
+                for (int q = 0; q < 3; ++q) { pp[q] = T.P[q][g + 2][lane + 1]; yl[q] = T.P[q][g + 1][lane]; yr[q] = T.P[q][g + 1][lane + 2]; }
                 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                 {
-                    const double pp = T.P[q][g + 2][lane + 1];
-                    const double dr = pp - pc[q];
+                    const double dr = pp[q] - pc[q];
                     T.G[q][g][lane]     = plm_from_differences(dl[q], dr, S.theta);
-                    T.G[3 + q][g][lane] = plm_from_differences(pc[q] - T.P[q][g + 1][lane], T.P[q][g + 1][lane + 2] - pc[q], S.theta);
-                    pc[q] = pp; dl[q] = dr;
+                    T.G[3 + q][g][lane] = plm_from_differences(pc[q] - yl[q], yr[q] - pc[q], S.theta);
+                    pc[q] = pp[q]; dl[q] = dr;
                 }
             }
             // gradient columns 32, 33: 36 cells, taken by the two warps with one row less
@@ -322,6 +325,9 @@ namespace
             if (combine) { un[0] = ldv(Un + c); un[1] = ldv(Un + FS + c); un[2] = ldv(Un + 2 * FS + c); }
         };
 
+        double u[3], u0[3], un[3], br;
+        load_cell(0, u, u0, br, un);        // in flight during the prologue
+
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
         // faces of strip row 0, whose x-flux is also the high-x flux of the strip below
         if (warp == 0)
@@ -345,8 +351,6 @@ namespace
 
         // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
         // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
-        double u[3], u0[3], un[3], br;
-        load_cell(0, u, u0, br, un);
         #pragma unroll 1
         for (int r = 1; r < STRIP; ++r)
         {
