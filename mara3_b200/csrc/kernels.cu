@@ -68,6 +68,11 @@ namespace
         const double* br;               // [FS]
         size_t GS;                      // gradient scratch stride
         int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
+        // multi-GPU: CTAs from first_wait_cta on update blocks with ghost neighbours and wait until the guard-zone
+        // unpack (running beside this kernel on the exchange stream) has published ready_value
+        int first_wait_cta;
+        const unsigned long long* ready_flag;
+        unsigned long long ready_value;
     };
 
     /** Everything a stage_strip CTA needs to find its data, in one 48-byte record per tile (one load instead of
@@ -570,6 +575,36 @@ namespace
         st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
     }
 
+    /** Everything of a stage input except dt (written later, when the CFL reduction is known). */
+    __device__ void fill_stage_but_dt(stage_t& st, double time, double theta, const two_body_t& b, double rk_b0, int combine, int compute_dt)
+    {
+        st.time = time; st.theta = theta;
+        st.x1 = b.body1.x; st.y1 = b.body1.y; st.m1 = b.body1.mass; st.vx1 = b.body1.vx; st.vy1 = b.body1.vy;
+        st.x2 = b.body2.x; st.y2 = b.body2.y; st.m2 = b.body2.mass; st.vx2 = b.body2.vx; st.vy2 = b.body2.vy;
+        st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
+    }
+
+    /**
+     * The slow half of prepare_next, off the critical path (side stream): body positions (a Kepler solve and a
+     * handful of divisions, ~9 us for one thread) for stages whose TIME is already known.  `src` is the first
+     * stage of a step with (time, dt) = (t, dt): the step's second stage `second` runs at t + dt and the first
+     * stage of the step after it, `following`, at t/2 + ((t + dt) + dt)/2 (scheme.cpp:1036, 1055).  Either may be null.
+     */
+    __global__ void prepare_positions(step_config_t cfg, const stage_t* __restrict__ src, stage_t* second, stage_t* following)
+    {
+        const double t = src->time, dt = src->dt;
+        if (threadIdx.x == 0 && second)
+        {
+            const double tb = t + dt;
+            fill_stage_but_dt(*second, tb, cfg.theta, two_body_state(cfg.elements, tb), 0.5, 1, ! cfg.fixed_dt);
+        }
+        if (threadIdx.x == 1 && following)
+        {
+            const double tn = t * 0.5 + ((t + dt) + dt) * 0.5;
+            fill_stage_but_dt(*following, tn, cfg.theta, two_body_state(cfg.elements, tn), 0.0, 0, 0);
+        }
+    }
+
     /** Optional epilogue of finish_stage (single rank): what prepare_next does, in the last CTA of the step's last stage. */
     struct prepare_args_t
     {
@@ -696,13 +731,15 @@ namespace
 
         // stage inputs of the next step (see prepare_next): one thread per stage
         __syncthreads();
-        if (threadIdx.x == 96 || threadIdx.x == 128)
+        if (threadIdx.x == 96 || threadIdx.x == 97)
         {
             const double t = prep.current_a->time, dt = prep.current_a->dt;
             const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
             const double dt_next = prep.cfg.fixed_dt ? prep.cfg.recommended_time_step : prep.cfg.cfl_number * dt_min_all;
-            if (threadIdx.x == 96) fill_stage(*prep.next_a, t_next, dt_next, prep.cfg.theta, two_body_state(prep.cfg.elements, t_next), 0.0, 0, 0);
-            else fill_stage(*prep.next_b, t_next + dt_next, dt_next, prep.cfg.theta, two_body_state(prep.cfg.elements, t_next + dt_next), 0.5, 1, ! prep.cfg.fixed_dt);
+            // time and dt only: the body positions of next_a were prepared a step ago, those of next_b follow on the
+            // side stream while next_a runs (prepare_positions)
+            if (threadIdx.x == 96) { prep.next_a->time = t_next; prep.next_a->dt = dt_next; }
+            else { prep.next_b->time = t_next + dt_next; prep.next_b->dt = dt_next; }
         }
     }
 
@@ -767,6 +804,147 @@ namespace
             int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
             size_t u = q * FS + (size_t(e.block) * N + i) * N + j;
             if (pack) buffer[e.offset + k] = U[u]; else U[u] = buffer[e.offset + k];
+        }
+    }
+
+    // =======================================================================
+    // Peer-memory guard-zone exchange (NVLink loads / stores, no NCCL in the step loop)
+    // =======================================================================
+    constexpr int MAX_PEERS = 16;
+
+    /** Mapped (CUDA IPC) pointers into every rank's mailbox; index = rank.  [me] points at the local mailbox. */
+    struct peer_table_t
+    {
+        double* recv[MAX_PEERS][2];                     // guard-zone landing buffers, one per exchange parity
+        unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
+        stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
+        unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
+    };
+
+    __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
+    {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    }
+
+    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+
+    /**
+     * Send side of extend() across GPUs (scheme.cpp:132-142): each CTA copies one strip / corner of an owned
+     * block straight into the destination rank's landing buffer (entry.pad = destination rank, entry.offset =
+     * position in ITS buffer); the last CTA to finish raises this rank's flag on every destination.
+     */
+    __global__ void __launch_bounds__(128) halo_push(const halo_entry_dev_t* __restrict__ entries, const double* __restrict__ U, size_t FS, int N,
+        peer_table_t peers, int parity, int me, unsigned int dest_mask, unsigned long long counter, int* ticket)
+    {
+        __shared__ int is_last;
+        const halo_entry_dev_t e = entries[blockIdx.x];
+        const int cells = e.ni * e.nj;
+        double* __restrict__ dst = peers.recv[e.pad][parity] + e.offset;
+
+        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
+        {
+            int q = k / cells, c = k % cells;
+            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
+            dst[k] = U[q * FS + (size_t(e.block) * N + i) * N + j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
+        __syncthreads();
+        if (! is_last) return;
+        __threadfence_system();
+        if (threadIdx.x < MAX_PEERS && ((dest_mask >> threadIdx.x) & 1u)) store_release_sys(peers.halo_flag[threadIdx.x] + me, counter);
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+
+    /** Receive side: wait for the source rank's flag (entry.pad = source rank), then scatter its strip into the ghost block. */
+    __global__ void __launch_bounds__(128) halo_wait_unpack(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
+        const double* __restrict__ landing, const unsigned long long* flags, unsigned long long counter, int* ticket, unsigned long long* ready)
+    {
+        __shared__ int is_last;
+        const halo_entry_dev_t e = entries[blockIdx.x];
+        if (threadIdx.x == 0)
+        {
+            while (load_acquire_sys(flags + e.pad) < counter) { }
+        }
+        __syncthreads();
+        const int cells = e.ni * e.nj;
+
+        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
+        {
+            int q = k / cells, c = k % cells;
+            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
+            U[q * FS + (size_t(e.block) * N + i) * N + j] = __ldcg(landing + e.offset + k);     // written by a peer: not through L1
+        }
+        // the last CTA tells the stage kernel's boundary tiles that every ghost block is in place
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
+        __syncthreads();
+        if (is_last && threadIdx.x == 0)
+        {
+            *ticket = 0;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(ready), "l"(counter) : "memory");
+        }
+    }
+
+    /**
+     * prepare_next for several ranks without NCCL: deliver this rank's two stage results to every rank's
+     * mailbox, wait for everybody else's, fold them in rank order (every rank gets the same bits) and write
+     * the stage inputs of the next step.
+     */
+    __global__ void __launch_bounds__(128) prepare_next_peer(const stage_result_t* __restrict__ local, peer_table_t peers, int me, int nranks,
+        int slot_stride, int slot_a, int slot_b, unsigned long long counter,
+        step_config_t cfg, const stage_t* __restrict__ current, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
+    {
+        __shared__ double dt_min_b;
+        constexpr int words = sizeof(stage_result_t) / sizeof(double);
+
+        for (int k = threadIdx.x; k < nranks * 2 * words; k += blockDim.x)
+        {
+            const int p = k / (2 * words), slot = (k / words) % 2 ? slot_b : slot_a, w = k % words;
+            reinterpret_cast<double*>(peers.results[p] + size_t(me) * slot_stride + slot)[w] = reinterpret_cast<const double*>(local + slot)[w];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < nranks)
+        {
+            if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
+            if (threadIdx.x != me) while (load_acquire_sys(peers.result_flag[me] + threadIdx.x) < counter) { }
+        }
+        __syncthreads();
+
+        const int k = threadIdx.x;
+        if (k < 2)
+        {
+            const int slot = k == 0 ? slot_a : slot_b;
+            stage_result_t r = stage_result_t();
+            r.dt_min = 1e300;
+            for (int p = 0; p < nranks; ++p)
+            {
+                const double* q = reinterpret_cast<const double*>(peers.results[me] + size_t(p) * slot_stride + slot);
+                for (int c = 0; c < 16; ++c) r.sums[c] += __ldcg(q + c);
+                r.work[0] += __ldcg(q + 16);
+                r.work[1] += __ldcg(q + 17);
+                r.dt_min = dmin(r.dt_min, __ldcg(q + 18));
+                r.num_negative += __ldcg(reinterpret_cast<const unsigned int*>(q + 19));
+            }
+            host_results[slot] = r;
+            if (k == 1) dt_min_b = r.dt_min;
+        }
+        __syncthreads();
+        if (k < 2)
+        {
+            const double t = current[slot_a].time, dt = current[slot_a].dt;
+            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
+            const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
+            if (k == 0) { next_a->time = t_next; next_a->dt = dt_next; }        // positions: prepare_positions, off the critical path
+            else        { next_b->time = t_next + dt_next; next_b->dt = dt_next; }
         }
     }
 
@@ -863,6 +1041,8 @@ struct device_solver_t::impl_t
     cudaStream_t finish_stream = nullptr;       // finish_stage of a step's first stage runs here, beside the second stage
     cudaEvent_t stage_done = nullptr, side_finish_done = nullptr;
     prepare_args_t pending_prepare = prepare_args_t();
+    cudaEvent_t fast_prepare_done = nullptr, positions_done[2] = {nullptr, nullptr};
+    bool fresh_pipeline = false;                // the host uploaded this step's inputs: nobody has prepared the next step's positions
     int* d_counters = nullptr;                  // per-block tile tickets, then the finish ticket
     size_t partial_rows = 0;
     cudaEvent_t step_done[2] = {nullptr, nullptr};
@@ -874,6 +1054,34 @@ struct device_solver_t::impl_t
     halo_entry_dev_t* d_recv_entries = nullptr;
     double* d_send_buffer = nullptr;
     double* d_recv_buffer = nullptr;
+    // M3B_TRACE=1: CUDA events at the marks of launch_step_async, averaged and printed by the destructor
+    bool trace = false;
+    std::vector<std::vector<cudaEvent_t>> trace_steps;
+    std::vector<cudaEvent_t> trace_current;
+    std::vector<const char*> trace_names;
+    void mark(cudaStream_t s, const char* name)
+    {
+        if (! trace || trace_steps.size() >= 400) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+        if (trace_steps.empty()) trace_names.push_back(name);
+        trace_current.push_back(e);
+    }
+    void end_step() { if (trace && ! trace_current.empty()) { trace_steps.push_back(trace_current); trace_current.clear(); } }
+    // peer-memory transport (set up in set_communicator; falls back to NCCL send / recv if CUDA IPC is unavailable)
+    bool peer_transport = false;
+    void* mailbox = nullptr;                        // this rank's mailbox: flags, results of all ranks, two landing buffers
+    std::vector<void*> peer_mailbox;                // cudaIpcOpenMemHandle mappings (null for this rank)
+    peer_table_t peers = peer_table_t();
+    halo_entry_dev_t* d_push_entries = nullptr;     // send entries addressed into the destination's landing buffer
+    std::vector<halo_entry_dev_t> send_entries_host;
+    std::vector<size_t> send_starts_host, recv_starts_host;
+    size_t recv_total = 0;
+    unsigned int dest_mask = 0;
+    unsigned long long exchange_counter = 0, step_counter = 0;
+    int* d_push_ticket = nullptr;                   // [0] halo_push, [1] halo_wait_unpack
+    unsigned long long* d_ready = nullptr;          // number of the last exchange whose ghost blocks are complete
+    bool defer_unpack = false;                      // set around the exchange of a stage launched with in-kernel waiting
+    bool in_kernel_wait = false;                    // boundary tiles wait inside the stage kernel (enough interior work to hide the exchange)
     std::vector<const double*> send_ptr;
     std::vector<double*> recv_ptr;
     std::vector<size_t> send_count, recv_count;
@@ -1053,6 +1261,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->stage_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->side_finish_done, cudaEventDisableTiming));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->fast_prepare_done, cudaEventDisableTiming));
+    for (auto& e : impl->positions_done) M3B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     M3B_CUDA(cudaMalloc(&impl->d_counters, 2 * sizeof(int)));
     M3B_CUDA(cudaMemset(impl->d_counters, 0, 2 * sizeof(int)));
     impl->partial_rows = max_rows;
@@ -1069,6 +1279,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     }
     // Measured on 4096^2 (profiles/): +4 % at 4 GPUs but -27 % at 8 GPUs, where the NCCL kernel spins on SMs until
     // the slowest peer arrives and the boundary launch adds a partial wave; off unless asked for.
+    if (const char* e = std::getenv("M3B_TRACE")) impl->trace = std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_OVERLAP_EXCHANGE")) impl->overlap_exchange = std::atoi(e) != 0;
     M3B_CUDA(cudaEventCreateWithFlags(&impl->input_ready, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->halo_ready, cudaEventDisableTiming));
@@ -1098,7 +1309,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
                     e.block = r.block;
                     e.i0 = r.di < 0 ? N - 2 : 0; e.ni = r.di ? 2 : N;
                     e.j0 = r.dj < 0 ? N - 2 : 0; e.nj = r.dj ? 2 : N;
-                    e.pad = 0;
+                    e.pad = p;              // the other side's rank
                     e.offset = offset;
                     offset += size_t(3) * e.ni * e.nj;
                     entries.push_back(e);
@@ -1114,6 +1325,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         impl->num_recv_entries = int(recv_entries.size());
         impl->d_send_entries = device_upload(send_entries);
         impl->d_recv_entries = device_upload(recv_entries);
+        impl->send_entries_host = send_entries;
+        impl->send_starts_host = send_starts;
+        impl->recv_starts_host = recv_starts;
+        impl->recv_total = recv_total;
         M3B_CUDA(cudaMalloc(&impl->d_send_buffer, std::max<size_t>(1, send_total) * sizeof(double)));
         M3B_CUDA(cudaMalloc(&impl->d_recv_buffer, std::max<size_t>(1, recv_total) * sizeof(double)));
         for (int p = 0; p < part.nranks; ++p)
@@ -1168,6 +1383,25 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->d_send_entries, (void*) impl->d_recv_entries, (void*) impl->d_send_buffer, (void*) impl->d_recv_buffer,
                    (void*) impl->d_results_local, (void*) impl->d_results_all})
         if (p) cudaFree(p);
+    if (impl->trace && impl->trace_steps.size() > 20)
+    {
+        const size_t n = impl->trace_names.size(), first = 10;
+        auto acc = std::vector<double>(n, 0.0);
+        size_t used = 0;
+        for (size_t k = first; k < impl->trace_steps.size(); ++k)
+        {
+            auto& ev = impl->trace_steps[k];
+            if (ev.size() != n) continue;
+            ++used;
+            for (size_t m = 1; m < n; ++m) { float ms = 0; cudaEventElapsedTime(&ms, ev[m - 1], ev[m]); acc[m] += ms; }
+            if (k + 1 < impl->trace_steps.size() && impl->trace_steps[k + 1].size() == n)
+            { float ms = 0; cudaEventElapsedTime(&ms, ev[n - 1], impl->trace_steps[k + 1][0]); acc[0] += ms; }
+        }
+        std::fprintf(stderr, "[m3b trace rank %d] %zu steps, us per step:\n  %-28s %8.1f\n", rank_, used, "(gap to next step)", acc[0] / used * 1e3);
+        for (size_t m = 1; m < n; ++m) std::fprintf(stderr, "  -> %-25s %8.1f\n", impl->trace_names[m], acc[m] / used * 1e3);
+    }
+    for (auto p : impl->peer_mailbox) if (p) cudaIpcCloseMemHandle(p);
+    for (auto p : {(void*) impl->mailbox, (void*) impl->d_push_entries, (void*) impl->d_push_ticket, (void*) impl->d_ready}) if (p) cudaFree(p);
     if (impl->h_results_all) cudaFreeHost(impl->h_results_all);
     if (impl->h_stage_ring) cudaFreeHost(impl->h_stage_ring);
     for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
@@ -1175,6 +1409,8 @@ device_solver_t::~device_solver_t()
     for (auto e : impl->step_done) if (e) cudaEventDestroy(e);
     if (impl->stage_done) cudaEventDestroy(impl->stage_done);
     if (impl->side_finish_done) cudaEventDestroy(impl->side_finish_done);
+    if (impl->fast_prepare_done) cudaEventDestroy(impl->fast_prepare_done);
+    for (auto e : impl->positions_done) if (e) cudaEventDestroy(e);
     if (impl->finish_stream) cudaStreamDestroy(impl->finish_stream);
     if (impl->input_ready) cudaEventDestroy(impl->input_ready);
     if (impl->halo_ready) cudaEventDestroy(impl->halo_ready);
@@ -1291,10 +1527,16 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
     int fused_ctas = num_fused * tpb;
     exchange = exchange && num_ranks > 1;
+    impl->mark(s, "stage begin");
+    bool waiting_tiles = false;
     if (exchange && ! impl->overlap_exchange)
     {
+        waiting_tiles = impl->peer_transport && impl->in_kernel_wait && impl->strip && num_general == 0 && impl->num_recv_entries > 0;
+        impl->defer_unpack = waiting_tiles;
         exchange_on(stream_, const_cast<device_field_t&>(in));     // plain ordering: exchange, then every block
+        impl->defer_unpack = false;
         exchange = false;
+        impl->mark(s, "exchange done");
     }
 
     // blocks [first, first + count) of the regular list: tile rows, block rows and tickets are indexed by list position
@@ -1312,7 +1554,11 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
                                   : (impl->fast_eos ? stage_strip<4, 0, true, 0> : stage_strip<4, 0, false, 0>);
             if (N == 64 && impl->fast_eos && stage_mode == 1) kernel = stage_strip<4, 64, true, 1>;
             if (N == 64 && impl->fast_eos && stage_mode == 2) kernel = stage_strip<4, 64, true, 2>;
-            kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(impl->mesh, impl->model, st, impl->d_tile_info + size_t(first) * tpb,
+            mesh_dev_t mesh = impl->mesh;
+            mesh.first_wait_cta = waiting_tiles ? std::max(0, impl->num_interior - first) * tpb : 0x7fffffff;
+            mesh.ready_flag = impl->d_ready;
+            mesh.ready_value = impl->exchange_counter;
+            kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(mesh, impl->model, st, impl->d_tile_info + size_t(first) * tpb,
                 in.data, un_data, out.data, tiles, impl->d_fail + slot);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
@@ -1369,7 +1615,10 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
+    if (waiting_tiles) M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));     // join the exchange stream
+    impl->mark(s, "stage kernels done");
     launch_finish(partials, num_fused, tpb, block_rows, num_fused + num_general, slot, finish_mode);
+    impl->mark(s, "finish done (or forked)");
     M3B_CUDA(cudaGetLastError());
 }
 
@@ -1431,17 +1680,48 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
     cfg.theta = theta;
     cfg.fixed_dt = fixed_dt;
 
+    const bool split_prepare = num_ranks == 1 || impl->peer_transport;
+    if (split_prepare)
+    {
+        if (impl->fresh_pipeline)
+        {
+            // the next step's first stage needs its body positions: normally prepared a step ahead, here for the first time
+            // (after the host's upload of this step's inputs, which is queued on the compute stream)
+            M3B_CUDA(cudaEventRecord(impl->fast_prepare_done, s));
+            M3B_CUDA(cudaStreamWaitEvent(impl->finish_stream, impl->fast_prepare_done, 0));
+            prepare_positions<<<1, 32, 0, impl->finish_stream>>>(cfg, impl->d_stage + a, nullptr, impl->d_stage + na);
+            ++launches;
+            M3B_CUDA(cudaEventRecord(impl->positions_done[1 - parity], impl->finish_stream));
+        }
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->positions_done[parity], 0));         // positions of this step's first stage
+    }
+    impl->fresh_pipeline = false;
+
     if (num_ranks == 1)
     {
         // the first stage's rows are folded on the side stream while the second stage runs; the second
-        // stage's finish_stage also writes the stage inputs of the next step (no separate prepare_next)
+        // stage's finish_stage also writes time and dt of the next step's stages (no separate prepare_next)
         impl->pending_prepare.enabled = 1;
         impl->pending_prepare.cfg = cfg;
         impl->pending_prepare.current_a = impl->d_stage + a;
         impl->pending_prepare.next_a = impl->d_stage + na;
         impl->pending_prepare.next_b = impl->d_stage + nb;
         launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1, 1);
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->positions_done[1 - parity], 0));     // positions of the second stage
         launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2, fixed_dt ? 0 : 2);
+    }
+    else if (impl->peer_transport)
+    {
+        // as on one rank, the first stage's rows are folded beside the second stage; the per-rank results then
+        // travel through the mailboxes and prepare_next_peer folds them (no NCCL call in the step)
+        impl->pending_prepare = prepare_args_t();
+        launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1, 1);
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->positions_done[1 - parity], 0));
+        launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2, fixed_dt ? 0 : 2);
+        prepare_next_peer<<<1, 128, 0, s>>>(impl->d_results_local, impl->peers, rank_, num_ranks, num_slots, a, b, ++impl->step_counter,
+            cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);
+        ++launches;
+        M3B_CUDA(cudaGetLastError());
     }
     else
     {
@@ -1453,6 +1733,18 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
         ++launches;
         M3B_CUDA(cudaGetLastError());
     }
+    if (split_prepare)
+    {
+        // the slow half: positions of the next step's second stage and of the first stage of the step after it
+        M3B_CUDA(cudaEventRecord(impl->fast_prepare_done, s));
+        M3B_CUDA(cudaStreamWaitEvent(impl->finish_stream, impl->fast_prepare_done, 0));
+        prepare_positions<<<1, 32, 0, impl->finish_stream>>>(cfg, impl->d_stage + na, impl->d_stage + nb, impl->d_stage + a);
+        ++launches;
+        M3B_CUDA(cudaEventRecord(impl->positions_done[parity], impl->finish_stream));
+        M3B_CUDA(cudaGetLastError());
+    }
+    impl->mark(s, "prepare done");
+    impl->end_step();
     M3B_CUDA(cudaEventRecord(impl->step_done[parity], s));
 }
 
@@ -1461,6 +1753,7 @@ void device_solver_t::upload_step_inputs(int parity, const stage_inputs_t& first
     M3B_CUDA(cudaSetDevice(device_id));
     upload_stage(first, first_async_slot + 2 * parity);
     upload_stage(second, first_async_slot + 2 * parity + 1);
+    impl->fresh_pipeline = true;
 }
 
 void device_solver_t::wait_step(int parity)
@@ -1497,6 +1790,98 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
 void device_solver_t::set_communicator(communicator_t* comm)
 {
     impl->comm = comm;
+    if (! comm || num_ranks == 1) return;
+    const char* transport = std::getenv("M3B_TRANSPORT");
+    if (transport && std::string(transport) == "nccl") return;
+    if (num_ranks > MAX_PEERS) return;
+
+    // ---- peer-memory transport: every rank maps every other rank's mailbox (CUDA IPC over NVLink); the handles and
+    // the landing-buffer layouts travel once through NCCL.  Any failure leaves the NCCL send / recv path in place.
+    M3B_CUDA(cudaSetDevice(device_id));
+    auto s = cudaStream_t(stream_);
+    const size_t flags_bytes = 1024, results_bytes = (size_t(num_ranks) * num_slots * sizeof(stage_result_t) + 255) / 256 * 256;
+    const size_t landing = (std::max<size_t>(1, impl->recv_total) * sizeof(double) + 255) / 256 * 256;
+    const size_t bytes = flags_bytes + results_bytes + 2 * landing;
+    M3B_CUDA(cudaMalloc(&impl->mailbox, bytes));
+    M3B_CUDA(cudaMemset(impl->mailbox, 0, bytes));
+    M3B_CUDA(cudaMalloc(&impl->d_push_ticket, 2 * sizeof(int)));
+    M3B_CUDA(cudaMemset(impl->d_push_ticket, 0, 2 * sizeof(int)));
+    M3B_CUDA(cudaMalloc(&impl->d_ready, sizeof(unsigned long long)));
+    M3B_CUDA(cudaMemset(impl->d_ready, 0, sizeof(unsigned long long)));
+
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, impl->mailbox) == cudaSuccess;
+    if (! ok) cudaGetLastError();
+
+    // per rank: [ok flag][64-byte handle as 8 doubles][recv_starts of every source rank]
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    const size_t words = 1 + 8 + size_t(num_ranks);
+    auto send = std::vector<double>(words, 0.0);
+    send[0] = ok ? 1.0 : 0.0;
+    std::memcpy(&send[1], &mine, sizeof(mine));
+    for (int p = 0; p < num_ranks; ++p) send[9 + p] = double(impl->recv_starts_host[p]);
+    double* d = nullptr;
+    M3B_CUDA(cudaMalloc(&d, (1 + size_t(num_ranks)) * words * sizeof(double)));
+    M3B_CUDA(cudaMemcpyAsync(d, send.data(), words * sizeof(double), cudaMemcpyHostToDevice, s));
+    comm->all_gather(d, d + words, words, stream_);
+    auto all = std::vector<double>(size_t(num_ranks) * words);
+    M3B_CUDA(cudaMemcpyAsync(all.data(), d + words, all.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaStreamSynchronize(s));
+    M3B_CUDA(cudaFree(d));
+
+    for (int p = 0; p < num_ranks; ++p) ok = ok && all[size_t(p) * words] == 1.0;
+    impl->peer_mailbox.assign(num_ranks, nullptr);
+    for (int p = 0; p < num_ranks && ok; ++p)
+    {
+        if (p == rank_) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, &all[size_t(p) * words + 1], sizeof(h));
+        if (cudaIpcOpenMemHandle(&impl->peer_mailbox[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    }
+    // everybody must agree, or the ranks would wait for each other on different transports
+    auto agree = all_gather_scalar(ok ? 1.0 : 0.0);
+    for (double a : agree) ok = ok && a == 1.0;
+    if (! ok) return;
+
+    for (int p = 0; p < num_ranks; ++p)
+    {
+        char* base = static_cast<char*>(p == rank_ ? impl->mailbox : impl->peer_mailbox[p]);
+        // the landing buffers of rank p have ITS size: only offsets below its recv_total are ever addressed, and the
+        // second buffer starts where rank p says -- which this rank learns from p's own layout words
+        impl->peers.halo_flag[p]   = reinterpret_cast<unsigned long long*>(base);
+        impl->peers.result_flag[p] = reinterpret_cast<unsigned long long*>(base + 512);
+        impl->peers.results[p]     = reinterpret_cast<stage_result_t*>(base + flags_bytes);
+        impl->peers.recv[p][0]     = reinterpret_cast<double*>(base + flags_bytes + results_bytes);
+        impl->peers.recv[p][1]     = nullptr;       // set below from rank p's landing size
+    }
+    // landing size of every rank: second all-gather (one double per rank)
+    auto sizes = all_gather_scalar(double(landing));
+    for (int p = 0; p < num_ranks; ++p)
+        impl->peers.recv[p][1] = reinterpret_cast<double*>(reinterpret_cast<char*>(impl->peers.recv[p][0]) + size_t(sizes[p]));
+
+    // send entries re-addressed into the destination's landing buffer: destination p expects this rank's strips at its recv_starts[me]
+    auto push = impl->send_entries_host;
+    impl->dest_mask = 0;
+    for (auto& e : push)
+    {
+        const int p = e.pad;
+        const size_t remote_start = size_t(all[size_t(p) * words + 9 + rank_]);
+        e.offset = remote_start + (e.offset - impl->send_starts_host[p]);
+        impl->dest_mask |= 1u << p;
+    }
+    if (! push.empty())
+    {
+        M3B_CUDA(cudaMalloc(&impl->d_push_entries, push.size() * sizeof(halo_entry_dev_t)));
+        M3B_CUDA(cudaMemcpy(impl->d_push_entries, push.data(), push.size() * sizeof(halo_entry_dev_t), cudaMemcpyHostToDevice));
+    }
+    impl->peer_transport = true;
+
+    // With at least two full generations of interior tiles ahead of them, the boundary tiles can wait for their guard zones
+    // inside the stage kernel while the unpack runs beside it: the exchange latency disappears behind the interior update.
+    // (With less interior work the stage kernel could fill every SM with waiting CTAs before the unpack is resident.)
+    const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
+    impl->in_kernel_wait = impl->strip && impl->irregular.empty() && impl->num_interior * tpb >= 2 * impl->sm_count * 4;
+    if (const char* e = std::getenv("M3B_IN_KERNEL_WAIT")) impl->in_kernel_wait = impl->in_kernel_wait && std::atoi(e) != 0;
 }
 
 std::uint64_t device_solver_t::halo_bytes_per_exchange() const
@@ -1516,6 +1901,36 @@ void device_solver_t::exchange_on(void* cuda_stream, device_field_t& field)
     auto s = cudaStream_t(cuda_stream);
     M3B_CUDA(cudaSetDevice(device_id));
 
+    if (impl->peer_transport)
+    {
+        // strips go straight into the neighbours' landing buffers over NVLink; the receive kernel waits on their flags.
+        // With in-kernel waiting both kernels run on the exchange stream, beside the stage kernel that follows on `s`
+        // (its boundary tiles poll d_ready), so none of the exchange sits on the compute stream.
+        const unsigned long long counter = ++impl->exchange_counter;
+        const int parity = int(counter & 1);
+        auto u = s;
+        if (impl->in_kernel_wait && impl->defer_unpack)
+        {
+            M3B_CUDA(cudaEventRecord(impl->input_ready, s));
+            M3B_CUDA(cudaStreamWaitEvent(impl->comm_stream, impl->input_ready, 0));
+            u = impl->comm_stream;
+        }
+        if (impl->num_send_entries)
+        {
+            halo_push<<<impl->num_send_entries, 128, 0, u>>>(impl->d_push_entries, field.data, cells, N, impl->peers, parity, rank_,
+                impl->dest_mask, counter, impl->d_push_ticket);
+            ++launches;
+        }
+        if (impl->num_recv_entries)
+        {
+            halo_wait_unpack<<<impl->num_recv_entries, 128, 0, u>>>(impl->d_recv_entries, field.data, cells, N, impl->peers.recv[rank_][parity],
+                impl->peers.halo_flag[rank_], counter, impl->d_push_ticket + 1, impl->d_ready);
+            ++launches;
+        }
+        if (u != s) M3B_CUDA(cudaEventRecord(impl->halo_ready, u));
+        M3B_CUDA(cudaGetLastError());
+        return;
+    }
     if (impl->num_send_entries)
     {
         halo_copy<<<impl->num_send_entries, 128, 0, s>>>(impl->d_send_entries, field.data, cells, N, impl->d_send_buffer, 1);
@@ -1581,6 +1996,8 @@ void device_solver_t::sync()
 {
     M3B_CUDA(cudaSetDevice(device_id));
     M3B_CUDA(cudaStreamSynchronize(cudaStream_t(stream_)));
+    if (impl->finish_stream) M3B_CUDA(cudaStreamSynchronize(impl->finish_stream));
+    if (impl->comm_stream) M3B_CUDA(cudaStreamSynchronize(impl->comm_stream));
 }
 
 std::vector<offender_t> device_solver_t::offenders(int slot)

@@ -134,6 +134,17 @@ namespace
 
         if (lane < 8) T.sinks[warp][lane] = 0.0;
 
+        // multi-GPU: a tile of a block with ghost neighbours waits until the guard-zone unpack has finished
+        if (int(blockIdx.x) >= mesh.first_wait_cta)
+        {
+            if (threadIdx.x == 0)
+            {
+                unsigned long long v;
+                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); } while (v < mesh.ready_value);
+            }
+            __syncthreads();
+        }
+
         // ------------------------------------------------------------------ phase 0: load + primitives
         {
             // The (SX + 4) x (SY + 4) region is 20 rows of 18 sixteen-byte chunks (two cells in y); columns j0 - 2 and
