@@ -605,6 +605,87 @@ namespace
         }
     }
 
+    // =======================================================================
+    // Peer-memory guard-zone exchange (NVLink loads / stores, no NCCL in the step loop)
+    // =======================================================================
+    constexpr int MAX_PEERS = 16;
+
+    /** Mapped (CUDA IPC) pointers into every rank's mailbox; index = rank.  [me] points at the local mailbox. */
+    struct peer_table_t
+    {
+        double* recv[MAX_PEERS][2];                     // guard-zone landing buffers, one per exchange parity
+        unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
+        stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
+        unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
+    };
+
+    __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
+    {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    }
+
+    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+
+    /**
+     * prepare_next for several ranks without NCCL (called by the >= 128 threads of one CTA): deliver this rank's
+     * two stage results to every rank's mailbox, wait for everybody else's, fold them in rank order (every rank
+     * gets the same bits) and write time and dt of the next step's stages.
+     */
+    __device__ void peer_prepare(const stage_result_t* __restrict__ local, const peer_table_t& peers, int me, int nranks,
+        int slot_stride, int slot_a, int slot_b, unsigned long long counter,
+        const step_config_t& cfg, const stage_t* __restrict__ current_a, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
+    {
+        __shared__ double dt_min_b;
+        constexpr int words = sizeof(stage_result_t) / sizeof(double);
+
+        for (int k = threadIdx.x; k < nranks * 2 * words; k += blockDim.x)
+        {
+            const int p = k / (2 * words), slot = (k / words) % 2 ? slot_b : slot_a, w = k % words;
+            reinterpret_cast<double*>(peers.results[p] + size_t(me) * slot_stride + slot)[w] = __ldcg(reinterpret_cast<const double*>(local + slot) + w);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < nranks)
+        {
+            if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
+            if (threadIdx.x != me) while (load_acquire_sys(peers.result_flag[me] + threadIdx.x) < counter) { }
+        }
+        __syncthreads();
+
+        const int k = threadIdx.x;
+        if (k < 2)
+        {
+            const int slot = k == 0 ? slot_a : slot_b;
+            stage_result_t r = stage_result_t();
+            r.dt_min = 1e300;
+            for (int p = 0; p < nranks; ++p)
+            {
+                const double* q = reinterpret_cast<const double*>(peers.results[me] + size_t(p) * slot_stride + slot);
+                for (int c = 0; c < 16; ++c) r.sums[c] += __ldcg(q + c);
+                r.work[0] += __ldcg(q + 16);
+                r.work[1] += __ldcg(q + 17);
+                r.dt_min = dmin(r.dt_min, __ldcg(q + 18));
+                r.num_negative += __ldcg(reinterpret_cast<const unsigned int*>(q + 19));
+            }
+            host_results[slot] = r;
+            if (k == 1) dt_min_b = r.dt_min;
+        }
+        __syncthreads();
+        if (k < 2)
+        {
+            const double t = current_a->time, dt = current_a->dt;
+            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
+            const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
+            if (k == 0) { next_a->time = t_next; next_a->dt = dt_next; }        // positions: prepare_positions, off the critical path
+            else        { next_b->time = t_next + dt_next; next_b->dt = dt_next; }
+        }
+    }
+
     /** Optional epilogue of finish_stage (single rank): what prepare_next does, in the last CTA of the step's last stage. */
     struct prepare_args_t
     {
@@ -613,6 +694,12 @@ namespace
         const stage_t* current_a;       // first stage of the step that is ending (its time and dt)
         stage_t* next_a;
         stage_t* next_b;
+        // enabled == 2: several ranks, results exchanged through the peer mailboxes (peer_prepare)
+        peer_table_t peers;
+        const stage_result_t* local;
+        stage_result_t* host_results;
+        int me, nranks, slot_stride, slot_a, slot_b;
+        unsigned long long counter;
     };
 
     /**
@@ -728,6 +815,14 @@ namespace
             *ticket = 0;
         }
         if (! prep.enabled) return;
+        if (prep.enabled == 2)
+        {
+            __threadfence();            // this launch's own result (written above) is read back through global memory
+            __syncthreads();
+            peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
+                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results);
+            return;
+        }
 
         // stage inputs of the next step (see prepare_next): one thread per stage
         __syncthreads();
@@ -807,32 +902,6 @@ namespace
         }
     }
 
-    // =======================================================================
-    // Peer-memory guard-zone exchange (NVLink loads / stores, no NCCL in the step loop)
-    // =======================================================================
-    constexpr int MAX_PEERS = 16;
-
-    /** Mapped (CUDA IPC) pointers into every rank's mailbox; index = rank.  [me] points at the local mailbox. */
-    struct peer_table_t
-    {
-        double* recv[MAX_PEERS][2];                     // guard-zone landing buffers, one per exchange parity
-        unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
-        stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
-        unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
-    };
-
-    __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
-    {
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-    }
-
-    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p)
-    {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-        return v;
-    }
-
     /**
      * Send side of extend() across GPUs (scheme.cpp:132-142): each CTA copies one strip / corner of an owned
      * block straight into the destination rank's landing buffer (entry.pad = destination rank, entry.offset =
@@ -890,61 +959,6 @@ namespace
         {
             *ticket = 0;
             asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(ready), "l"(counter) : "memory");
-        }
-    }
-
-    /**
-     * prepare_next for several ranks without NCCL: deliver this rank's two stage results to every rank's
-     * mailbox, wait for everybody else's, fold them in rank order (every rank gets the same bits) and write
-     * the stage inputs of the next step.
-     */
-    __global__ void __launch_bounds__(128) prepare_next_peer(const stage_result_t* __restrict__ local, peer_table_t peers, int me, int nranks,
-        int slot_stride, int slot_a, int slot_b, unsigned long long counter,
-        step_config_t cfg, const stage_t* __restrict__ current, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
-    {
-        __shared__ double dt_min_b;
-        constexpr int words = sizeof(stage_result_t) / sizeof(double);
-
-        for (int k = threadIdx.x; k < nranks * 2 * words; k += blockDim.x)
-        {
-            const int p = k / (2 * words), slot = (k / words) % 2 ? slot_b : slot_a, w = k % words;
-            reinterpret_cast<double*>(peers.results[p] + size_t(me) * slot_stride + slot)[w] = reinterpret_cast<const double*>(local + slot)[w];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < nranks)
-        {
-            if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
-            if (threadIdx.x != me) while (load_acquire_sys(peers.result_flag[me] + threadIdx.x) < counter) { }
-        }
-        __syncthreads();
-
-        const int k = threadIdx.x;
-        if (k < 2)
-        {
-            const int slot = k == 0 ? slot_a : slot_b;
-            stage_result_t r = stage_result_t();
-            r.dt_min = 1e300;
-            for (int p = 0; p < nranks; ++p)
-            {
-                const double* q = reinterpret_cast<const double*>(peers.results[me] + size_t(p) * slot_stride + slot);
-                for (int c = 0; c < 16; ++c) r.sums[c] += __ldcg(q + c);
-                r.work[0] += __ldcg(q + 16);
-                r.work[1] += __ldcg(q + 17);
-                r.dt_min = dmin(r.dt_min, __ldcg(q + 18));
-                r.num_negative += __ldcg(reinterpret_cast<const unsigned int*>(q + 19));
-            }
-            host_results[slot] = r;
-            if (k == 1) dt_min_b = r.dt_min;
-        }
-        __syncthreads();
-        if (k < 2)
-        {
-            const double t = current[slot_a].time, dt = current[slot_a].dt;
-            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
-            const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
-            if (k == 0) { next_a->time = t_next; next_a->dt = dt_next; }        // positions: prepare_positions, off the critical path
-            else        { next_b->time = t_next + dt_next; next_b->dt = dt_next; }
         }
     }
 
@@ -1714,14 +1728,20 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
     {
         // as on one rank, the first stage's rows are folded beside the second stage; the per-rank results then
         // travel through the mailboxes and prepare_next_peer folds them (no NCCL call in the step)
-        impl->pending_prepare = prepare_args_t();
+        auto& pp = impl->pending_prepare;
+        pp.enabled = 2;
+        pp.cfg = cfg;
+        pp.current_a = impl->d_stage + a;
+        pp.next_a = impl->d_stage + na;
+        pp.next_b = impl->d_stage + nb;
+        pp.peers = impl->peers;
+        pp.local = impl->d_results_local;
+        pp.host_results = impl->d_results;
+        pp.me = rank_; pp.nranks = num_ranks; pp.slot_stride = num_slots; pp.slot_a = a; pp.slot_b = b;
+        pp.counter = ++impl->step_counter;
         launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1, 1);
         M3B_CUDA(cudaStreamWaitEvent(s, impl->positions_done[1 - parity], 0));
         launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2, fixed_dt ? 0 : 2);
-        prepare_next_peer<<<1, 128, 0, s>>>(impl->d_results_local, impl->peers, rank_, num_ranks, num_slots, a, b, ++impl->step_counter,
-            cfg, impl->d_stage, impl->d_stage + na, impl->d_stage + nb, impl->d_results);
-        ++launches;
-        M3B_CUDA(cudaGetLastError());
     }
     else
     {
