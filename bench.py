@@ -39,6 +39,18 @@ ALGORITHMIC_BYTES_PER_CELL_STEP = 120.0     # RK2 = 2 x (24 read
 ALGORITHMIC_BYTES_PER_CELL_LAUNCH = 60.0    # mean over the two stage launches of a step (48 and 72)
 
 
+def ncu_traffic(workload, local_cells):
+    """DRAM bytes per stage launch from the committed ncu --set full capture (profiles/r01_traffic.json), if it is of this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"] == workload and t["algorithmic_bytes_per_launch"] == local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH:
+            return t["traffic_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -128,7 +140,8 @@ def time_reference(config, steps, warmup, threads):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload or ("c2" if world == 1 else "c3")]
+    wl_name = args.workload or ("c2" if world == 1 else "c3")
+    wl = WORKLOADS[wl_name]
     threads = os.cpu_count() or 1
     steps, warmup = args.steps, args.warmup
     cells = (2 ** wl["config"]["depth"] * wl["config"]["block_size"]) ** 2
@@ -187,7 +200,8 @@ def main():
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
 
-    wl = WORKLOADS[args.workload or ("c2" if world == 1 else "c3")]
+    wl_name = args.workload or ("c2" if world == 1 else "c3")
+    wl = WORKLOADS[wl_name]
     scaling_reference = None
     if world > 1 and rank == 0 and not args.no_scaling_reference:
         # the same workload on ONE GPU, measured in this run, so that strong-scaling efficiency can be
@@ -273,7 +287,7 @@ def main():
     local_cells = solver.num_owned_cells
     achieved = local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH / (kernel_ms * 1e-3) * 1e-9 if stage_launches else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "kernel": "stage_fused", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
+                "traffic": ncu_traffic(wl_name, local_cells), "kernel": "stage_strip", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
                 "algorithmic_bytes_per_launch": local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH, "per": "GPU (rank 0)", "peak_source": peak_how,
                 "step_frac_of_hbm_roofline": value * 1e6 * ALGORITHMIC_BYTES_PER_CELL_STEP / (peak * 1e9)}
 
