@@ -32,6 +32,8 @@ WORKLOADS = {
                config=dict(depth=4, block_size=64, focus_factor=1e3, mach_number=10.0)),
     "c3": dict(name="binary iso2d uniform 4096^2 (depth=6, 4096 blocks of 64^2), PLM+HLLE, RK2",
                config=dict(depth=6, block_size=64, focus_factor=1e3, mach_number=10.0)),
+    "c4": dict(name="binary iso2d nested quadtree (depth=8, 424 blocks of 64^2 on levels 3-8, prolong/restrict at the jumps), PLM+HLLE, RK2",
+               config=dict(depth=8, block_size=64)),
     "c5": dict(name="binary iso2d uniform 16384^2 (depth=8, 65536 blocks of 64^2), PLM+HLLE, RK2",
                config=dict(depth=8, block_size=64, focus_factor=1e3, mach_number=10.0)),
 }
@@ -145,6 +147,8 @@ def run_reference_arm(args, rank, world):
     threads = os.cpu_count() or 1
     steps, warmup = args.steps, args.warmup
     cells = (2 ** wl["config"]["depth"] * wl["config"]["block_size"]) ** 2
+    if wl_name == "c4":
+        cells = 424 * 64 * 64       # leaves of the default-focus depth-8 tree x block cells
     # bounded sample: the reference manages ~1 Mzps, keep the run to a few minutes
     max_steps = max(1, int(120e6 / cells))
     sample_steps = min(steps, max_steps)

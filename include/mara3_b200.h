@@ -82,6 +82,9 @@ void        m3b_local_to_global(const m3b_solver_t* s, int* out);
 int         m3b_halo_plan_size(const m3b_solver_t* s, int peer, int send);
 void        m3b_halo_plan(const m3b_solver_t* s, int peer, int send, int* out);
 void        m3b_neighbor_table(const m3b_solver_t* s, int* out);
+/* [local block][4 sides: -x, +x, -y, +y][kind (0 same, 1 coarser, 2 finer), 4 leaf ids in local numbering or -1]:
+ * the face-neighbour table the any-tree kernels read guard cells through (mesh_tree_operators.hpp:223-252) */
+void        m3b_face_neighbor_table(const m3b_solver_t* s, int* out);
 uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
 int         m3b_block_size(const m3b_solver_t* s);
 int64_t     m3b_num_cells(const m3b_solver_t* s);

@@ -85,6 +85,7 @@ def load_library():
     L.m3b_halo_plan_size.argtypes = [vp, C.c_int, C.c_int]
     L.m3b_halo_plan.argtypes = [vp, C.c_int, C.c_int, ip]
     L.m3b_neighbor_table.argtypes = [vp, ip]
+    L.m3b_face_neighbor_table.argtypes = [vp, ip]
     L.m3b_halo_bytes_per_exchange.argtypes = [vp]
     L.m3b_halo_bytes_per_exchange.restype = C.c_uint64
     L.m3b_solver_destroy.argtypes = [vp]
@@ -276,6 +277,13 @@ class Solver:
         """[owned][3][3] local ids of the same-level neighbours (-1: none), the table the stage kernel reads its halo through."""
         a = np.empty((self.num_blocks, 3, 3), dtype=np.int32)
         _lib.m3b_neighbor_table(self._h, a.ctypes.data_as(C.POINTER(C.c_int)))
+        return a
+
+    @property
+    def face_neighbor_table(self):
+        """[local block][side -x, +x, -y, +y][kind, 4 leaf ids] in local numbering (-1: none or not stored on this rank)."""
+        a = np.empty((self.num_local_blocks, 4, 5), dtype=np.int32)
+        _lib.m3b_face_neighbor_table(self._h, a.ctypes.data_as(C.POINTER(C.c_int)))
         return a
 
     def halo_plan(self, peer, send):

@@ -137,6 +137,19 @@ void m3b_neighbor_table(const m3b_solver_t* s, int* out)
             }
 }
 
+void m3b_face_neighbor_table(const m3b_solver_t* s, int* out)
+{
+    const auto& d = s->solver->solver_data();
+    for (int b = 0; b < d.num_local; ++b)
+        for (int side = 0; side < 4; ++side)
+        {
+            auto fn = d.tree->face_neighbor(d.global_block(b), side);
+            int* o = out + (b * 4 + side) * 5;
+            o[0] = int(fn.kind);
+            for (int q = 0; q < 4; ++q) o[1 + q] = fn.leaf[q] < 0 ? -1 : d.partition.global_to_local[fn.leaf[q]];
+        }
+}
+
 uint64_t m3b_halo_bytes_per_exchange(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().halo_bytes_per_exchange() : 0; }
 int m3b_block_size(const m3b_solver_t* s) { return s->solver->solver_data().block_size; }
 int64_t m3b_num_cells(const m3b_solver_t* s) { return int64_t(s->solver->solver_data().num_cells()); }

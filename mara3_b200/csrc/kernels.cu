@@ -1137,9 +1137,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     {
         const int g = sd.global_block(b);
         spacing[b] = sd.spacing(tree.index(g).level);
-        if (b >= BO) continue;          // ghost blocks are only read from
-        bool regular = true;
 
+        // face tables also for ghost blocks: the any-tree kernels compute gradients of layer-1 ghosts from
+        // layer-2 ghosts and walk from a fine ghost back to the coarse block it borders (ids of blocks this
+        // rank does not store are -1 and never followed)
         for (int side = 0; side < 4; ++side)
         {
             auto fn = tree.face_neighbor(g, side);
@@ -1148,6 +1149,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             for (int q = 0; q < 4; ++q) d.leaf[q] = local(fn.leaf[q]);
             d.bx = fn.bx; d.by = fn.by; d.pad = 0;
         }
+        if (b >= BO) continue;          // ghost blocks are only read from
+        bool regular = true;
         for (int di = -1; di <= 1; ++di)
             for (int dj = -1; dj <= 1; ++dj)
             {

@@ -15,23 +15,59 @@ std::vector<int> m3b::partition_offsets(int num_leaves, int nranks)
 
 namespace
 {
-    /** The (source block, di, dj) triples rank `r` needs from other ranks, ordered by
-     *  (owner, source block, di, dj) and without duplicates. */
+    /**
+     * The (owner, source block, di, dj) regions rank `r` needs from other ranks, ordered by
+     * (owner, source block, di, dj) and without duplicates.  (di, dj) = (0, 0) is the whole block.
+     *
+     * A block whose eight same-level neighbours are all leaves is updated by the fused kernel and needs
+     * their two-cell edge strips / 2x2 corners.  A block that touches a refinement jump is updated by the
+     * any-tree kernels, which read primitives AND PLM gradients of its face neighbours through the
+     * prolongation / restriction rules (mesh_tree_operators.hpp:223-252): the gradients of those
+     * neighbours are computed on this rank too, from THEIR face neighbours -- so the rank stores whole
+     * copies of the face neighbours (layer 1) and of the face neighbours of those (layer 2).
+     */
     std::vector<std::tuple<int, int, int, int>> remote_needs(const quadtree_t& tree, const std::vector<int>& owner, int first, int count, int r)
     {
         auto needs = std::set<std::tuple<int, int, int, int>>();
+        auto whole = std::set<int>();
+        auto want_whole = [&] (int leaf) { if (leaf >= 0 && owner[leaf] != r) whole.insert(leaf); };
 
         for (int b = first; b < first + count; ++b)
+        {
+            bool regular = true;
             for (int di = -1; di <= 1; ++di)
                 for (int dj = -1; dj <= 1; ++dj)
+                    if ((di || dj) && tree.same_level_neighbor(b, di, dj) < 0) regular = false;
+
+            if (regular)
+            {
+                for (int di = -1; di <= 1; ++di)
+                    for (int dj = -1; dj <= 1; ++dj)
+                    {
+                        if (di == 0 && dj == 0) continue;
+                        int n = tree.same_level_neighbor(b, di, dj);
+                        if (owner[n] != r) needs.insert({owner[n], n, di, dj});
+                    }
+                continue;
+            }
+            for (int side = 0; side < 4; ++side)
+            {
+                auto f1 = tree.face_neighbor(b, side);
+                for (int l1 : f1.leaf)
                 {
-                    if (di == 0 && dj == 0) continue;
-                    int n = tree.same_level_neighbor(b, di, dj);
-                    if (n < 0)
-                        throw std::invalid_argument("multi-GPU runs need a uniform-level tree in this build: block " + std::to_string(b)
-                            + " touches a refinement jump (raise focus_factor, or run nested trees on one GPU)");
-                    if (owner[n] != r) needs.insert({owner[n], n, di, dj});
+                    if (l1 < 0) continue;
+                    want_whole(l1);
+                    for (int side2 = 0; side2 < 4; ++side2)
+                        for (int l2 : tree.face_neighbor(l1, side2).leaf) want_whole(l2);
                 }
+            }
+        }
+        // a whole block makes its strips redundant
+        for (auto it = needs.begin(); it != needs.end(); )
+        {
+            if (whole.count(std::get<1>(*it))) it = needs.erase(it); else ++it;
+        }
+        for (int leaf : whole) needs.insert({owner[leaf], leaf, 0, 0});
         return {needs.begin(), needs.end()};
     }
 }

@@ -8,7 +8,8 @@
  * contiguous ranges of (nearly) equal length; a rank stores its own blocks followed by ghost
  * copies of every remote block that one of its blocks touches (faces and corners, periodic), and
  * before each RK stage the two-cell-deep edge strips / 2x2 corners those blocks need are moved
- * rank to rank.  Both sides derive the same ordered lists from the global tree, so no handshake
+ * rank to rank.  Blocks at a refinement jump read whole neighbour blocks two face-layers deep
+ * (partition.cpp: remote_needs), which travel as whole-block regions.  Both sides derive the same ordered lists from the global tree, so no handshake
  * is needed.
  */
 #pragma once
@@ -19,7 +20,8 @@ namespace m3b
 {
     /** One strip or corner of a block: which cells move.  (di, dj) is the position of the SOURCE
      *  block relative to the block that needs it, so the cells are the source's rows facing back:
-     *  di = -1 -> rows N-2, N-1;  di = +1 -> rows 0, 1;  di = 0 -> all rows (same for dj / columns). */
+     *  di = -1 -> rows N-2, N-1;  di = +1 -> rows 0, 1;  di = 0 -> all rows (same for dj / columns);
+     *  (0, 0) is the whole block. */
     struct halo_region_t
     {
         int block;          // local block id (owned on the sending side, ghost on the receiving side)
@@ -46,7 +48,6 @@ namespace m3b
     /** First leaf of each rank's range: balanced by leaf count (all leaves hold N^2 cells). */
     std::vector<int> partition_offsets(int num_leaves, int nranks);
 
-    /** Build the partition and exchange plan seen by `rank`.  Throws if a block owned by this rank
-     *  touches a refinement jump and nranks > 1 (the any-tree kernels are single-GPU in this build). */
+    /** Build the partition and exchange plan seen by `rank` (any 2:1 balanced tree). */
     partition_t make_partition(const quadtree_t& tree, int rank, int nranks);
 }

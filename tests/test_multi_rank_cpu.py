@@ -66,21 +66,41 @@ def worker(rank, world, port, cfg, q):
                 U[b][:, rows, cols] = buf[at:at + int(np.prod(shape))].reshape(shape)
                 at += int(np.prod(shape))
 
-        # every halo cell the stage kernel reads is now the true neighbour's value
+        # every halo cell the stage kernels read is now the true neighbour's value
         full = m3.Solver(cfg, host_only=True)                       # whole tree on one rank: ground truth
         table, full_table = s.neighbor_table, full.neighbor_table
+        faces, full_faces = s.face_neighbor_table, full.face_neighbor_table
         checked = 0
         for b in range(owned):
             g = l2g[b]
-            for di in (-1, 0, 1):
-                for dj in (-1, 0, 1):
-                    if di == 0 and dj == 0:
-                        continue
-                    n_local, n_global = table[b, di + 1, dj + 1], full_table[g, di + 1, dj + 1]
-                    assert n_local >= 0 and l2g[n_local] == n_global
-                    rows, cols = region(N, di, dj)
-                    assert np.array_equal(U[n_local][:, rows, cols], known(n_global, N)[:, rows, cols])
-                    checked += 1
+            if (table[b] >= 0).all():
+                # fused kernel: two-cell strips / corners of the eight same-level neighbours
+                for di in (-1, 0, 1):
+                    for dj in (-1, 0, 1):
+                        if di == 0 and dj == 0:
+                            continue
+                        n_local, n_global = table[b, di + 1, dj + 1], full_table[g, di + 1, dj + 1]
+                        assert n_local >= 0 and l2g[n_local] == n_global
+                        rows, cols = region(N, di, dj)
+                        assert np.array_equal(U[n_local][:, rows, cols], known(n_global, N)[:, rows, cols])
+                        checked += 1
+            else:
+                # any-tree kernels: whole face neighbours (layer 1) and whole face neighbours of those (layer 2)
+                assert (full_table[g] < 0).any()
+                for side in range(4):
+                    assert faces[b, side, 0] == full_faces[g, side, 0]
+                    for l1, g1 in zip(faces[b, side, 1:], full_faces[g, side, 1:]):
+                        assert (l1 < 0) == (g1 < 0)
+                        if l1 < 0:
+                            continue
+                        assert l2g[l1] == g1 and np.array_equal(U[l1], known(g1, N))
+                        for side2 in range(4):
+                            assert faces[l1, side2, 0] == full_faces[g1, side2, 0]
+                            for l2, g2 in zip(faces[l1, side2, 1:], full_faces[g1, side2, 1:]):
+                                assert (l2 < 0) == (g2 < 0)
+                                if l2 >= 0:
+                                    assert l2g[l2] == g2 and np.array_equal(U[l2], known(g2, N))
+                checked += 8
         first, count = s.first_block, owned
         counts = [None] * world
         dist.all_gather_object(counts, (first, count, L - owned, checked))
@@ -101,6 +121,8 @@ def free_port():
     (dict(depth=3, block_size=8, focus_factor=1e3), 2),      # 64 blocks, 8x8
     (dict(depth=2, block_size=6, focus_factor=1e3), 2),      # 16 blocks, 4x4: wrap neighbours are everywhere
     (dict(depth=3, block_size=4, focus_factor=1e3), 3),      # uneven ranges: 21 / 21 / 22
+    (dict(depth=4, block_size=8), 2),                        # nested tree (64 leaves, levels 2-4): whole-block ghosts at the jumps
+    (dict(depth=5, block_size=4), 3),                        # deeper nesting on three ranks
 ])
 def test_exchange_plan_with_gloo(cfg, world):
     import torch.multiprocessing as mp
@@ -116,7 +138,7 @@ def test_exchange_plan_with_gloo(cfg, world):
         assert status == "ok", status
     counts = results[0][2]
     total = sum(c[1] for c in counts)
-    assert total == 4 ** cfg["depth"]
+    assert total == m3.Solver(cfg, host_only=True).num_blocks
     assert [c[0] for c in counts] == [sum(x[1] for x in counts[:k]) for k in range(world)]      # contiguous Morton ranges
     assert max(c[1] for c in counts) - min(c[1] for c in counts) <= 1                            # balanced
     assert all(c[2] > 0 and c[3] == 8 * c[1] for c in counts)                                    # ghosts exist; all 8 neighbours checked
@@ -129,6 +151,9 @@ def test_partition_is_identity_on_one_rank():
     assert len(s.halo_plan(0, True)) == 0
 
 
-def test_nested_trees_are_refused_on_several_ranks():
-    with pytest.raises(m3.Mara3Error, match="uniform-level tree"):
-        m3.Solver(dict(depth=4, block_size=8), host_only=True, rank=0, nranks=2)
+def test_nested_trees_store_whole_ghost_blocks():
+    s = m3.Solver(dict(depth=4, block_size=8), host_only=True, rank=0, nranks=2)
+    plan = s.halo_plan(1, False)
+    assert s.num_blocks == 32 and len(plan) > 0
+    assert ((plan[:, 1] == 0) & (plan[:, 2] == 0)).any()         # whole blocks for the any-tree kernels
+    assert (plan[:, 0] >= s.num_blocks).all()

@@ -35,7 +35,9 @@ def main():
 
     cases = [(dict(depth=3, block_size=32, focus_factor=1e3, domain_radius=6.0), 12, True),
              (dict(depth=2, block_size=64), 34, True),             # runs into the safe-mode retries (steps 23-33)
-             (dict(depth=4, block_size=64, focus_factor=1e3), 5, False)]
+             (dict(depth=4, block_size=64, focus_factor=1e3), 5, False),
+             (dict(depth=4, block_size=32), 6, True),              # nested tree: refinement jumps across the rank boundary
+             (dict(depth=6, block_size=64), 4, False)]             # config-4-like nesting (136 leaves, levels 2-6)
     for cfg, steps, with_oracle in cases:
         s = m3.Solver(cfg, device=local, rank=rank, nranks=world, nccl_unique_id=fresh_id())
         u = s.create_solution()
