@@ -86,6 +86,9 @@ void        m3b_neighbor_table(const m3b_solver_t* s, int* out);
  * the face-neighbour table the any-tree kernels read guard cells through (mesh_tree_operators.hpp:223-252) */
 void        m3b_face_neighbor_table(const m3b_solver_t* s, int* out);
 uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
+/* test hook of the built-in HDF5 writer / reader (h5lite): write one file with every structure it emits and / or
+ * list the root group of an existing file into `report`; 0 or -1 (message in `report`) */
+int         m3b_h5_selftest(const char* write_path, const char* read_path, char* report, int report_len);
 int         m3b_block_size(const m3b_solver_t* s);
 int64_t     m3b_num_cells(const m3b_solver_t* s);
 int         m3b_num_regular_blocks(const m3b_solver_t* s);   /* blocks served by the fused kernel */

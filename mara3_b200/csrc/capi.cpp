@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include "../../include/mara3_b200.h"
 #include "scheme.hpp"
+#include "h5lite.hpp"
 
 using namespace m3b;
 
@@ -148,6 +149,62 @@ void m3b_face_neighbor_table(const m3b_solver_t* s, int* out)
             o[0] = int(fn.kind);
             for (int q = 0; q < 4; ++q) o[1 + q] = fn.leaf[q] < 0 ? -1 : d.partition.global_to_local[fn.leaf[q]];
         }
+}
+
+int m3b_h5_selftest(const char* write_path, const char* read_path, char* report, int report_len)
+{
+    // exercises every structure h5lite emits (test infrastructure for tests/test_h5lite.py) and, if read_path is given,
+    // lists that file's root group through the reader
+    try
+    {
+        using m3b::h5::type_t;
+        std::string out;
+        if (write_path && *write_path)
+        {
+            m3b::h5::writer_t w(write_path);
+            struct inner_t { double a, b; };
+            struct outer_t { double t; double v[2]; inner_t in; int n; int pad; };
+            auto inner = type_t::compound(sizeof(inner_t), {type_t::member("a", offsetof(inner_t, a), type_t::f64()), type_t::member("b", offsetof(inner_t, b), type_t::f64())});
+            auto outer = type_t::compound(sizeof(outer_t), {type_t::member("t", offsetof(outer_t, t), type_t::f64()),
+                type_t::member("v", offsetof(outer_t, v), type_t::array(type_t::f64(), 2)), type_t::member("in", offsetof(outer_t, in), inner),
+                type_t::member("n", offsetof(outer_t, n), type_t::i32())});
+            std::vector<outer_t> series(5);
+            for (int k = 0; k < 5; ++k) series[k] = {0.5 * k, {1.0 + k, 2.0 + k}, {10.0 * k, -1.0 * k}, k, 0};
+            w.write("/series", outer, {5}, series.data(), true);
+            w.write_double("/group/time", 3.25);
+            w.write_int("/group/count", -7);
+            w.write_string("/group/name", "write_checkpoint");
+            w.write_string("/group/empty", "");
+            int rational[2] = {22, 7};
+            w.write("/group/iteration", type_t::array(type_t::i32(), 2), {}, rational, true);
+            std::vector<double> field(6 * 4 * 3);
+            for (std::size_t k = 0; k < field.size(); ++k) field[k] = 0.125 * double(k);
+            w.write("/group/nested/field", type_t::array(type_t::f64(), 3), {6, 4}, field.data(), true);
+            w.write("/group/nested/nothing", type_t::array(type_t::f64(), 3), {0, 0}, field.data(), true);
+            w.require_group("/hollow");
+            std::vector<double> values(300);
+            for (int k = 0; k < 300; ++k)
+            {
+                char name[32];
+                std::snprintf(name, sizeof(name), "8:%03d-%03d", k, 299 - k);
+                values[k] = k;
+                w.write(std::string("/many/") + name, type_t::f64(), {1}, &values[k]);
+            }
+            w.close();
+        }
+        if (read_path && *read_path)
+        {
+            m3b::h5::reader_t r(read_path);
+            for (auto& k : r.keys("/")) out += k + (r.is_group("/" + k) ? "/ " : " ");
+        }
+        if (report && report_len > 0) std::snprintf(report, report_len, "%s", out.c_str());
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (report && report_len > 0) std::snprintf(report, report_len, "error: %s", e.what());
+        return -1;
+    }
 }
 
 uint64_t m3b_halo_bytes_per_exchange(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().halo_bytes_per_exchange() : 0; }

@@ -38,6 +38,8 @@ def main():
              (dict(depth=4, block_size=64, focus_factor=1e3), 5, False),
              (dict(depth=4, block_size=32), 6, True),              # nested tree: refinement jumps across the rank boundary
              (dict(depth=6, block_size=64), 4, False)]             # config-4-like nesting (136 leaves, levels 2-6)
+    if os.environ.get("MGC_QUICK"):
+        cases = [(dict(depth=3, block_size=32, focus_factor=1e3, domain_radius=6.0), 6, False), (dict(depth=6, block_size=64), 3, False)]
     for cfg, steps, with_oracle in cases:
         s = m3.Solver(cfg, device=local, rank=rank, nranks=world, nccl_unique_id=fresh_id())
         u = s.create_solution()
