@@ -86,6 +86,10 @@ def load_library():
     L.m3b_halo_plan.argtypes = [vp, C.c_int, C.c_int, ip]
     L.m3b_neighbor_table.argtypes = [vp, ip]
     L.m3b_face_neighbor_table.argtypes = [vp, ip]
+    for name in ("m3b_write_checkpoint", "m3b_write_diagnostics", "m3b_read_checkpoint"):
+        getattr(L, name).argtypes = [vp, vp, C.c_char_p]
+    L.m3b_time_series_sample.argtypes = [vp, vp, dp]
+    L.m3b_binary_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
     L.m3b_halo_bytes_per_exchange.argtypes = [vp]
     L.m3b_halo_bytes_per_exchange.restype = C.c_uint64
     L.m3b_solver_destroy.argtypes = [vp]
@@ -358,6 +362,25 @@ class Solver:
         self._check(_lib.m3b_next_solution_host(self._h, _dptr(u), _dptr(scalars), _dptr(u_out), _dptr(s_out), C.byref(dt), C.byref(fb)))
         return u_out, s_out, dt.value, bool(fb.value)
 
+    # ---- HDF5 products --------------------------------------------------------
+    def write_checkpoint(self, solution, filename):
+        """chkpt.NNNN.h5 layout (subprog_binary_io.cpp:131-158) for `solution`, initial schedule, empty time series."""
+        self._check(_lib.m3b_write_checkpoint(self._h, solution._h, os.fsencode(filename)))
+
+    def write_diagnostics(self, solution, filename):
+        """diagnostics.NNNN.h5 layout (subprog_binary_io.cpp:160-172): vertices, sigma, radial and azimuthal velocity per leaf."""
+        self._check(_lib.m3b_write_diagnostics(self._h, solution._h, os.fsencode(filename)))
+
+    def read_checkpoint(self, solution, filename):
+        """Load /solution of a checkpoint (written by this library or by the reference with libhdf5's defaults) into `solution`."""
+        self._check(_lib.m3b_read_checkpoint(self._h, solution._h, os.fsencode(filename)))
+
+    def time_series_sample(self, solution):
+        """The 47 doubles of time_series_sample_t (subprog_binary.hpp:144-161) for `solution`."""
+        a = np.empty(47, dtype=np.float64)
+        self._check(_lib.m3b_time_series_sample(self._h, solution._h, _dptr(a)))
+        return a
+
     # ---- measurement helpers ------------------------------------------------------------------
     def stage_timing(self, enable):
         _lib.m3b_stage_timing(self._h, int(enable))
@@ -409,6 +432,13 @@ def orbital_elements(bodies, t):
     if L.m3b_orbital_elements(_dptr(b), float(t), _dptr(out)):
         raise ValueError("mara::compute_orbital_elements (two_body_state does not correspond to a bound orbit)")
     return out
+
+
+def binary_main(argv, device=0):
+    """The `binary` subprogram (subprog_binary.cpp:414-436): argv = ["binary", "key=value", ...]; returns the exit code."""
+    load_library()
+    args = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
+    return _lib.m3b_binary_main(len(argv), args, int(device))
 
 
 def nccl_unique_id():

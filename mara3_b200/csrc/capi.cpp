@@ -9,6 +9,9 @@
 #include "../../include/mara3_b200.h"
 #include "scheme.hpp"
 #include "h5lite.hpp"
+#include "binary_io.hpp"
+#include <chrono>
+#include <iostream>
 
 using namespace m3b;
 
@@ -149,6 +152,58 @@ void m3b_face_neighbor_table(const m3b_solver_t* s, int* out)
             o[0] = int(fn.kind);
             for (int q = 0; q < 4; ++q) o[1 + q] = fn.leaf[q] < 0 ? -1 : d.partition.global_to_local[fn.leaf[q]];
         }
+}
+
+int m3b_write_checkpoint(m3b_solver_t* s, const m3b_solution_t* u, const char* filename)
+{
+    return guarded(s, [&]
+    {
+        // a state with the initial schedule (all three tasks performed zero times, none due) and no time series:
+        // what the run loop would store before its first task
+        auto state = m3b::state_t();
+        state.solution = u->solution;
+        for (const char* task : {"write_checkpoint", "write_diagnostics", "record_time_series"}) state.schedule.tasks[task] = {task, 0, 0.0, false};
+        m3b::write_checkpoint(filename, *s->solver, state);
+        return M3B_OK;
+    });
+}
+
+int m3b_write_diagnostics(m3b_solver_t* s, const m3b_solution_t* u, const char* filename)
+{
+    return guarded(s, [&] { m3b::write_diagnostics(filename, *s->solver, u->solution); return M3B_OK; });
+}
+
+int m3b_read_checkpoint(m3b_solver_t* s, m3b_solution_t* u, const char* filename)
+{
+    return guarded(s, [&] { s->solver->invalidate(); u->solution = m3b::read_checkpoint(filename, *s->solver).solution; return M3B_OK; });
+}
+
+int m3b_time_series_sample(m3b_solver_t* s, const m3b_solution_t* u, double* out47)
+{
+    return guarded(s, [&]
+    {
+        auto sample = m3b::make_time_series_sample(*s->solver, u->solution);
+        std::memcpy(out47, &sample, sizeof(sample));
+        return M3B_OK;
+    });
+}
+
+int m3b_binary_main(int argc, const char* const* argv, int device)
+{
+    // app_main.cpp:75-79: run the subprogram, then report the wall time; an exception ends the run with its message
+    try
+    {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        int code = m3b::binary_main(argc, argv, device);
+        double s = 1e-9 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count());
+        std::cout << "total execution time: " << s << " seconds" << std::endl;
+        return code;
+    }
+    catch (const std::exception& e)
+    {
+        std::cout << e.what() << std::endl;
+        return 1;
+    }
 }
 
 int m3b_h5_selftest(const char* write_path, const char* read_path, char* report, int report_len)

@@ -69,6 +69,10 @@ namespace m3b
         void upload(const double* host_block_major, device_field_t& dst);
         void download(const device_field_t& src, double* host_block_major);
         void copy(const device_field_t& src, device_field_t& dst);
+        /** disk_mass, disk_angular_momentum of the owned blocks (subprog_binary_diagnostics.cpp:19-41). */
+        void disk_totals(const device_field_t& src, double out[2]);
+        /** sigma, radial velocity, azimuthal velocity, [owned block][3][N][N] on the host (subprog_binary_diagnostics.cpp:48-82). */
+        void diagnostic_fields(const device_field_t& src, double* host);
         void load_initial(device_field_t& dst);
         /** dst = a * wa + b * wb (solution_t::operator+ / *, scheme.cpp:1033-1069) */
         void combine(const device_field_t& a, double wa, const device_field_t& b, double wb, device_field_t& dst);

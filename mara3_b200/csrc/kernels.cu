@@ -962,6 +962,61 @@ namespace
         }
     }
 
+    /**
+     * disk_mass and disk_angular_momentum of the time series (subprog_binary_diagnostics.cpp:19-41): per block the
+     * sums of sigma dA and (x py - y px) dA, folded in a fixed order; the host adds the blocks in tree order.
+     */
+    __global__ void __launch_bounds__(THREADS) disk_totals_kernel(mesh_dev_t mesh, const double* __restrict__ U, double* __restrict__ out)
+    {
+        __shared__ double red[2][THREADS / 32];
+        const int N = mesh.N, b = blockIdx.x;
+        const double* xv = mesh.xv + size_t(b) * (N + 1);
+        const double* yv = mesh.yv + size_t(b) * (N + 1);
+        double m = 0.0, l = 0.0;
+
+        for (int k = threadIdx.x; k < N * N; k += THREADS)
+        {
+            int i = k / N, j = k % N;
+            size_t c = size_t(b) * N * N + k;
+            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
+            double dA = (xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]);
+            m += U[c] * dA;
+            l += (x * U[2 * mesh.FS + c] - y * U[mesh.FS + c]) * dA;
+        }
+        m = warp_sum(m); l = warp_sum(l);
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m; red[1][threadIdx.x >> 5] = l; }
+        __syncthreads();
+        if (threadIdx.x < 2)
+        {
+            double v = 0.0;
+            for (int w = 0; w < THREADS / 32; ++w) v += red[threadIdx.x][w];
+            out[2 * b + threadIdx.x] = v;
+        }
+    }
+
+    /**
+     * diagnostic_fields (subprog_binary_diagnostics.cpp:48-82): sigma, v_r = v . rhat, v_phi = v . phihat per cell,
+     * block major [B][3][NN] for the writer.
+     */
+    __global__ void diagnostic_fields_kernel(mesh_dev_t mesh, const double* __restrict__ U, double* __restrict__ out, int BO)
+    {
+        const int N = mesh.N;
+        const size_t NN = size_t(N) * N, n = size_t(BO) * NN;
+        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
+        {
+            const size_t b = k / NN, cell = k % NN;
+            const int i = int(cell / N), j = int(cell % N);
+            const double* xv = mesh.xv + b * (N + 1);
+            const double* yv = mesh.yv + b * (N + 1);
+            const double xc = (xv[i] + xv[i + 1]) * 0.5, yc = (yv[j] + yv[j + 1]) * 0.5;
+            const double rc = sqrt(xc * xc + yc * yc);
+            const double sigma = U[k], vx = U[mesh.FS + k] / sigma, vy = U[2 * mesh.FS + k] / sigma;
+            out[(b * 3 + 0) * NN + cell] = sigma;
+            out[(b * 3 + 1) * NN + cell] = vx * (xc / rc) + vy * (yc / rc);
+            out[(b * 3 + 2) * NN + cell] = vx * (-yc / rc) + vy * (xc / rc);
+        }
+    }
+
     /** [B][3][NN] (host, block major) <-> [3][B][NN] (device, field major) */
     __global__ void permute_state(const double* __restrict__ src, double* __restrict__ dst, int B, int NN, size_t FS, int to_device)
     {
@@ -1462,6 +1517,30 @@ void device_solver_t::download(const device_field_t& src, double* host)
     ++launches;
     M3B_CUDA(cudaGetLastError());
     M3B_CUDA(cudaMemcpyAsync(host, impl->d_staging, 3 * size_t(BO) * N * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaStreamSynchronize(s));
+}
+
+void device_solver_t::disk_totals(const device_field_t& src, double out[2])
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    auto s = cudaStream_t(stream_);
+    double* d = impl->d_staging;                    // [BO][2], idle between transfers
+    disk_totals_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, src.data, d);
+    ++launches;
+    auto h = std::vector<double>(size_t(BO) * 2);
+    M3B_CUDA(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3B_CUDA(cudaStreamSynchronize(s));
+    out[0] = out[1] = 0.0;
+    for (int b = 0; b < BO; ++b) { out[0] += h[2 * b]; out[1] += h[2 * b + 1]; }    // tree order, as the reference's .sum()
+}
+
+void device_solver_t::diagnostic_fields(const device_field_t& src, double* host)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    auto s = cudaStream_t(stream_);
+    diagnostic_fields_kernel<<<impl->sm_count * 4, 256, 0, s>>>(impl->mesh, src.data, impl->d_staging, BO);
+    ++launches;
+    M3B_CUDA(cudaMemcpyAsync(host, impl->d_staging, size_t(BO) * 3 * N * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     M3B_CUDA(cudaStreamSynchronize(s));
 }
 
