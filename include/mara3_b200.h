@@ -87,6 +87,7 @@ void        m3b_neighbor_table(const m3b_solver_t* s, int* out);
 void        m3b_face_neighbor_table(const m3b_solver_t* s, int* out);
 uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
 /* ---- HDF5 products and the subprogram itself (no libhdf5 needed: mara3_b200/csrc/h5lite.cpp) ----
+ * (with several ranks the writers are collective calls: every rank hands its blocks to rank 0, which writes the file)
  * m3b_write_checkpoint   replaces mara::write<state_t> into chkpt.NNNN.h5 (subprog_binary_io.cpp:131-158) for a solution
  *                        with the initial schedule and an empty time series; the run loop below stores its full state
  * m3b_write_diagnostics  replaces mara::write<diagnostic_fields_t> (subprog_binary_io.cpp:160-172, subprog_binary_diagnostics.cpp:48-82)
@@ -98,6 +99,8 @@ int         m3b_write_diagnostics(m3b_solver_t* s, const m3b_solution_t* u, cons
 int         m3b_read_checkpoint(m3b_solver_t* s, m3b_solution_t* u, const char* filename);
 int         m3b_time_series_sample(m3b_solver_t* s, const m3b_solution_t* u, double* out47);
 int         m3b_binary_main(int argc, const char* const* argv, int device);
+/* the same on `nranks` GPUs, one process each: every rank runs the loop, rank 0 prints and writes the gathered products */
+int         m3b_binary_main_distributed(int argc, const char* const* argv, int device, int rank, int nranks, const unsigned char* nccl_unique_id128);
 /* test hook of the built-in HDF5 writer / reader (h5lite): write one file with every structure it emits and / or
  * list the root group of an existing file into `report`; 0 or -1 (message in `report`) */
 int         m3b_h5_selftest(const char* write_path, const char* read_path, char* report, int report_len);

@@ -90,6 +90,7 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, C.c_char_p]
     L.m3b_time_series_sample.argtypes = [vp, vp, dp]
     L.m3b_binary_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
+    L.m3b_binary_main_distributed.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_char_p]
     L.m3b_halo_bytes_per_exchange.argtypes = [vp]
     L.m3b_halo_bytes_per_exchange.restype = C.c_uint64
     L.m3b_solver_destroy.argtypes = [vp]
@@ -434,11 +435,14 @@ def orbital_elements(bodies, t):
     return out
 
 
-def binary_main(argv, device=0):
-    """The `binary` subprogram (subprog_binary.cpp:414-436): argv = ["binary", "key=value", ...]; returns the exit code."""
+def binary_main(argv, device=0, rank=0, nranks=1, nccl_unique_id=None):
+    """The `binary` subprogram (subprog_binary.cpp:414-436): argv = ["binary", "key=value", ...]; returns the exit code.
+    With nranks > 1 every rank (one process per GPU) calls this; rank 0 prints and writes the gathered products."""
     load_library()
     args = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
-    return _lib.m3b_binary_main(len(argv), args, int(device))
+    if nranks == 1:
+        return _lib.m3b_binary_main(len(argv), args, int(device))
+    return _lib.m3b_binary_main_distributed(len(argv), args, int(device), int(rank), int(nranks), bytes(nccl_unique_id))
 
 
 def nccl_unique_id():

@@ -88,9 +88,9 @@ namespace
         }
     }
 
-    std::string leaf_name(const solver_data_t& data, int local_block)
+    std::string leaf_name(const solver_data_t& data, int global_block)
     {
-        auto index = data.tree->index(data.global_block(local_block));
+        auto index = data.tree->index(global_block);
         return format_tree_index(index.level, int(index.i), int(index.j));
     }
 }
@@ -125,8 +125,13 @@ void m3b::write_checkpoint(const std::string& filename, binary_solver_t& solver,
 {
     const auto& data = solver.solver_data();
     const auto& u = state.solution;
-    const int N = data.block_size, B = data.num_owned;
+    // several ranks: a collective -- every rank hands its blocks to rank 0, which writes the one file
+    const int N = data.block_size, B = data.num_blocks;
     const std::size_t NN = std::size_t(N) * N;
+    const bool root = solver.device().rank() == 0;
+    auto planes = std::vector<double>(root ? std::size_t(B) * 3 * NN : 0);
+    solver.device().gather_state(*u.conserved_u, planes.data());
+    if (! root) return;
     auto w = h5::writer_t(filename);
     auto v2 = type_t::array(type_t::f64(), 2), v3 = type_t::array(type_t::f64(), 3), el = elements_type();
 
@@ -137,8 +142,6 @@ void m3b::write_checkpoint(const std::string& filename, binary_solver_t& solver,
 
     // conserved_u/<level:ii-jj>: (N, N) of double[3], the raw image of the reference's std::tuple<sigma, px, py>,
     // which libstdc++ lays out in reverse: (py, px, sigma)  (SURVEY.md 8c caveat 1)
-    auto planes = std::vector<double>(std::size_t(B) * 3 * NN);
-    solver.device().download(*u.conserved_u, planes.data());
     auto cells = std::vector<double>(planes.size());
     for (int b = 0; b < B; ++b)
         for (std::size_t c = 0; c < NN; ++c)
@@ -176,8 +179,12 @@ void m3b::write_checkpoint(const std::string& filename, binary_solver_t& solver,
 void m3b::write_diagnostics(const std::string& filename, binary_solver_t& solver, const solution_t& u)
 {
     const auto& data = solver.solver_data();
-    const int N = data.block_size, B = data.num_owned, V = N + 1;
+    const int N = data.block_size, B = data.num_blocks, V = N + 1;
     const std::size_t NN = std::size_t(N) * N;
+    const bool root = solver.device().rank() == 0;
+    auto fields = std::vector<double>(root ? std::size_t(B) * 3 * NN : 0);
+    solver.device().gather_diagnostic_fields(*u.conserved_u, fields.data());       // collective
+    if (! root) return;
     auto w = h5::writer_t(filename);
     auto v2 = type_t::array(type_t::f64(), 2);
 
@@ -187,14 +194,15 @@ void m3b::write_diagnostics(const std::string& filename, binary_solver_t& solver
     // vertices/<idx>: (N + 1, N + 1) of (x, y)
     auto verts = std::vector<double>(std::size_t(B) * V * V * 2);
     for (int b = 0; b < B; ++b)
+    {
+        const auto& leaf = data.tree->leaf_node(b);             // the whole tree is known on every rank
         for (int i = 0; i < V; ++i)
             for (int j = 0; j < V; ++j)
             {
-                verts[((std::size_t(b) * V + i) * V + j) * 2 + 0] = data.xv[std::size_t(b) * V + i];
-                verts[((std::size_t(b) * V + i) * V + j) * 2 + 1] = data.yv[std::size_t(b) * V + j];
+                verts[((std::size_t(b) * V + i) * V + j) * 2 + 0] = leaf.xv[i] * data.domain_radius;
+                verts[((std::size_t(b) * V + i) * V + j) * 2 + 1] = leaf.yv[j] * data.domain_radius;
             }
-    auto fields = std::vector<double>(std::size_t(B) * 3 * NN);
-    solver.device().diagnostic_fields(*u.conserved_u, fields.data());
+    }
     const char* names[3] = {"sigma", "radial_velocity", "phi_velocity"};
     for (const char* n : names) w.require_group(std::string("/") + n);
     w.require_group("/vertices");
@@ -247,11 +255,11 @@ state_t m3b::read_checkpoint(const std::string& filename, binary_solver_t& solve
     u.iteration_num = iteration[0]; u.iteration_den = iteration[1];
 
     auto names = r.keys("/solution/conserved_u");
-    if (int(names.size()) != B) throw std::runtime_error("restart file has " + std::to_string(names.size()) + " blocks, the run configuration makes " + std::to_string(B));
+    if (int(names.size()) != data.num_blocks) throw std::runtime_error("restart file has " + std::to_string(names.size()) + " blocks, the run configuration makes " + std::to_string(data.num_blocks));
     auto planes = std::vector<double>(std::size_t(B) * 3 * NN);
     for (int b = 0; b < B; ++b)
     {
-        const auto path = "/solution/conserved_u/" + leaf_name(data, b);
+        const auto path = "/solution/conserved_u/" + leaf_name(data, data.global_block(b));     // every rank reads its own blocks
         if (! r.exists(path)) throw std::runtime_error("restart file has no block " + path + " (different mesh?)");
         auto shape = r.shape(path);
         if (shape.size() != 2 || int(shape[0]) != N || int(shape[1]) != N) throw std::runtime_error("restart block " + path + " has the wrong shape");
@@ -319,7 +327,7 @@ namespace
     }
 
     /** binary::run_tasks (subprog_binary.cpp:313-381): diagnostics, time series, checkpoint -- those due in the INCOMING state. */
-    void run_tasks(binary_solver_t& solver, state_t& state)
+    void run_tasks(binary_solver_t& solver, state_t& state, bool root)
     {
         const auto due = state.schedule;
         const auto outdir = solver.run_config().get_string("outdir");
@@ -328,7 +336,7 @@ namespace
         {
             auto fname = numbered(outdir, "diagnostics", state.schedule.at("write_diagnostics").num_times_performed);
             write_diagnostics(fname, solver, state.solution);
-            std::printf("write diagnostics: %s\n", fname.c_str());
+            if (root) std::printf("write diagnostics: %s\n", fname.c_str());
             state.schedule.mark_as_completed("write_diagnostics");
         }
         if (due.at("record_time_series").is_due)
@@ -342,7 +350,7 @@ namespace
             auto fname = numbered(outdir, "chkpt", state.schedule.at("write_checkpoint").num_times_performed);
             state.schedule.mark_as_completed("write_checkpoint");
             write_checkpoint(fname, solver, state);
-            std::printf("write checkpoint: %s\n", fname.c_str());
+            if (root) std::printf("write checkpoint: %s\n", fname.c_str());
         }
     }
 
@@ -358,8 +366,10 @@ namespace
     }
 }
 
-int m3b::binary_main(int argc, const char* const argv[], int device)
+int m3b::binary_main(int argc, const char* const argv[], int device, int rank, int nranks, const unsigned char* nccl_unique_id)
 {
+    const bool root = rank == 0;        // several ranks: rank 0 prints and writes; the products are gathered (binary_io.cpp)
+
     // ---- create_run_config (subprog_binary.cpp:155-164): template <- restart file's run_config <- command line
     auto config = config_t::binary_template();
     std::string restart;
@@ -377,8 +387,8 @@ int m3b::binary_main(int argc, const char* const argv[], int device)
             if (eq != std::string::npos) config.set(arg.substr(0, eq), arg.substr(eq + 1));
         }
     }
-    auto solver = binary_solver_t(config, device);
-    solver.set_quiet(false);
+    auto solver = binary_solver_t(config, device, false, false, rank, nranks, nccl_unique_id);
+    solver.set_quiet(! root);
 
     auto state = state_t();
     if (restart.empty())
@@ -388,9 +398,9 @@ int m3b::binary_main(int argc, const char* const argv[], int device)
     }
     else state = read_checkpoint(restart, solver);
 
-    require_dir(config.get_string("outdir"));
-    config.pretty_print(std::cout, "config");
-    run_tasks(solver, state);
+    if (root) require_dir(config.get_string("outdir"));
+    if (root) config.pretty_print(std::cout, "config");
+    run_tasks(solver, state, root);
 
     const double cells = double(solver.solver_data().num_cells());
     auto step = [&] ()
@@ -402,16 +412,19 @@ int m3b::binary_main(int argc, const char* const argv[], int device)
         auto st = solver.next_solution(state.solution, &dt, &fell_back);
         if (st != status_ok) throw std::runtime_error(solver.last_error().empty() ? "the step failed" : solver.last_error());
         mark_tasks(config, time_before, state.schedule);
-        run_tasks(solver, state);
+        run_tasks(solver, state, root);
     };
     while (state.solution.time / (2 * M_PI) < config.get_double("tfinal"))
     {
         auto t0 = std::chrono::high_resolution_clock::now();
         step();
         auto ms = 1e-6 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count());
-        std::printf("[%04d] orbits=%3.7lf kzps=%3.2lf\n", state.solution.iteration_num / state.solution.iteration_den,
-                    state.solution.time / (2 * M_PI), cells / ms);
-        std::fflush(stdout);
+        if (root)
+        {
+            std::printf("[%04d] orbits=%3.7lf kzps=%3.2lf\n", state.solution.iteration_num / state.solution.iteration_den,
+                        state.solution.time / (2 * M_PI), cells / ms);
+            std::fflush(stdout);
+        }
     }
     step();     // the reference finishes with tasks(next(state)): one more step and its tasks
     return 0;

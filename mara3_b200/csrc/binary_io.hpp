@@ -77,6 +77,7 @@ namespace m3b
     /**
      * The subprogram: `binary key=value ...` (subprog_binary.cpp:414-436) -- config, initial or restarted state,
      * run loop with the scheduled tasks, the same stdout lines and output files.  Returns the exit code.
+     * With nranks > 1 (one process per GPU) every rank runs the same loop; rank 0 prints and writes the gathered products.
      */
-    int binary_main(int argc, const char* const argv[], int device);
+    int binary_main(int argc, const char* const argv[], int device, int rank = 0, int nranks = 1, const unsigned char* nccl_unique_id = nullptr);
 }

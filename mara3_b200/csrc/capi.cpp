@@ -188,6 +188,23 @@ int m3b_time_series_sample(m3b_solver_t* s, const m3b_solution_t* u, double* out
     });
 }
 
+int m3b_binary_main_distributed(int argc, const char* const* argv, int device, int rank, int nranks, const unsigned char* nccl_unique_id)
+{
+    try
+    {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        int code = m3b::binary_main(argc, argv, device, rank, nranks, nccl_unique_id);
+        double s = 1e-9 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count());
+        if (rank == 0) std::cout << "total execution time: " << s << " seconds" << std::endl;
+        return code;
+    }
+    catch (const std::exception& e)
+    {
+        std::cout << e.what() << std::endl;
+        return 1;
+    }
+}
+
 int m3b_binary_main(int argc, const char* const* argv, int device)
 {
     // app_main.cpp:75-79: run the subprogram, then report the wall time; an exception ends the run with its message

@@ -69,7 +69,13 @@ namespace m3b
         void upload(const double* host_block_major, device_field_t& dst);
         void download(const device_field_t& src, double* host_block_major);
         void copy(const device_field_t& src, device_field_t& dst);
-        /** disk_mass, disk_angular_momentum of the owned blocks (subprog_binary_diagnostics.cpp:19-41). */
+        /** Collective: every rank's owned blocks on rank 0, in global block order (one rank: a download). */
+        void gather_blocks(const double* d_local, std::size_t doubles_per_block, double* host_all);
+        void gather_state(const device_field_t& src, double* host_all);              // [global block][3][N][N] on rank 0
+        void gather_diagnostic_fields(const device_field_t& src, double* host_all);  // sigma, v_r, v_phi, same layout
+        int rank() const { return rank_; }
+        int ranks() const { return num_ranks; }
+        /** disk_mass, disk_angular_momentum (subprog_binary_diagnostics.cpp:19-41); summed over the ranks (collective). */
         void disk_totals(const device_field_t& src, double out[2]);
         /** sigma, radial velocity, azimuthal velocity, [owned block][3][N][N] on the host (subprog_binary_diagnostics.cpp:48-82). */
         void diagnostic_fields(const device_field_t& src, double* host);

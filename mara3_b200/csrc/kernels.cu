@@ -1076,6 +1076,7 @@ struct device_solver_t::impl_t
     model_t model {};
     int tile_x = 0, tile_y = 0;
     int strip_min_ctas = 4;
+    int num_global_blocks = 0;
     int num_interior = 0;                   // leading entries of `regular` that touch no ghost block
     bool overlap_exchange = false;          // M3B_OVERLAP_EXCHANGE=1: exchange on its own stream beside the interior update
     cudaStream_t comm_stream = nullptr;     // guard-zone exchange runs here, beside the interior update
@@ -1176,6 +1177,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     cells = sd.num_local_cells();
     const auto& tree = *sd.tree;
     const auto& part = sd.partition;
+    impl->num_global_blocks = sd.num_blocks;
     auto local = [&part] (int global) { return global < 0 ? -1 : part.global_to_local[global]; };
 
     cudaStream_t s;
@@ -1520,6 +1522,64 @@ void device_solver_t::download(const device_field_t& src, double* host)
     M3B_CUDA(cudaStreamSynchronize(s));
 }
 
+/** Collective over the ranks: the owned blocks' data (`d_local`: [owned block][doubles_per_block], device memory) of every
+ *  rank, concatenated in rank (= global Morton) order into `host_all` on rank 0.  One rank: a plain download. */
+void device_solver_t::gather_blocks(const double* d_local, std::size_t doubles_per_block, double* host_all)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    auto s = cudaStream_t(stream_);
+    if (num_ranks == 1)
+    {
+        M3B_CUDA(cudaMemcpyAsync(host_all, d_local, size_t(BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
+        M3B_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    const int total = impl->num_global_blocks;
+    auto offsets = std::vector<size_t>(num_ranks + 1);
+    for (int r = 0; r <= num_ranks; ++r) offsets[r] = size_t((long(total) * r) / num_ranks);       // partition_offsets
+    auto send = std::vector<const double*>(num_ranks, nullptr);
+    auto recv = std::vector<double*>(num_ranks, nullptr);
+    auto send_count = std::vector<size_t>(num_ranks, 0), recv_count = std::vector<size_t>(num_ranks, 0);
+    double* d_all = nullptr;
+
+    if (rank_ == 0)
+    {
+        M3B_CUDA(cudaMalloc(&d_all, std::max<size_t>(1, size_t(total - BO)) * doubles_per_block * sizeof(double)));
+        for (int p = 1; p < num_ranks; ++p)
+        {
+            recv[p] = d_all + (offsets[p] - offsets[1]) * doubles_per_block;
+            recv_count[p] = (offsets[p + 1] - offsets[p]) * doubles_per_block;
+        }
+    }
+    else { send[0] = d_local; send_count[0] = size_t(BO) * doubles_per_block; }
+    impl->comm->exchange(send, send_count, recv, recv_count, stream_);
+
+    if (rank_ == 0)
+    {
+        M3B_CUDA(cudaMemcpyAsync(host_all, d_local, size_t(BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
+        M3B_CUDA(cudaMemcpyAsync(host_all + size_t(BO) * doubles_per_block, d_all, size_t(total - BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    M3B_CUDA(cudaStreamSynchronize(s));
+    if (d_all) M3B_CUDA(cudaFree(d_all));
+}
+
+/** [block][3][N][N] of every rank's owned blocks on rank 0 (the layout of download()). */
+void device_solver_t::gather_state(const device_field_t& src, double* host_all)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    permute_state<<<impl->sm_count * 4, 256, 0, cudaStream_t(stream_)>>>(src.data, impl->d_staging, BO, N * N, cells, 0);
+    ++launches;
+    gather_blocks(impl->d_staging, size_t(3) * N * N, host_all);
+}
+
+void device_solver_t::gather_diagnostic_fields(const device_field_t& src, double* host_all)
+{
+    M3B_CUDA(cudaSetDevice(device_id));
+    diagnostic_fields_kernel<<<impl->sm_count * 4, 256, 0, cudaStream_t(stream_)>>>(impl->mesh, src.data, impl->d_staging, BO);
+    ++launches;
+    gather_blocks(impl->d_staging, size_t(3) * N * N, host_all);
+}
+
 void device_solver_t::disk_totals(const device_field_t& src, double out[2])
 {
     M3B_CUDA(cudaSetDevice(device_id));
@@ -1532,6 +1592,16 @@ void device_solver_t::disk_totals(const device_field_t& src, double out[2])
     M3B_CUDA(cudaStreamSynchronize(s));
     out[0] = out[1] = 0.0;
     for (int b = 0; b < BO; ++b) { out[0] += h[2 * b]; out[1] += h[2 * b + 1]; }    // tree order, as the reference's .sum()
+    if (num_ranks > 1)
+    {
+        // per-rank sums folded in rank order on every rank
+        for (int k = 0; k < 2; ++k)
+        {
+            auto parts = all_gather_scalar(out[k]);
+            out[k] = 0.0;
+            for (double v : parts) out[k] += v;
+        }
+    }
 }
 
 void device_solver_t::diagnostic_fields(const device_field_t& src, double* host)
