@@ -381,20 +381,27 @@ namespace
         }
 
         // ------------------------------------------------------------------ fold the CTA's sums
-        // per-warp shuffle tree over the groups that can be non-zero, then 4 warps through shared memory
+        // per warp, then 4 warps through shared memory
         __syncwarp();
-        #pragma unroll
-        for (int k = GRV_FX; k < NUM_SUMS; ++k)
         {
-            const bool buffer_group = k >= BUF_M;
-            double v = 0.0;
-            if (! buffer_group || has_buffer)      // warp-uniform
+            // Eight sums over 32 lanes by recursive halving: at distances 16, 8, 4 a lane keeps half of its values and
+            // trades the other half (7 exchanged doubles instead of 8 x 3), then two butterfly steps finish the one value
+            // that is left: 9 shuffled doubles per lane instead of 40.  Lane 4 j ends with the total of value j.
+            static_assert(NUM_SUMS - GRV_FX == 8, "the halving below is written for eight values");
+            double v4[4], v2[2], v1;
+            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
             {
-                v = sums[k];
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const double lo = sums[GRV_FX + k], hi = sums[GRV_FX + 4 + k];
+                v4[k] = (b16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b16 ? lo : hi, 16);
             }
-            if (lane == 0) T.red[warp][k] = v;
+            #pragma unroll
+            for (int k = 0; k < 2; ++k) v2[k] = (b8 ? v4[2 + k] : v4[k]) + __shfl_xor_sync(0xffffffffu, b8 ? v4[k] : v4[2 + k], 8);
+            v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v2[0] : v2[1], 4);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            if ((lane & 3) == 0) T.red[warp][GRV_FX + (lane >> 2)] = v1;
         }
         if (lane < GRV_FX) T.red[warp][lane] = T.sinks[warp][lane];
         {
