@@ -144,7 +144,7 @@ namespace m3b
         void launch_stage_kernels(const device_field_t& in, const device_field_t* un, device_field_t& out, int slot, bool exchange, int finish_mode = 0, int stage_mode = 0);
         void exchange_on(void* cuda_stream, device_field_t& field);
         stage_result_t* result_target(int slot);
-        void launch_finish(const double* tile_rows, int num_fused, int tpb, const double* general_rows, int num_rows, int slot, int finish_mode);
+        void launch_finish(const double* tile_rows, int num_fused, int tpb, const double* general_rows, int gtpb, int num_rows, int slot, int finish_mode);
         struct impl_t;
         std::unique_ptr<impl_t> impl;
         int device_id = 0;

@@ -413,6 +413,42 @@ namespace
         }
     }
 
+    /** The same in TX x TY tiles: the tile's primitives plus one guard layer go through shared memory once. */
+    template<int TX, int TY>
+    __global__ void __launch_bounds__(THREADS) general_gradients_tiled(
+        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
+        const double* __restrict__ Uin, double* __restrict__ G)
+    {
+        __shared__ double P[3][TX + 2][TY + 2];
+        const stage_t S = *stage_ptr;
+        const int N = mesh.N;
+        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
+        const int b = list[blockIdx.x / tiles_per_block], t = blockIdx.x % tiles_per_block;
+        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
+        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
+        const size_t base = size_t(mesh.gslot[b]) * N * N;
+
+        for (int k = threadIdx.x; k < (TX + 2) * (TY + 2); k += THREADS)
+        {
+            const int li = k / (TY + 2), lj = k % (TY + 2);
+            if ((li == 0 || li == TX + 1) && (lj == 0 || lj == TY + 1)) continue;      // corners are not part of the stencil
+            const prim_t p = prim_at(mesh, Uin, b, i0 - 1 + li, j0 - 1 + lj);
+            P[0][li][lj] = p.s; P[1][li][lj] = p.vx; P[2][li][lj] = p.vy;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < TX * TY; k += THREADS)
+        {
+            const int li = k / TY + 1, lj = k % TY + 1;
+            const size_t c = base + size_t(i0 + li - 1) * N + (j0 + lj - 1);
+            #pragma unroll
+            for (int q = 0; q < 3; ++q)
+            {
+                G[q * mesh.GS + c]       = plm_diff(P[q][li - 1][lj], P[q][li][lj], P[q][li + 1][lj], theta) * inv_h;
+                G[(3 + q) * mesh.GS + c] = plm_diff(P[q][li][lj - 1], P[q][li][lj], P[q][li][lj + 1], theta) * inv_h;
+            }
+        }
+    }
+
     /**
      * Flux (times face length) through face f (0..N) of block b along AXIS at transverse index k,
      * as block b computes it: block_fluxes_u (scheme.cpp:472-516).
@@ -519,6 +555,133 @@ namespace
             if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
         }
         reduce_and_store(red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
+    }
+
+
+    /**
+     * P6-P8 + P11 for blocks at refinement jumps, one CTA per TX x TY tile: the same update as general_update, but the
+     * tile's primitives (guard cells through prolongation / restriction, mesh_tree_operators.hpp:223-252) and the
+     * gradients of general_gradients are staged in shared memory once, every face flux is computed once, and only the
+     * faces on a block side whose neighbour is finer take the slow path (sum of the two fine fluxes, scheme.cpp:614-720).
+     * Rows: one per tile, folded per block by finish_stage like the fused kernels' rows.
+     */
+    template<int TX, int TY>
+    __global__ void __launch_bounds__(THREADS, 2) general_update_tiled(
+        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
+        const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
+        double* __restrict__ partials, fail_dev_t* fail)
+    {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
+
+        const stage_t S = *stage_ptr;
+        const int N = mesh.N;
+        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
+        const int b  = list[blockIdx.x / tiles_per_block];
+        const int t  = blockIdx.x % tiles_per_block;
+        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
+        const size_t FS = mesh.FS;
+        const int tid = threadIdx.x;
+        const double h = mesh.spacing[b];
+
+        // ---- tile + 1 guard layer (no corners: a face only needs its two cells): primitives and physical gradients
+        for (int k = tid; k < (TX + 2) * (TY + 2); k += THREADS)
+        {
+            const int li = k / (TY + 2), lj = k % (TY + 2);         // region cell <-> block cell (i0 - 1 + li, j0 - 1 + lj)
+            const bool edge_i = li == 0 || li == TX + 1, edge_j = lj == 0 || lj == TY + 1;
+            if (edge_i && edge_j) continue;
+            const int gi = i0 - 1 + li, gj = j0 - 1 + lj;
+            const prim_t p = prim_at(mesh, Uin, b, gi, gj);
+            const prim_t gx = grad_at(mesh, G, 0, b, gi, gj), gy = grad_at(mesh, G, 1, b, gi, gj);
+            T.P[0][li][lj] = p.s;  T.P[1][li][lj] = p.vx;  T.P[2][li][lj] = p.vy;
+            T.G[0][li][lj] = gx.s; T.G[1][li][lj] = gx.vx; T.G[2][li][lj] = gx.vy;
+            T.G[3][li][lj] = gy.s; T.G[4][li][lj] = gy.vx; T.G[5][li][lj] = gy.vy;
+        }
+        if (tid <= TX) T.xv[tid] = mesh.xv[size_t(b) * (N + 1) + i0 + tid];
+        if (tid >= 64 && tid - 64 <= TY) T.yv[tid - 64] = mesh.yv[size_t(b) * (N + 1) + j0 + tid - 64];
+        __syncthreads();
+
+        // ---- fluxes (times face length, as block_fluxes_u, scheme.cpp:472-516)
+        const bool finer_lo_x = i0 == 0 && mesh.nbr[b * 4 + 0].kind == 2, finer_hi_x = i0 + TX == N && mesh.nbr[b * 4 + 1].kind == 2;
+        const bool finer_lo_y = j0 == 0 && mesh.nbr[b * 4 + 2].kind == 2, finer_hi_y = j0 + TY == N && mesh.nbr[b * 4 + 3].kind == 2;
+
+        auto x_face = [&] (int li, int lj)      // between tile cells (li - 1, lj) and (li, lj), 0 <= li <= TX
+        {
+            double F[3];
+            if ((li == 0 && finer_lo_x) || (li == TX && finer_hi_x)) general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i0 + li, j0 + lj, F);
+            else
+            {
+                const eos_t e = eos_at_face(model, S, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]));
+                const prim_t pl = {T.P[0][li][lj + 1], T.P[1][li][lj + 1], T.P[2][li][lj + 1]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
+                const prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]}, gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
+                face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5 * h, 1.0, F);
+                const double len = T.yv[lj + 1] - T.yv[lj];
+                F[0] *= len; F[1] *= len; F[2] *= len;
+            }
+            T.Fx[0][li][lj] = F[0]; T.Fx[1][li][lj] = F[1]; T.Fx[2][li][lj] = F[2];
+        };
+        auto y_face = [&] (int li, int lj)      // between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= TY
+        {
+            double F[3];
+            if ((lj == 0 && finer_lo_y) || (lj == TY && finer_hi_y)) general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j0 + lj, i0 + li, F);
+            else
+            {
+                const eos_t e = eos_at_face(model, S, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj]);
+                const prim_t pl = {T.P[0][li + 1][lj], T.P[1][li + 1][lj], T.P[2][li + 1][lj]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
+                const prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]}, gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
+                face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5 * h, 1.0, F);
+                const double len = T.xv[li + 1] - T.xv[li];
+                F[0] *= len; F[1] *= len; F[2] *= len;
+            }
+            T.Fy[0][li][lj] = F[0]; T.Fy[1][li][lj] = F[1]; T.Fy[2][li][lj] = F[2];
+        };
+        for (int k = tid; k < TX * TY; k += THREADS)
+        {
+            x_face(k / TY, k % TY);
+            y_face(k / TY, k % TY);
+        }
+        for (int k = tid; k < TX + TY; k += THREADS)
+        {
+            if (k < TY) x_face(TX, k); else y_face(k - TY, TY);
+        }
+        __syncthreads();
+
+        // ---- update (block_update_u, scheme.cpp:568-587), validation, CFL estimate
+        double sums[NUM_SUMS];
+        #pragma unroll
+        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
+        double dtmin = 1e300;
+
+        for (int k = tid; k < TX * TY; k += THREADS)
+        {
+            const int li = k / TY, lj = k % TY;
+            const size_t c = (size_t(b) * N + (i0 + li)) * N + (j0 + lj);
+            const double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
+            const double br = mesh.br[c];
+            const double u0s = mesh.U0[c], u0x = mesh.U0[FS + c], u0y = mesh.U0[2 * FS + c];
+            const double x = 0.5 * (T.xv[li] + T.xv[li + 1]), y = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
+            const double dt_over_dA = S.dt / ((T.xv[li + 1] - T.xv[li]) * (T.yv[lj + 1] - T.yv[lj]));
+            double src[3], y1, y2;
+            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
+
+            double n0 = s  - ((T.Fx[0][li + 1][lj] - T.Fx[0][li][lj]) + (T.Fy[0][li][lj + 1] - T.Fy[0][li][lj])) * dt_over_dA + src[0];
+            double n1 = px - ((T.Fx[1][li + 1][lj] - T.Fx[1][li][lj]) + (T.Fy[1][li][lj + 1] - T.Fy[1][li][lj])) * dt_over_dA + src[1];
+            double n2 = py - ((T.Fx[2][li + 1][lj] - T.Fx[2][li][lj]) + (T.Fy[2][li][lj + 1] - T.Fy[2][li][lj])) * dt_over_dA + src[2];
+
+            if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
+
+            if (S.combine)
+            {
+                const double w = 1.0 - S.rk_b0;
+                n0 = Un[c] * S.rk_b0 + n0 * w;
+                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
+                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
+            }
+            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
+
+            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
+        }
+        reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
     }
 
 
@@ -706,14 +869,14 @@ namespace
      * Fold the stage kernels' rows in a fixed order (deterministic) and publish the stage result.
      * Rows [0, num_fused) are regular blocks: their `tpb` tile rows (written by stage_strip / stage_fused,
      * no fences or tickets in those kernels) are first folded, in tile order, into one row per block;
-     * rows [num_fused, num_rows) come one per block from the general path.
+     * rows [num_fused, num_rows) are the any-tree path's blocks, `gtpb` tile rows each (1: one row per block).
      * The reference evaluates the work done on each body PER BLOCK from that block's accreted
      * mass and momentum -- a non-linear function -- and then sums over blocks
      * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
      * CTA c handles FINISH_ROWS_PER_CTA block rows; the last CTA to finish folds the CTA rows in CTA order.
      */
     __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* tile_rows, int num_fused, int tpb,
-        const double* general_rows, int num_rows, double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr,
+        const double* general_rows, int gtpb, int num_rows, double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr,
         fail_dev_t* fail, stage_result_t* result, prepare_args_t prep)
     {
         __shared__ double dt_min_all;
@@ -740,7 +903,17 @@ namespace
                     v = k == NUM_SUMS ? dmin(v, p) : v + p;
                 }
             }
-            else v = __ldcg(general_rows + size_t(R - num_fused) * ROW + k);
+            else
+            {
+                // blocks of the any-tree path: gtpb tile rows each (general_update_tiled), or one row (general_update)
+                const double* rows = general_rows + size_t(R - num_fused) * gtpb * ROW + k;
+                v = __ldcg(rows);
+                for (int t = 1; t < gtpb; ++t)
+                {
+                    double p = __ldcg(rows + size_t(t) * ROW);
+                    v = k == NUM_SUMS ? dmin(v, p) : v + p;
+                }
+            }
             srow[r][k] = v;
         }
         __syncthreads();
@@ -1106,6 +1279,8 @@ struct device_solver_t::impl_t
     int ring_next = 0;
     double* d_partials2 = nullptr;              // second row buffer: the two stages of a step stay separate
     double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
+    double* d_general_tile_rows[2] = {nullptr, nullptr};    // general_update_tiled: one row per tile of a block at a refinement jump
+    bool untiled_general = false;               // M3B_UNTILED_GENERAL=1: the one-CTA-per-block any-tree update (reference for the tiled one)
     double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows, one set per slot parity
     size_t cta_rows_stride = 0;
     cudaStream_t finish_stream = nullptr;       // finish_stage of a step's first stage runs here, beside the second stage
@@ -1330,6 +1505,12 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_partials2, max_rows * ROW * sizeof(double)));
     for (auto& p : impl->d_block_rows) M3B_CUDA(cudaMalloc(&p, size_t(BO + 1) * ROW * sizeof(double)));
+    if (N % 16 == 0)
+    {
+        for (auto& p : impl->d_general_tile_rows) M3B_CUDA(cudaMalloc(&p, std::max<size_t>(1, size_t(BO) * (N / 16) * (N / 16)) * ROW * sizeof(double)));
+        M3B_CUDA(cudaFuncSetAttribute(general_update_tiled<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(tile_t<16, 16>))));
+    }
+    if (const char* e = std::getenv("M3B_UNTILED_GENERAL")) impl->untiled_general = std::atoi(e) != 0;
     impl->cta_rows_stride = size_t(BO / FINISH_ROWS_PER_CTA + 1) * ROW;
     M3B_CUDA(cudaMalloc(&impl->d_cta_rows, 2 * impl->cta_rows_stride * sizeof(double)));
     M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
@@ -1479,7 +1660,7 @@ device_solver_t::~device_solver_t()
     if (impl->h_results_all) cudaFreeHost(impl->h_results_all);
     if (impl->h_stage_ring) cudaFreeHost(impl->h_stage_ring);
     for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
-                   (void*) impl->d_cta_rows, (void*) impl->d_counters}) if (p) cudaFree(p);
+                   (void*) impl->d_cta_rows, (void*) impl->d_counters, (void*) impl->d_general_tile_rows[0], (void*) impl->d_general_tile_rows[1]}) if (p) cudaFree(p);
     for (auto e : impl->step_done) if (e) cudaEventDestroy(e);
     if (impl->stage_done) cudaEventDestroy(impl->stage_done);
     if (impl->side_finish_done) cudaEventDestroy(impl->side_finish_done);
@@ -1692,6 +1873,9 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     const int* d_general = force_general ? static_cast<const int*>(impl->owned[0]) : impl->d_irregular;
     const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
     int fused_ctas = num_fused * tpb;
+    // the any-tree path in 16 x 16 tiles where the block size allows (one row per tile), else one CTA and one row per block
+    const int gtpb = N % 16 == 0 && ! impl->untiled_general ? (N / 16) * (N / 16) : 1;
+    double* general_rows = gtpb > 1 ? impl->d_general_tile_rows[slot & 1] : block_rows;
     exchange = exchange && num_ranks > 1;
     impl->mark(s, "stage begin");
     bool waiting_tiles = false;
@@ -1775,22 +1959,27 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         // gradients are needed for the general blocks and every block they can fetch from
         int ng = int(impl->gradient_blocks.size());
-        general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
-            in.data, impl->d_gradients, un_data, out.data, block_rows, impl->d_fail + slot);
+        if (gtpb > 1) general_gradients_tiled<16, 16><<<ng * gtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        else general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        if (gtpb > 1)
+            general_update_tiled<16, 16><<<num_general * gtpb, THREADS, sizeof(tile_t<16, 16>), s>>>(impl->mesh, impl->model, st, d_general,
+                in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
+        else
+            general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
+                in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
     if (waiting_tiles) M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));     // join the exchange stream
     impl->mark(s, "stage kernels done");
-    launch_finish(partials, num_fused, tpb, block_rows, num_fused + num_general, slot, finish_mode);
+    launch_finish(partials, num_fused, tpb, general_rows, gtpb, num_fused + num_general, slot, finish_mode);
     impl->mark(s, "finish done (or forked)");
     M3B_CUDA(cudaGetLastError());
 }
 
 /** finish_mode 0: on the compute stream.  1: on the side stream, beside the next stage (its result is only read at the end of
  *  the step).  2: on the compute stream after the side stream's finish, with the next step's stage inputs written by the last CTA. */
-void device_solver_t::launch_finish(const double* tile_rows, int num_fused, int tpb, const double* general_rows, int num_rows, int slot, int finish_mode)
+void device_solver_t::launch_finish(const double* tile_rows, int num_fused, int tpb, const double* general_rows, int gtpb, int num_rows, int slot, int finish_mode)
 {
     auto s = cudaStream_t(stream_);
     int ctas = std::max(1, (num_rows + FINISH_ROWS_PER_CTA - 1) / FINISH_ROWS_PER_CTA);
@@ -1808,7 +1997,7 @@ void device_solver_t::launch_finish(const double* tile_rows, int num_fused, int 
         M3B_CUDA(cudaStreamWaitEvent(s, impl->side_finish_done, 0));
         prep = impl->pending_prepare;
     }
-    finish_stage<<<ctas, FINISH_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, num_rows, cta_rows,
+    finish_stage<<<ctas, FINISH_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, gtpb, num_rows, cta_rows,
         impl->d_counters + (slot & 1), impl->d_stage + slot, impl->d_fail + slot, result_target(slot), prep);
     ++launches;
     M3B_CUDA(cudaGetLastError());
@@ -1956,7 +2145,7 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     double* block_rows = impl->d_block_rows[slot & 1];
     max_timestep_kernel<<<BO, THREADS, 0, s>>>(impl->mesh, impl->model, impl->d_stage + slot, in.data, block_rows);
     ++launches;
-    launch_finish(nullptr, 0, 1, block_rows, BO, slot, 0);
+    launch_finish(nullptr, 0, 1, block_rows, 1, BO, slot, 0);
 }
 
 void device_solver_t::set_communicator(communicator_t* comm)
