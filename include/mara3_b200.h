@@ -94,6 +94,8 @@ uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
  * m3b_read_checkpoint    replaces mara::read<solution_t> (subprog_binary_io.cpp:174-190): the restart file must hold the solver's mesh
  * m3b_time_series_sample replaces record_time_series' sample (subprog_binary.cpp:358-379): the 47 doubles of time_series_sample_t
  * m3b_binary_main        replaces subprog_binary::main (subprog_binary.cpp:414-436): `binary key=value ...`, same stdout lines and files */
+/* dataset name of a leaf in the products: mara::format_tree_index (app_serialize_tree.hpp:72-87), "level:ii-jj" */
+void        m3b_format_tree_index(int level, int i, int j, char* out, int out_len);
 int         m3b_write_checkpoint(m3b_solver_t* s, const m3b_solution_t* u, const char* filename);
 int         m3b_write_diagnostics(m3b_solver_t* s, const m3b_solution_t* u, const char* filename);
 int         m3b_read_checkpoint(m3b_solver_t* s, m3b_solution_t* u, const char* filename);

@@ -154,6 +154,11 @@ void m3b_face_neighbor_table(const m3b_solver_t* s, int* out)
         }
 }
 
+void m3b_format_tree_index(int level, int i, int j, char* out, int out_len)
+{
+    std::snprintf(out, out_len, "%s", m3b::format_tree_index(level, i, j).c_str());
+}
+
 int m3b_write_checkpoint(m3b_solver_t* s, const m3b_solution_t* u, const char* filename)
 {
     return guarded(s, [&]

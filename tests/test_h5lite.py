@@ -83,3 +83,18 @@ def test_writer_output_parses_as_hdf5(tmp_path):
 def test_writer_refuses_duplicates_and_reader_reports_missing(tmp_path):
     rc, report = selftest(read_path=str(tmp_path / "absent.h5"))
     assert rc == -1 and "cannot open" in report
+
+
+def test_leaf_dataset_names_match_the_reference_known_answers():
+    """mara::format_tree_index known answers (Mara3 src/app_test.cpp:379-382), 2-D form: zero padded to the width of 2^level."""
+    lib = m3.load_library()
+    lib.m3b_format_tree_index.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    def name(level, i, j):
+        buf = C.create_string_buffer(64)
+        lib.m3b_format_tree_index(level, i, j, buf, 64)
+        return buf.value.decode()
+    assert name(0, 0, 0) == "0:0-0"
+    assert name(3, 5, 6) == "3:5-6"
+    assert name(5, 1, 16) == "5:01-16"
+    assert name(8, 1, 2) == "8:001-002"
+    assert name(4, 15, 0) == "4:15-00" and name(10, 1023, 7) == "10:1023-0007"
