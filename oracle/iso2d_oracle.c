@@ -388,9 +388,18 @@ m3o_mesh_t* m3o_mesh_create(const m3o_config_t* c)
                 /* initial conserved: subprog_binary.cpp:198-205, physics_iso2d.hpp:249-258 */
                 double p[3];
                 disk_profile(c, x, y, p);
-                U0[0 * N * N + i * N + j] = p[0];
-                U0[1 * N * N + i * N + j] = p[0] * p[1];
-                U0[2 * N * N + i * N + j] = p[0] * p[2];
+                if (c->conserve_linear_p)
+                {
+                    U0[0 * N * N + i * N + j] = p[0];
+                    U0[1 * N * N + i * N + j] = p[0] * p[1];
+                    U0[2 * N * N + i * N + j] = p[0] * p[2];
+                }
+                else    /* to_conserved_angmom_per_area (physics_iso2d.hpp:263-272): (sigma, Sr, Lz); held in the same array */
+                {
+                    U0[0 * N * N + i * N + j] = p[0];
+                    U0[1 * N * N + i * N + j] = p[0] * (x * p[1] + y * p[2]);
+                    U0[2 * N * N + i * N + j] = p[0] * (x * p[2] - y * p[1]);
+                }
 
                 double vmag = sqrt(p[1] * p[1] + p[2] * p[2]);
                 if (vmag > max_v) max_v = vmag;
@@ -765,6 +774,19 @@ static void viscous_flux(int axis, const double* gl, const double* gr, const dou
 }
 
 /* intercell_flux_u: scheme.cpp:268-293 */
+/* to_angmom_fluxes (scheme.cpp:199-214; physics_iso2d.hpp:434-441): F(Sr) = x F(px) + y F(py), F(Lz) = x F(py) - y F(px),
+ * and no angular momentum leaves through the domain edge */
+static void to_angmom_fluxes(int axis, double rd, double x, double y, double* f)
+{
+    double flux_px = f[1], flux_py = f[2];
+    double flux_sr = x * flux_px + y * flux_py;
+    double flux_lz = x * flux_py - y * flux_px;
+    if (axis == 0 && (x == -rd || x == rd)) flux_lz = 0.0;
+    if (axis == 1 && (y == -rd || y == rd)) flux_lz = 0.0;
+    f[1] = flux_sr;
+    f[2] = flux_lz;
+}
+
 static void intercell_flux_u(const m3o_config_t* c, const m3o_two_body_t* tb, int axis, double grid_spacing,
     double xf, double yf, const double* pl, const double* pr, const double* gl, const double* gr,
     const double* hl, const double* hr, double* flux)
@@ -911,7 +933,8 @@ static double work_on(const double* body, const double* du)
 int m3o_advance(const m3o_mesh_t* m, const m3o_solution_t* in, double dt, int safe_mode, m3o_solution_t* out)
 {
     const m3o_config_t* c = &m->config;
-    if (! c->conserve_linear_p) return 2;
+    /* conserve_linear_p = 0: advance_q (scheme.cpp:906-1020); in->U then holds conserved_q = (sigma, Sr, Lz) */
+    const int qmode = ! c->conserve_linear_p;
 
     int N = m->N, B = m->B, V = N + 1;
     size_t bs = (size_t) 3 * N * N;
@@ -938,9 +961,21 @@ int m3o_advance(const m3o_mesh_t* m, const m3o_solution_t* in, double dt, int sa
         {
             const double* U = in->U + b * bs;
             double sigma = U[k];
-            p0[b * bs + k]             = sigma;
-            p0[b * bs + N * N + k]     = U[N * N + k] / sigma;
-            p0[b * bs + 2 * N * N + k] = U[2 * N * N + k] / sigma;
+            p0[b * bs + k] = sigma;
+            if (! qmode)
+            {
+                p0[b * bs + N * N + k]     = U[N * N + k] / sigma;
+                p0[b * bs + 2 * N * N + k] = U[2 * N * N + k] / sigma;
+            }
+            else    /* recover_primitive(Q, x) (physics_iso2d.hpp:376-389) */
+            {
+                double x = m->centers[(size_t) b * 2 * N * N + k], y = m->centers[(size_t) b * 2 * N * N + N * N + k];
+                double sr = U[N * N + k] / sigma;
+                double lz = U[2 * N * N + k] / sigma;
+                double r2 = x * x + y * y;
+                p0[b * bs + N * N + k]     = (sr * x - lz * y) / r2;
+                p0[b * bs + 2 * N * N + k] = (sr * y + lz * x) / r2;
+            }
         }
 
     /* P2 + P3 guard fill of p0, PLM gradients / spacing (scheme.cpp:794-809, 148-154) */
@@ -995,6 +1030,7 @@ int m3o_advance(const m3o_mesh_t* m, const m3o_solution_t* in, double dt, int sa
                 double yf = (yv[f * V + j] + yv[f * V + j + 1]) * 0.5;
                 double dy = yv[f * V + j + 1] - yv[f * V + j];           /* difference_on_axis(1) of y */
                 intercell_flux_u(c, &tb, 0, grid_spacing, xf, yf, pl, pr, gl, gr, hl, hr, flux);
+                if (qmode) to_angmom_fluxes(0, c->domain_radius, xf, yf, flux);
                 for (int q = 0; q < 3; ++q) Fx[(size_t) q * (N + 1) * N + f * N + j] = flux[q] * dy;
             }
         for (int i = 0; i < N; ++i)         /* y faces: (N, N+1) */
@@ -1012,6 +1048,7 @@ int m3o_advance(const m3o_mesh_t* m, const m3o_solution_t* in, double dt, int sa
                 double yf = (yv[i * V + f] + yv[(i + 1) * V + f]) * 0.5;
                 double dx = xv[(i + 1) * V + f] - xv[i * V + f];           /* difference_on_axis(0) of x */
                 intercell_flux_u(c, &tb, 1, grid_spacing, xf, yf, pl, pr, gl, gr, hl, hr, flux);
+                if (qmode) to_angmom_fluxes(1, c->domain_radius, xf, yf, flux);
                 for (int q = 0; q < 3; ++q) Fy[(size_t) q * N * (N + 1) + i * (N + 1) + f] = flux[q] * dx;
             }
     }
@@ -1080,6 +1117,81 @@ int m3o_advance(const m3o_mesh_t* m, const m3o_solution_t* in, double dt, int sa
         double* T = totals + (size_t) b * T_COUNT;
         double sink_sum[2][3] = {{0}};
 
+        if (qmode)
+        {
+            /* block_update_q + source_terms_q (scheme.cpp:589-608, 417-466) */
+            double sr2 = m->gst_suppr_radius * m->gst_suppr_radius;
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j)
+                {
+                    int k = i * N + j;
+                    double x = xc[k], y = yc[k];
+                    double q0[3] = {U[k], U[N * N + k], U[2 * N * N + k]};
+                    double sigma = q0[0];
+                    double fg[2][2], s_grav[2][3], s_sink[2][3], s_buffer[3], s_geom[3], dps[2][2];
+
+                    for (int a = 0; a < 2; ++a)
+                    {
+                        double bxp = tb.b[a][1], byp = tb.b[a][2], bm = tb.b[a][0], G = 1.0;
+                        double drx = x - bxp, dry = y - byp;
+                        double dr2 = drx * drx + dry * dry;
+                        double rs2 = rs * rs;
+                        double p15 = pow(dr2 + rs2, 1.5);
+                        fg[a][0] = -drx / p15 * G * bm * sigma;
+                        fg[a][1] = -dry / p15 * G * bm * sigma;
+                        /* force_to_source_terms_q (:333-339), then * dt */
+                        s_grav[a][0] = 0.0 * dt;
+                        s_grav[a][1] = (x * fg[a][0] + y * fg[a][1]) * dt;
+                        s_grav[a][2] = (x * fg[a][1] - y * fg[a][0]) * dt;
+
+                        double s2 = c->sink_radius * c->sink_radius;
+                        double a2 = (drx * drx + dry * dry) / s2 / 2.0;
+                        double rate = c->sink_rate * exp(-a2);
+                        for (int q = 0; q < 3; ++q) s_sink[a][q] = -q0[q] * rate * dt;
+
+                        /* to_conserved_per_area(s_sink, xc) | momentum_vector (physics_iso2d.hpp:402-417) */
+                        double r2 = x * x + y * y;
+                        dps[a][0] = (s_sink[a][1] * x - s_sink[a][2] * y) / r2;
+                        dps[a][1] = (s_sink[a][1] * y + s_sink[a][2] * x) / r2;
+                    }
+                    for (int q = 0; q < 3; ++q) s_buffer[q] = (U0[(size_t) q * N * N + k] - q0[q]) * br[k] * dt;
+                    {
+                        /* source_terms_conserved_angmom (physics_iso2d.hpp:277-285) with the ramp (:439-444) */
+                        const double* pp = p0 + b * bs;
+                        double vx = pp[N * N + k], vy = pp[2 * N * N + k];
+                        double ramp = 1.0 - exp(-(x * x + y * y) / sr2);
+                        double cs2 = cs2_at(c, &tb, x, y);
+                        double Ek = 0.5 * sigma * (vx * vx + vy * vy);
+                        double pg = sigma * cs2;
+                        s_geom[0] = 0.0 * ramp * dt;
+                        s_geom[1] = (Ek + pg) * 2.0 * ramp * dt;
+                        s_geom[2] = 0.0 * ramp * dt;
+                    }
+                    for (int a = 0; a < 2; ++a)
+                    {
+                        T[T_MASS + a] = T[T_MASS + a] + s_sink[a][0] * dA[k];
+                        T[T_LACC + a] = T[T_LACC + a] + s_sink[a][2] * dA[k];
+                        T[T_TORQ + a] = T[T_TORQ + a] + s_grav[a][2] * dA[k];
+                        T[T_FX + a]   = T[T_FX + a]   + fg[a][0] * dt * dA[k];
+                        T[T_FY + a]   = T[T_FY + a]   + fg[a][1] * dt * dA[k];
+                        T[T_PXAC + a] = T[T_PXAC + a] + dps[a][0] * dA[k];
+                        T[T_PYAC + a] = T[T_PYAC + a] + dps[a][1] * dA[k];
+                    }
+                    T[T_LEJ] = T[T_LEJ] + s_buffer[2] * dA[k];
+                    T[T_MEJ] = T[T_MEJ] + s_buffer[0] * dA[k];
+
+                    for (int q = 0; q < 3; ++q)
+                    {
+                        double lx = Fx[(size_t) q * (N + 1) * N + (i + 1) * N + j] - Fx[(size_t) q * (N + 1) * N + i * N + j];
+                        double ly = Fy[(size_t) q * N * (N + 1) + i * (N + 1) + j + 1] - Fy[(size_t) q * N * (N + 1) + i * (N + 1) + j];
+                        double s = s_grav[0][q] + s_grav[1][q] + s_sink[0][q] + s_sink[1][q] + s_buffer[q] + s_geom[q];
+                        U1[(size_t) q * N * N + k] = q0[q] - (lx + ly) * dt / dA[k] + s;
+                    }
+                }
+            for (int k = 0; k < T_COUNT; ++k) T[k] = -T[k];
+            T[T_WORK] = T[T_WORK + 1] = 0.0;        /* source_terms_q does not set work_done_on */
+            continue;
+        }
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j)
             {
@@ -1241,6 +1353,12 @@ double m3o_maximum_timestep(const m3o_mesh_t* m, const m3o_solution_t* s)
         for (int k = 0; k < N * N; ++k)
         {
             double sigma = U[k], vx = U[N * N + k] / sigma, vy = U[2 * N * N + k] / sigma;
+            if (! c->conserve_linear_p)     /* (the reference itself cannot take this path: it needs fixed_dt = 1 with conserved_q) */
+            {
+                double sr = vx, lz = vy, r2 = xc[k] * xc[k] + yc[k] * yc[k];
+                vx = (sr * xc[k] - lz * yc[k]) / r2;
+                vy = (sr * yc[k] + lz * xc[k]) / r2;
+            }
             double cs = sqrt(cs2_at(c, &tb, xc[k], yc[k]));
             double ax = fmax(fabs(vx - cs), fabs(vx + cs));
             double ay = fmax(fabs(vy - cs), fabs(vy + cs));

@@ -82,19 +82,24 @@ static std::vector<double> elements_vector(const mara::full_orbital_elements_t& 
             E.elements.separation, E.elements.total_mass, E.elements.mass_ratio, E.elements.eccentricity};
 }
 
+// conserve_linear_p = 0: the active variable set is conserved_q = (sigma, Sr, Lz); it is dumped under the same
+// names ("conserved_u", "initial_conserved_u") so that every consumer of the dump format stays as it is
+static bool g_q_mode = false;
+
 static void dump_solution(dump_t& dump, const std::string& prefix, const binary::solution_t& s, std::size_t N)
 {
-    auto B = s.conserved_u.size();
+    auto B = g_q_mode ? s.conserved_q.size() : s.conserved_u.size();
     auto U = std::vector<double>();
     U.reserve(B * 3 * N * N);
 
     // layout: [block][field][i][j], blocks in the reference's traversal order
-    s.conserved_u.sink([&] (auto block)
+    auto flatten = [&] (auto block)
     {
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U.push_back(mara::get<0>(block(i, j)).value);
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U.push_back(mara::get<1>(block(i, j)).value);
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U.push_back(mara::get<2>(block(i, j)).value);
-    });
+    };
+    if (g_q_mode) s.conserved_q.sink(flatten); else s.conserved_u.sink(flatten);
     dump.f64(prefix + "conserved_u", {B, 3, N, N}, U);
     dump.scalar(prefix + "time", s.time.value);
     dump.i64(prefix + "iteration", {2}, {s.iteration.get_numerator(), s.iteration.get_denominator()});
@@ -144,12 +149,13 @@ static void dump_solver_data(dump_t& dump, const binary::solver_data_t& d)
     {
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) br.push_back(block(i, j).value);
     });
-    d.initial_conserved_u.sink([&] (auto block)
+    auto flatten0 = [&] (auto block)
     {
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U0.push_back(mara::get<0>(block(i, j)).value);
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U0.push_back(mara::get<1>(block(i, j)).value);
         for (std::size_t i = 0; i < N; ++i) for (std::size_t j = 0; j < N; ++j) U0.push_back(mara::get<2>(block(i, j)).value);
-    });
+    };
+    if (g_q_mode) d.initial_conserved_q.sink(flatten0); else d.initial_conserved_u.sink(flatten0);
     dump.i64("tree_index", {B, 3}, index);
     dump.f64("vertices", {B, 2, N + 1, N + 1}, verts);
     dump.f64("cell_centers", {B, 2, N, N}, xc);
@@ -242,6 +248,7 @@ int main(int argc, const char* argv[])
 
     auto run_config  = binary::create_run_config(argc - 1, argv + 1);
     auto solver_data = binary::create_solver_data(run_config);
+    g_q_mode         = ! solver_data.conserve_linear_p;
     auto dump        = dump_t(dump_name);
     auto N           = solver_data.block_size;
     auto B           = solver_data.vertices.size();
@@ -284,7 +291,8 @@ int main(int argc, const char* argv[])
 
     // Known-answer line: plain sum of sigma over all cells in traversal order.
     auto sum_sigma = 0.0;
-    solution.conserved_u.sink([&] (auto block) { for (auto u : block) sum_sigma += mara::get<0>(u).value; });
+    if (g_q_mode) solution.conserved_q.sink([&] (auto block) { for (auto u : block) sum_sigma += mara::get<0>(u).value; });
+    else solution.conserved_u.sink([&] (auto block) { for (auto u : block) sum_sigma += mara::get<0>(u).value; });
 
     std::printf("blocks=%lu cells=%lu steps=%d fallbacks=%d t=%.17g sum_sigma=%.17g\n",
         (unsigned long)B, (unsigned long)(B * N * N), steps, num_fallbacks, solution.time.value, sum_sigma);

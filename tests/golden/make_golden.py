@@ -27,6 +27,11 @@ CASES = {
     # RK1, fixed dt, axisymmetric sound speed, retrograde disk
     "rk1_axisym_d3_n8": dict(config=dict(depth=3, block_size=8, axisymmetric_cs2=1, counter_rotate=1, rk_order=1, fixed_dt=1,
                                          no_accretion_force=1), steps=[1, 5], stages=False),
+    # angular-momentum-conserving variables (advance_q): conserve_linear_p=0 needs fixed_dt=1 in the reference;
+    # "conserved_u" then holds conserved_q = (sigma, Sr, Lz)
+    "angmom_nested_d3_n8": dict(config=dict(depth=3, block_size=8, conserve_linear_p=0, fixed_dt=1), steps=[1, 4], stages=True),
+    "angmom_live_rk1_d2_n16": dict(config=dict(depth=2, block_size=16, domain_radius=6.0, conserve_linear_p=0, fixed_dt=1, rk_order=1,
+                                               eccentricity=0.2, mass_ratio=0.5, begin_live_binary=0.0, nu=0.01), steps=[1, 5], stages=False),
     # deeper nested tree with a non power-of-two block size: topology + geometry only
     "mesh_d5_n12": dict(config=dict(depth=5, block_size=12), steps=[], stages=False),
     # default run config: depth=4 block_size=24 (64 leaves): topology + geometry only
