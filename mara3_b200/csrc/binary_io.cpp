@@ -147,11 +147,14 @@ void m3b::write_checkpoint(const std::string& filename, binary_solver_t& solver,
         for (std::size_t c = 0; c < NN; ++c)
             for (int q = 0; q < 3; ++q)
                 cells[(std::size_t(b) * NN + c) * 3 + (2 - q)] = planes[(std::size_t(b) * 3 + q) * NN + c];
-    w.require_group("/solution/conserved_u");
+    // conserve_linear_p = 0: the state is conserved_q = (sigma, Sr, Lz) -- its tuple image is (Lz, Sr, sigma) all the same
+    const std::string used = data.conserve_linear_p ? "/solution/conserved_u" : "/solution/conserved_q";
+    const std::string unused = data.conserve_linear_p ? "/solution/conserved_q" : "/solution/conserved_u";
+    w.require_group(used);
     for (int b = 0; b < B; ++b)
-        w.write("/solution/conserved_u/" + leaf_name(data, b), v3, {std::uint64_t(N), std::uint64_t(N)}, cells.data() + std::size_t(b) * NN * 3);
+        w.write(used + "/" + leaf_name(data, b), v3, {std::uint64_t(N), std::uint64_t(N)}, cells.data() + std::size_t(b) * NN * 3);
     // the unused variable set is a default tree: one leaf "0:0-0" holding an empty array
-    w.write("/solution/conserved_q/0:0-0", v3, {0, 0}, cells.data());
+    w.write(unused + "/0:0-0", v3, {0, 0}, cells.data());
 
     w.write("/solution/mass_accreted_on", v2, {}, u.mass_accreted_on, true);
     w.write("/solution/angular_momentum_accreted_on", v2, {}, u.angular_momentum_accreted_on, true);
@@ -254,12 +257,13 @@ state_t m3b::read_checkpoint(const std::string& filename, binary_solver_t& solve
     get("/solution/iteration", type_t::array(type_t::i32(), 2), iteration);
     u.iteration_num = iteration[0]; u.iteration_den = iteration[1];
 
-    auto names = r.keys("/solution/conserved_u");
+    const std::string used = data.conserve_linear_p ? "/solution/conserved_u" : "/solution/conserved_q";
+    auto names = r.keys(used);
     if (int(names.size()) != data.num_blocks) throw std::runtime_error("restart file has " + std::to_string(names.size()) + " blocks, the run configuration makes " + std::to_string(data.num_blocks));
     auto planes = std::vector<double>(std::size_t(B) * 3 * NN);
     for (int b = 0; b < B; ++b)
     {
-        const auto path = "/solution/conserved_u/" + leaf_name(data, data.global_block(b));     // every rank reads its own blocks
+        const auto path = used + "/" + leaf_name(data, data.global_block(b));     // every rank reads its own blocks
         if (! r.exists(path)) throw std::runtime_error("restart file has no block " + path + " (different mesh?)");
         auto shape = r.shape(path);
         if (shape.size() != 2 || int(shape[0]) != N || int(shape[1]) != N) throw std::runtime_error("restart block " + path + " has the wrong shape");

@@ -28,6 +28,10 @@ struct model_t
     double alpha, nu, alpha_cutoff_radius;
     double density_floor;
     int axisymmetric_cs2;
+    // conserve_linear_p = 0: the state is conserved_q = (sigma, Sr, Lz) (advance_q, scheme.cpp:906-1020)
+    int qmode;
+    double domain_radius;       // no Lz flux through faces at x, y = +- domain_radius (scheme.cpp:209-210)
+    double gst_suppr_radius2;   // ramp of the geometric source term (scheme.cpp:424, 439-444)
 };
 
 /** Per-stage inputs (body positions at the stage time; scheme.cpp:814). */
@@ -324,6 +328,85 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
     if (! FAST && s < M.density_floor)      // FAST: the caller has checked density_floor == 0
     {
         a0 = fma(s, 1e-2, a0);  a1 = fma(px, 1e-2, a1);  a2 = fma(py, 1e-2, a2);
+    }
+    src[0] = a0; src[1] = a1; src[2] = a2;
+}
+
+/** to_angmom_fluxes (scheme.cpp:199-214): F(Sr) = x F(px) + y F(py), F(Lz) = x F(py) - y F(px); none through the domain edge. */
+template<int AXIS>
+__device__ __forceinline__ void to_angmom_fluxes(const model_t& M, double x, double y, double F[3])
+{
+    const double fpx = F[1], fpy = F[2];
+    double flz = x * fpy - y * fpx;
+    if (AXIS == 0 && (x == -M.domain_radius || x == M.domain_radius)) flz = 0.0;
+    if (AXIS == 1 && (y == -M.domain_radius || y == M.domain_radius)) flz = 0.0;
+    F[1] = x * fpx + y * fpy;
+    F[2] = flz;
+}
+
+/** recover_primitive(Q, x) / to_conserved_per_area(Q, x) (physics_iso2d.hpp:376-417): linear momentum from (Sr, Lz). */
+__device__ __forceinline__ void angmom_to_linear(double x, double y, double sr, double lz, double& px, double& py)
+{
+    const double r2 = x * x + y * y;
+    const double a = (sr * x - lz * y) / r2, b = (sr * y + lz * x) / r2;      // (px, py may alias sr, lz)
+    px = a;
+    py = b;
+}
+
+/**
+ * source_terms_q (scheme.cpp:417-466) for one cell of the angular-momentum-conserving variable set: gravity and sinks
+ * in (Sr, Lz) form, buffer towards the initial conserved_q, and the geometric term 2 (E_kin + p) of the radial
+ * momentum with its ramp.  The running sums keep the meaning they have for source_terms_u (momentum accreted is the
+ * sink term converted back to linear momentum, :446-447), so the host bookkeeping is shared; no work integral.
+ */
+__device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& S, double x, double y,
+    double s, double sr, double lz, double vx, double vy, double q0s, double q0r, double q0l, double br,
+    double src[3], double sums[NUM_SUMS], double& y1, double& y2)
+{
+    double dx1 = x - S.x1, dy1 = y - S.y1, dx2 = x - S.x2, dy2 = y - S.y2;
+    double r1 = fma(dx1, dx1, dy1 * dy1);
+    double r2 = fma(dx2, dx2, dy2 * dy2);
+    y1 = fast_rsqrt(r1 + M.softening_radius2);
+    y2 = fast_rsqrt(r2 + M.softening_radius2);
+    double k1 = -(y1 * y1) * y1 * S.m1 * s;
+    double k2 = -(y2 * y2) * y2 * S.m2 * s;
+    double fx1 = dx1 * k1, fy1 = dy1 * k1, fx2 = dx2 * k2, fy2 = dy2 * k2;
+    double tq1 = x * fy1 - y * fx1, tq2 = x * fy2 - y * fx2;
+
+    sums[GRV_FX + 0] += fx1;  sums[GRV_FY + 0] += fy1;  sums[GRV_TQ + 0] += tq1;
+    sums[GRV_FX + 1] += fx2;  sums[GRV_FY + 1] += fy2;  sums[GRV_TQ + 1] += tq2;
+
+    double a0 = 0.0;
+    double a1 = (x * fx1 + y * fy1) * S.dt + (x * fx2 + y * fy2) * S.dt;
+    double a2 = tq1 * S.dt + tq2 * S.dt;
+
+    double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
+    if (e1 < 100.0 || e2 < 100.0)
+    {
+        double w1 = sink_weight(M.sink_rate, e1);
+        double w2 = sink_weight(M.sink_rate, e2);
+        double px, py;
+        angmom_to_linear(x, y, sr, lz, px, py);
+        sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
+        sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
+        sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
+        sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        double w = -(w1 + w2) * S.dt;
+        a0 = fma(s, w, a0);  a1 = fma(sr, w, a1);  a2 = fma(lz, w, a2);
+    }
+    if (br != 0.0)
+    {
+        double b0 = (q0s - s) * br, b1 = (q0r - sr) * br, b2 = (q0l - lz) * br;
+        sums[BUF_M] += b0;
+        sums[BUF_L] += b2;
+        a0 = fma(b0, S.dt, a0);  a1 = fma(b1, S.dt, a1);  a2 = fma(b2, S.dt, a2);
+    }
+    // source_terms_conserved_angmom (physics_iso2d.hpp:277-285): (0, 2 (E_kin + p), 0), ramped up away from the origin
+    {
+        double cs2 = M.axisymmetric_cs2 ? fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2 : fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;
+        double ramp = 1.0 - exp(-(x * x + y * y) / M.gst_suppr_radius2);
+        double ek = 0.5 * s * (vx * vx + vy * vy);
+        a1 += (ek + s * cs2) * 2.0 * ramp * S.dt;
     }
     src[0] = a0; src[1] = a1; src[2] = a2;
 }

@@ -67,6 +67,7 @@ namespace
         const double* U0;               // [3][FS]
         const double* br;               // [FS]
         size_t GS;                      // gradient scratch stride
+        int qmode;                      // the state is conserved_q = (sigma, Sr, Lz): primitives need the cell position
         int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
         // multi-GPU: CTAs from first_wait_cta on update blocks with ghost neighbours and wait until the guard-zone
         // unpack (running beside this kernel on the exchange stream) has published ready_value
@@ -285,7 +286,12 @@ namespace
             }
             Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
 
-            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
+            if (S.compute_dt)
+            {
+                double mx = n1, my = n2;
+                if (mesh.qmode) angmom_to_linear(x, y, n1, n2, mx, my);
+                dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, mx, my));
+            }
         }
         reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
     }
@@ -349,6 +355,17 @@ namespace
     __device__ __forceinline__ prim_t load_prim(const mesh_dev_t& m, const double* U, int leaf, int i, int j)
     {
         size_t c = (size_t(leaf) * m.N + i) * m.N + j;
+        if (m.qmode)
+        {
+            // recover_primitive(Q, x) (physics_iso2d.hpp:376-389) at the centre of the cell in ITS block
+            const double* xv = m.xv + size_t(leaf) * (m.N + 1);
+            const double* yv = m.yv + size_t(leaf) * (m.N + 1);
+            const double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
+            const double s = U[c], sr = U[m.FS + c] / s, lz = U[2 * m.FS + c] / s;
+            double vx, vy;
+            angmom_to_linear(x, y, sr, lz, vx, vy);
+            return {s, vx, vy};
+        }
         return cons_to_prim(U[c], U[m.FS + c], U[2 * m.FS + c]);
     }
 
@@ -471,6 +488,7 @@ namespace
         prim_t hl = grad_at(m, G, 1 - AXIS, b, li, lj), hr = grad_at(m, G, 1 - AXIS, b, ri, rj);
         eos_t e = eos_at_face(model, S, x, y);
         face_flux<AXIS>(e, pl, pr, gl, gr, hl.vx, hl.vy, hr.vx, hr.vy, 0.5 * m.spacing[b], 1.0, F);
+        if (m.qmode) to_angmom_fluxes<AXIS>(model, x, y, F);
         F[0] *= len; F[1] *= len; F[2] *= len;
     }
 
@@ -535,7 +553,12 @@ namespace
             double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
             double dt_over_dA = S.dt / ((xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]));
             double src[3], y1, y2;
-            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
+            if (mesh.qmode)
+            {
+                const prim_t p = load_prim(mesh, Uin, b, i, j);
+                source_terms_q(model, S, x, y, s, px, py, p.vx, p.vy, u0s, u0x, u0y, br, src, sums, y1, y2);
+            }
+            else source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
 
             double n0 = s  - ((Fr[0] - Fl[0]) + (Ft[0] - Fb[0])) * dt_over_dA + src[0];
             double n1 = px - ((Fr[1] - Fl[1]) + (Ft[1] - Fb[1])) * dt_over_dA + src[1];
@@ -552,7 +575,12 @@ namespace
             }
             Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
 
-            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
+            if (S.compute_dt)
+            {
+                double mx = n1, my = n2;
+                if (mesh.qmode) angmom_to_linear(x, y, n1, n2, mx, my);
+                dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, mx, my));
+            }
         }
         reduce_and_store(red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
     }
@@ -615,6 +643,7 @@ namespace
                 const prim_t pl = {T.P[0][li][lj + 1], T.P[1][li][lj + 1], T.P[2][li][lj + 1]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
                 const prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]}, gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
                 face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5 * h, 1.0, F);
+                if (mesh.qmode) to_angmom_fluxes<0>(model, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]), F);
                 const double len = T.yv[lj + 1] - T.yv[lj];
                 F[0] *= len; F[1] *= len; F[2] *= len;
             }
@@ -630,6 +659,7 @@ namespace
                 const prim_t pl = {T.P[0][li + 1][lj], T.P[1][li + 1][lj], T.P[2][li + 1][lj]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
                 const prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]}, gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
                 face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5 * h, 1.0, F);
+                if (mesh.qmode) to_angmom_fluxes<1>(model, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj], F);
                 const double len = T.xv[li + 1] - T.xv[li];
                 F[0] *= len; F[1] *= len; F[2] *= len;
             }
@@ -662,7 +692,8 @@ namespace
             const double x = 0.5 * (T.xv[li] + T.xv[li + 1]), y = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
             const double dt_over_dA = S.dt / ((T.xv[li + 1] - T.xv[li]) * (T.yv[lj + 1] - T.yv[lj]));
             double src[3], y1, y2;
-            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
+            if (mesh.qmode) source_terms_q(model, S, x, y, s, px, py, T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1], u0s, u0x, u0y, br, src, sums, y1, y2);
+            else source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
 
             double n0 = s  - ((T.Fx[0][li + 1][lj] - T.Fx[0][li][lj]) + (T.Fy[0][li][lj + 1] - T.Fy[0][li][lj])) * dt_over_dA + src[0];
             double n1 = px - ((T.Fx[1][li + 1][lj] - T.Fx[1][li][lj]) + (T.Fy[1][li][lj + 1] - T.Fy[1][li][lj])) * dt_over_dA + src[1];
@@ -708,7 +739,9 @@ namespace
             double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
             double y1, y2;
             sound_speed_squared(model, S, x, y, y1, y2);
-            dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, U[c], U[mesh.FS + c], U[2 * mesh.FS + c]));
+            double mx = U[mesh.FS + c], my = U[2 * mesh.FS + c];
+            if (mesh.qmode) angmom_to_linear(x, y, mx, my, mx, my);      // (the reference itself needs fixed_dt = 1 with conserved_q)
+            dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, U[c], mx, my));
         }
         dtmin = warp_min(dtmin);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dtmin;
@@ -1154,7 +1187,7 @@ namespace
             double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
             double dA = (xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]);
             m += U[c] * dA;
-            l += (x * U[2 * mesh.FS + c] - y * U[mesh.FS + c]) * dA;
+            l += (mesh.qmode ? U[2 * mesh.FS + c] : x * U[2 * mesh.FS + c] - y * U[mesh.FS + c]) * dA;     // Lz is the third component of conserved_q
         }
         m = warp_sum(m); l = warp_sum(l);
         if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m; red[1][threadIdx.x >> 5] = l; }
@@ -1183,7 +1216,9 @@ namespace
             const double* yv = mesh.yv + b * (N + 1);
             const double xc = (xv[i] + xv[i + 1]) * 0.5, yc = (yv[j] + yv[j + 1]) * 0.5;
             const double rc = sqrt(xc * xc + yc * yc);
-            const double sigma = U[k], vx = U[mesh.FS + k] / sigma, vy = U[2 * mesh.FS + k] / sigma;
+            const double sigma = U[k];
+            double vx = U[mesh.FS + k] / sigma, vy = U[2 * mesh.FS + k] / sigma;
+            if (mesh.qmode) angmom_to_linear(xc, yc, vx, vy, vx, vy);
             out[(b * 3 + 0) * NN + cell] = sigma;
             out[(b * 3 + 1) * NN + cell] = vx * (xc / rc) + vy * (yc / rc);
             out[(b * 3 + 2) * NN + cell] = vx * (-yc / rc) + vy * (xc / rc);
@@ -1499,6 +1534,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->model.alpha_cutoff_radius = sd.alpha_cutoff_radius;
     impl->model.density_floor       = sd.density_floor;
     impl->model.axisymmetric_cs2    = sd.axisymmetric_cs2;
+    impl->model.qmode               = ! sd.conserve_linear_p;
+    impl->model.domain_radius       = sd.domain_radius;
+    impl->model.gst_suppr_radius2   = sd.gst_suppr_radius * sd.gst_suppr_radius;
+    impl->mesh.qmode                = ! sd.conserve_linear_p;
 
     // ---- scratch
     size_t max_rows = size_t(BO) * std::max(1, (N / std::max(1, impl->tile_x)) * (N / std::max(1, impl->tile_y))) + B;

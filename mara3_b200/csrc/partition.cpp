@@ -26,7 +26,7 @@ namespace
      * neighbours are computed on this rank too, from THEIR face neighbours -- so the rank stores whole
      * copies of the face neighbours (layer 1) and of the face neighbours of those (layer 2).
      */
-    std::vector<std::tuple<int, int, int, int>> remote_needs(const quadtree_t& tree, const std::vector<int>& owner, int first, int count, int r)
+    std::vector<std::tuple<int, int, int, int>> remote_needs(const quadtree_t& tree, const std::vector<int>& owner, int first, int count, int r, bool all_general)
     {
         auto needs = std::set<std::tuple<int, int, int, int>>();
         auto whole = std::set<int>();
@@ -34,7 +34,7 @@ namespace
 
         for (int b = first; b < first + count; ++b)
         {
-            bool regular = true;
+            bool regular = ! all_general;
             for (int di = -1; di <= 1; ++di)
                 for (int dj = -1; dj <= 1; ++dj)
                     if ((di || dj) && tree.same_level_neighbor(b, di, dj) < 0) regular = false;
@@ -72,7 +72,7 @@ namespace
     }
 }
 
-partition_t m3b::make_partition(const quadtree_t& tree, int rank, int nranks)
+partition_t m3b::make_partition(const quadtree_t& tree, int rank, int nranks, bool all_general)
 {
     if (nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("make_partition: bad rank / nranks");
 
@@ -98,7 +98,7 @@ partition_t m3b::make_partition(const quadtree_t& tree, int rank, int nranks)
     if (p.num_owned == 0) throw std::invalid_argument("make_partition: more ranks than leaf blocks");
 
     // what this rank receives: ghosts are numbered after the owned blocks in ascending global id
-    auto mine = remote_needs(tree, p.owner, p.first_owned, p.num_owned, rank);
+    auto mine = remote_needs(tree, p.owner, p.first_owned, p.num_owned, rank, all_general);
     auto ghosts = std::set<int>();
     for (auto& [o, n, di, dj] : mine) ghosts.insert(n);
     for (int g : ghosts)
@@ -112,7 +112,7 @@ partition_t m3b::make_partition(const quadtree_t& tree, int rank, int nranks)
     for (int peer = 0; peer < nranks; ++peer)
     {
         if (peer == rank) continue;
-        for (auto& [o, n, di, dj] : remote_needs(tree, p.owner, offsets[peer], offsets[peer + 1] - offsets[peer], peer))
+        for (auto& [o, n, di, dj] : remote_needs(tree, p.owner, offsets[peer], offsets[peer + 1] - offsets[peer], peer, all_general))
             if (o == rank) p.send[peer].push_back({p.global_to_local[n], di, dj});
     }
     return p;

@@ -49,5 +49,6 @@ namespace m3b
     std::vector<int> partition_offsets(int num_leaves, int nranks);
 
     /** Build the partition and exchange plan seen by `rank` (any 2:1 balanced tree). */
-    partition_t make_partition(const quadtree_t& tree, int rank, int nranks);
+    /** all_general: every block is updated by the any-tree kernels (conserve_linear_p = 0): whole-block ghosts everywhere. */
+    partition_t make_partition(const quadtree_t& tree, int rank, int nranks, bool all_general = false);
 }

@@ -64,7 +64,8 @@ binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool ge
         throw std::invalid_argument("binary::next_solution");
     if (device >= 0)
     {
-        gpu = std::make_unique<device_solver_t>(data, device, general_only, tiled_kernel);
+        // conserve_linear_p = 0 (advance_q, scheme.cpp:906-1020): the state is conserved_q and every block takes the any-tree kernels
+        gpu = std::make_unique<device_solver_t>(data, device, general_only || ! data.conserve_linear_p, tiled_kernel);
         if (nranks > 1)
         {
             if (! nccl_unique_id) throw std::invalid_argument("a multi-rank solver needs the NCCL unique id of the job");
@@ -162,7 +163,8 @@ status_t binary_solver_t::bookkeeping(const solution_t& in, const stage_result_t
         fy[k]       = -r.sums[GRV_FY + k] * dt;
         torque[k]   = -r.sums[GRV_TQ + k] * dt;
 
-        work[k]     = r.work[k];        // evaluated per block on the device, then summed (scheme.cpp:407-408)
+        // evaluated per block on the device, then summed (scheme.cpp:407-408); source_terms_q does not set it (:446-463)
+        work[k]     = data.conserve_linear_p ? r.work[k] : 0.0;
     }
     double mass_ejected = -r.sums[BUF_M] * dt;
     double lz_ejected   = -r.sums[BUF_L] * dt;
@@ -236,11 +238,6 @@ void binary_solver_t::record_offenders(int slot)
 
 status_t binary_solver_t::advance(const solution_t& in, double dt, bool safe_mode, solution_t& out)
 {
-    if (! data.conserve_linear_p)
-    {
-        error = "conserve_linear_p=0 (advance_q) is not implemented by the B200 path";
-        return status_unsupported;
-    }
     if (! out.conserved_u || out.conserved_u == in.conserved_u) out.conserved_u = new_field();
 
     auto inputs = stage_inputs(in, dt, safe_mode);
@@ -442,11 +439,6 @@ status_t binary_solver_t::finish_pipelined(solution_t& s, const speculation_t& s
 
 status_t binary_solver_t::next_solution(solution_t& s, double* dt_used, bool* fell_back, bool speculate)
 {
-    if (! data.conserve_linear_p)
-    {
-        error = "conserve_linear_p=0 (advance_q) is not implemented by the B200 path";
-        return status_unsupported;
-    }
     if (fell_back) *fell_back = false;
 
     // ---- a step queued earlier for exactly this state?

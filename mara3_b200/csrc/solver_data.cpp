@@ -84,7 +84,7 @@ solver_data_t m3b::create_solver_data(const config_t& cfg, int rank, int nranks)
     d.initial_elements.eccentricity = cfg.get_double("eccentricity");
 
     d.tree = std::make_shared<quadtree_t>(d.block_size, cfg.get_int("depth"), cfg.get_double("focus_factor"), cfg.get_double("focus_index"));
-    d.partition = make_partition(*d.tree, rank, nranks);
+    d.partition = make_partition(*d.tree, rank, nranks, /*all_general*/ ! d.conserve_linear_p);
     d.num_blocks = d.tree->num_leaves();
     d.num_owned = d.partition.num_owned;
     d.num_local = d.partition.num_local();
@@ -131,8 +131,16 @@ solver_data_t m3b::create_solver_data(const config_t& cfg, int rank, int nranks)
                 std::size_t k = (std::size_t(b) * N + i) * N + j;
 
                 d.initial_conserved_u[0 * d.num_local_cells() + k] = prim[0];
-                d.initial_conserved_u[1 * d.num_local_cells() + k] = prim[0] * prim[1];
-                d.initial_conserved_u[2 * d.num_local_cells() + k] = prim[0] * prim[2];
+                if (d.conserve_linear_p)
+                {
+                    d.initial_conserved_u[1 * d.num_local_cells() + k] = prim[0] * prim[1];
+                    d.initial_conserved_u[2 * d.num_local_cells() + k] = prim[0] * prim[2];
+                }
+                else    // conserved_q = (sigma, Sr, Lz): to_conserved_angmom_per_area (physics_iso2d.hpp:263-272), held in the same array
+                {
+                    d.initial_conserved_u[1 * d.num_local_cells() + k] = prim[0] * (x * prim[1] + y * prim[2]);
+                    d.initial_conserved_u[2 * d.num_local_cells() + k] = prim[0] * (x * prim[2] - y * prim[1]);
+                }
                 if (b < d.num_owned) max_v = std::max(max_v, std::sqrt(prim[1] * prim[1] + prim[2] * prim[2]));
 
                 // buffer zone: rate * (1 + tanh(3 (r - domain_radius))) (solver_data.cpp:64-78)

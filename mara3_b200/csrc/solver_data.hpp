@@ -39,7 +39,7 @@ namespace m3b
         std::vector<double> xv;                  // [L][N+1] block vertex x coordinates (already * domain_radius)
         std::vector<double> yv;                  // [L][N+1]
         std::vector<double> buffer_rate_field;   // [L][N][N]
-        std::vector<double> initial_conserved_u; // [3][L][N][N]   (sigma, px, py)
+        std::vector<double> initial_conserved_u; // [3][L][N][N]   (sigma, px, py); conserve_linear_p = 0: conserved_q = (sigma, Sr, Lz)
         double min_spacing = 0.0;                // over the whole tree
         double max_velocity_local = 0.0;         // over this rank's owned cells (reduce over ranks for recommended_time_step)
 

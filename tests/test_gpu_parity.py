@@ -63,6 +63,12 @@ STAGE_CASES = [
     (dict(depth=3, block_size=16, axisymmetric_cs2=1, counter_rotate=1, focus_factor=1e3), False),
     (dict(depth=3, block_size=16, alpha=0.0, sink_rate=5.0, sink_radius=0.1, softening_radius=0.1,
           buffer_damping_rate=0.0, mach_number=5.0, plm_theta=1.0, focus_factor=1e3), False),
+    # angular-momentum-conserving variables (advance_q, conserve_linear_p=0): state = conserved_q, any-tree kernels
+    (dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1), False),                     # nested, 16x16 tiles
+    (dict(depth=3, block_size=8, conserve_linear_p=0, fixed_dt=1), False),                      # nested, one CTA per block
+    (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), False),
+    (dict(depth=2, block_size=16, domain_radius=6.0, conserve_linear_p=0, fixed_dt=1, rk_order=1, eccentricity=0.2,
+          mass_ratio=0.5, begin_live_binary=0.0, nu=0.01), False),
 ]
 
 
@@ -109,7 +115,8 @@ def test_advance_on_rough_seeded_states(cfg, seed):
     assert block_rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
 
 
-@pytest.mark.parametrize("name", ["nested_d3_n8", "uniform_d2_n16", "live_ecc_d3_n8", "rk1_axisym_d3_n8"])
+@pytest.mark.parametrize("name", ["nested_d3_n8", "uniform_d2_n16", "live_ecc_d3_n8", "rk1_axisym_d3_n8",
+                                  "angmom_nested_d3_n8", "angmom_live_rk1_d2_n16"])
 def test_steps_match_reference_golden_vectors(name):
     """tests/golden/*.npz were produced by the reference's own compiled code."""
     g = load_golden(name)
