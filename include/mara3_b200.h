@@ -22,6 +22,9 @@
  *                                    cm_velocity_y, separation, total_mass, mass_ratio, eccentricity
  *                                    (subprog_binary.hpp:108-126, model_two_body.hpp:40-62)
  *
+ * With conserve_linear_p=0 the conserved state is conserved_q = (sigma, S_r, L_z) (advance_q, scheme.cpp:906-1020)
+ * in the same [block][3][N][N] layout; everything else is unchanged.
+ *
  * Status codes: 0 ok; 1 negative density in the updated state (the reference throws
  * std::runtime_error, scheme.cpp:747-750); 2 unbound orbit (model_two_body.hpp:385-386);
  * 3 unsupported option; -1 other error (see m3b_last_error).  There is no CPU fallback:

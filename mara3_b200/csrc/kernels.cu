@@ -1463,7 +1463,12 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         mark(b);
         for (int side = 0; side < 4; ++side) for (int q = 0; q < 4; ++q) mark(nbr[size_t(b) * 4 + side].leaf[q]);
     }
-    if (force_general) for (int b = 0; b < BO; ++b) mark(b);
+    if (force_general)
+        for (int b = 0; b < BO; ++b)        // every owned block takes the any-tree kernels: its face neighbours' gradients too (ghosts included)
+        {
+            mark(b);
+            for (int side = 0; side < 4; ++side) for (int q = 0; q < 4; ++q) mark(nbr[size_t(b) * 4 + side].leaf[q]);
+        }
     for (int b = 0; b < B; ++b) if (in_gradient_set[b]) { gslot[b] = int(impl->gradient_blocks.size()); impl->gradient_blocks.push_back(b); }
 
     impl->mesh.B = B;

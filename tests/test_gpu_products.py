@@ -138,3 +138,24 @@ def test_subprogram_run_loop_products_and_restart(tmp_path):
 
     bad = subprocess.run([exe, "binary", "no_such_key=1"], capture_output=True, text=True, timeout=120)
     assert bad.returncode == 1 and "config has no option no_such_key" in bad.stdout
+
+
+def test_checkpoint_of_angular_momentum_variables(tmp_path):
+    """conserve_linear_p=0: the state is written under /solution/conserved_q, conserved_u is the empty default tree."""
+    s = m3.Solver(dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1))
+    u = s.create_solution()
+    s.next_solution(u)
+    path = str(tmp_path / "chkpt.q.h5")
+    s.write_checkpoint(u, path)
+    f = H5File(path)
+    assert f.keys("/solution/conserved_u") == ["0:0-0"] and f.shape("/solution/conserved_u/0:0-0") == (0, 0)
+    names = leaf_names(s)
+    assert sorted(names) == f.keys("/solution/conserved_q")
+    Q = u.conserved_u                      # the API's state array holds conserved_q = (sigma, Sr, Lz) in this mode
+    block = f.read("/solution/conserved_q/" + names[5])
+    assert np.array_equal(block[..., 2], Q[5, 0]) and np.array_equal(block[..., 1], Q[5, 1]) and np.array_equal(block[..., 0], Q[5, 2])
+    v = s.create_solution()
+    s.read_checkpoint(v, path)
+    assert np.array_equal(v.conserved_u, Q) and np.array_equal(v.scalars, u.scalars)
+    sample = s.time_series_sample(u)
+    assert abs(sample[2] - float((Q[:, 2] * s.cell_areas).sum())) <= 1e-12 * abs(sample[2])        # disk Lz = sum of the third component

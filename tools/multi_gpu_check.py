@@ -37,7 +37,8 @@ def main():
              (dict(depth=2, block_size=64), 34, True),             # runs into the safe-mode retries (steps 23-33)
              (dict(depth=4, block_size=64, focus_factor=1e3), 5, False),
              (dict(depth=4, block_size=32), 6, True),              # nested tree: refinement jumps across the rank boundary
-             (dict(depth=6, block_size=64), 4, False)]             # config-4-like nesting (136 leaves, levels 2-6)
+             (dict(depth=6, block_size=64), 4, False),             # config-4-like nesting (136 leaves, levels 2-6)
+             (dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1), 4, True)]   # advance_q: whole-block ghosts everywhere
     if os.environ.get("MGC_QUICK"):
         cases = [(dict(depth=3, block_size=32, focus_factor=1e3, domain_radius=6.0), 6, False), (dict(depth=6, block_size=64), 3, False)]
     for cfg, steps, with_oracle in cases:
