@@ -244,7 +244,7 @@ namespace
             #pragma unroll
             for (int q = 0; q < 3; ++q) { pc[q] = T.P[q][g0 + 1][lane + 1]; dl[q] = pc[q] - T.P[q][g0][lane + 1]; }
 
-            #pragma unroll 1
+            #pragma unroll 2
             for (int g = g0; g < g1; ++g)
             {
                 // all nine loads first: behind a store to T.G the compiler will not hoist a load from T.P
@@ -362,7 +362,7 @@ namespace
 
         // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
         // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
-        #pragma unroll 1
+        #pragma unroll
         for (int r = 1; r < STRIP; ++r)
         {
             double FxNew[3], FyNew[3];
