@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include "comm.hpp"
 #include "device_solver.hpp"
 #include "iso2d_device.cuh"
@@ -1045,6 +1046,137 @@ namespace
     }
 
     /**
+     * finish_stage for up to FINISH_CLUSTER_MAX_ROWS blocks as ONE CLUSTER of eight CTAs (thread-block cluster, distributed
+     * shared memory): every CTA folds its share of the blocks -- tile rows -> block row (tile order), block-wise work integral,
+     * column sums by 32 interleaved groups -- then a hardware cluster barrier replaces the __threadfence + ticket of the
+     * multi-CTA version, and CTA 0 folds the eight partial rows through DSMEM in rank order, publishes the result and writes
+     * the next step's time and dt.  This kernel sits on the critical path of every step (stage b -> finish -> next stage a);
+     * eight SMs give it the memory-level parallelism one CTA lacks (the tile rows come from L2, ~2000 cycles away).
+     */
+    constexpr int FINISH_CLUSTER = 8, FINISH_CLUSTER_THREADS = 1024, FINISH_CLUSTER_ROWS = 128;
+    constexpr int FINISH_CLUSTER_MAX_ROWS = FINISH_CLUSTER * FINISH_CLUSTER_ROWS;
+
+    __global__ void __cluster_dims__(FINISH_CLUSTER, 1, 1) __launch_bounds__(FINISH_CLUSTER_THREADS) finish_stage_cluster(
+        const double* tile_rows, int num_fused, int tpb, const double* general_rows, int gtpb, int num_rows,
+        const stage_t* __restrict__ stage_ptr, fail_dev_t* fail, stage_result_t* result, prepare_args_t prep)
+    {
+        namespace cg = cooperative_groups;
+        __shared__ double srows[FINISH_CLUSTER_ROWS][ROW];
+        __shared__ double part[32][ROW];
+        __shared__ double mine[ROW];
+        __shared__ double dt_min_all;
+        auto cluster = cg::this_cluster();
+        const int tid = threadIdx.x, rank = int(cluster.block_rank());
+        const int per = (num_rows + FINISH_CLUSTER - 1) / FINISH_CLUSTER;
+        const int r0 = min(num_rows, rank * per), n = min(num_rows, r0 + per) - r0;
+
+        // (A) one row per block, tiles in tile order, eight loads in flight at a time
+        for (int idx = tid; idx < n * ROW; idx += FINISH_CLUSTER_THREADS)
+        {
+            const int r = idx / ROW, k = idx % ROW, R = r0 + r;
+            if (k > NUM_SUMS) continue;
+            const bool fused = R < num_fused;
+            const int nt = fused ? tpb : gtpb;
+            const double* rows = (fused ? tile_rows + size_t(R) * tpb * ROW : general_rows + size_t(R - num_fused) * gtpb * ROW) + k;
+            double v = k == NUM_SUMS ? 1e300 : 0.0;
+            for (int t0 = 0; t0 < nt; t0 += 8)
+            {
+                double p[8];
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) p[t] = t0 + t < nt ? __ldcg(rows + size_t(t0 + t) * ROW) : (k == NUM_SUMS ? 1e300 : 0.0);
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) v = k == NUM_SUMS ? dmin(v, p[t]) : (t0 + t < nt ? v + p[t] : v);
+            }
+            srows[r][k] = v;
+        }
+        __syncthreads();
+
+        // block-wise work integral (scheme.cpp:363-374, 407-408) into the two spare columns of the block's row
+        const stage_t S = *stage_ptr;
+        for (int idx = tid; idx < 2 * n; idx += FINISH_CLUSTER_THREADS)
+        {
+            const int r = idx >> 1, k = idx & 1;
+            const double dm = srows[r][ACC_MASS + k], dpx = srows[r][ACC_PX + k], dpy = srows[r][ACC_PY + k];
+            double w = 0.0;
+            if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
+            {
+                const double M0 = k ? S.m2 : S.m1, px0 = (k ? S.vx2 : S.vx1) * M0, py0 = (k ? S.vy2 : S.vy1) * M0;
+                const double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
+                w = ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
+            }
+            srows[r][NUM_SUMS + 1 + k] = w;
+        }
+        __syncthreads();
+
+        // (B) this CTA's columns: group g folds rows g, g + 32, ... in order, then the 32 groups are folded in order
+        {
+            const int col = tid % 32, grp = tid / 32;
+            if (col < ROW - 1)
+            {
+                const bool is_min = col == NUM_SUMS;
+                double v = is_min ? 1e300 : 0.0;
+                for (int r = grp; r < n; r += 32)
+                {
+                    double p = srows[r][col];
+                    v = is_min ? dmin(v, p) : v + p;
+                }
+                part[grp][col] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < ROW - 1)
+        {
+            const int k = tid;
+            double f = part[0][k];
+            for (int g = 1; g < 32; ++g) f = k == NUM_SUMS ? dmin(f, part[g][k]) : f + part[g][k];
+            mine[k] = f;
+        }
+        cluster.sync();
+
+        // (C) CTA 0: the eight partial rows through distributed shared memory, in rank order
+        if (rank == 0)
+        {
+            if (tid < ROW - 1)
+            {
+                const int k = tid;
+                double f = mine[k];
+                for (int c = 1; c < FINISH_CLUSTER; ++c)
+                {
+                    const double p = cluster.map_shared_rank(mine, c)[k];
+                    f = k == NUM_SUMS ? dmin(f, p) : f + p;
+                }
+                if (k < NUM_SUMS) result->sums[k] = f;
+                else if (k == NUM_SUMS) { result->dt_min = f; dt_min_all = f; }
+                else result->work[k - NUM_SUMS - 1] = f;
+            }
+            if (tid == 64)
+            {
+                result->num_negative = fail->count;
+                fail->pad = fail->count;
+                fail->count = 0;
+            }
+        }
+        cluster.sync();         // the other CTAs' shared memory stays alive until CTA 0 has read it
+        if (rank != 0 || ! prep.enabled) return;
+        if (prep.enabled == 2)
+        {
+            __threadfence();
+            __syncthreads();
+            peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
+                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results);
+            return;
+        }
+        if (tid == 96 || tid == 97)
+        {
+            const double t = prep.current_a->time, dt = prep.current_a->dt;
+            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
+            const double dt_next = prep.cfg.fixed_dt ? prep.cfg.recommended_time_step : prep.cfg.cfl_number * dt_min_all;
+            if (tid == 96) { prep.next_a->time = t_next; prep.next_a->dt = dt_next; }
+            else { prep.next_b->time = t_next + dt_next; prep.next_b->dt = dt_next; }
+        }
+    }
+
+    /**
      * End of an RK2 step, on the device: fold the two stage results over the ranks (rank order, so every
      * rank gets the same bits), publish them to the host, and write the stage inputs of the NEXT step --
      * dt = cfl * min(spacing / wavespeed) (subprog_binary.cpp:281-283), time = t/2 + ((t + dt) + dt)/2
@@ -1315,6 +1447,7 @@ struct device_solver_t::impl_t
     double* d_partials2 = nullptr;              // second row buffer: the two stages of a step stay separate
     double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
     double* d_general_tile_rows[2] = {nullptr, nullptr};    // general_update_tiled: one row per tile of a block at a refinement jump
+    bool multi_cta_finish = false;              // M3B_MULTI_CTA_FINISH=1: never use finish_stage_cluster
     bool untiled_general = false;               // M3B_UNTILED_GENERAL=1: the one-CTA-per-block any-tree update (reference for the tiled one)
     double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows, one set per slot parity
     size_t cta_rows_stride = 0;
@@ -1555,8 +1688,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         M3B_CUDA(cudaFuncSetAttribute(general_update_tiled<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(tile_t<16, 16>))));
     }
     if (const char* e = std::getenv("M3B_UNTILED_GENERAL")) impl->untiled_general = std::atoi(e) != 0;
+    if (const char* e = std::getenv("M3B_MULTI_CTA_FINISH")) impl->multi_cta_finish = std::atoi(e) != 0;
     impl->cta_rows_stride = size_t(BO / FINISH_ROWS_PER_CTA + 1) * ROW;
     M3B_CUDA(cudaMalloc(&impl->d_cta_rows, 2 * impl->cta_rows_stride * sizeof(double)));
+    // (default priority: with the highest one the first stage's finish_stage displaces CTAs of the second stage kernel, +2 us)
     M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->stage_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->side_finish_done, cudaEventDisableTiming));
@@ -2041,8 +2176,13 @@ void device_solver_t::launch_finish(const double* tile_rows, int num_fused, int 
         M3B_CUDA(cudaStreamWaitEvent(s, impl->side_finish_done, 0));
         prep = impl->pending_prepare;
     }
-    finish_stage<<<ctas, FINISH_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, gtpb, num_rows, cta_rows,
-        impl->d_counters + (slot & 1), impl->d_stage + slot, impl->d_fail + slot, result_target(slot), prep);
+    // on the critical path (not beside a stage kernel, finish_mode 1, where eight 1024-thread CTAs would wait for SMs to drain)
+    if (num_rows <= FINISH_CLUSTER_MAX_ROWS && ! impl->multi_cta_finish && finish_mode != 1)
+        finish_stage_cluster<<<FINISH_CLUSTER, FINISH_CLUSTER_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, gtpb,
+            num_rows, impl->d_stage + slot, impl->d_fail + slot, result_target(slot), prep);
+    else
+        finish_stage<<<ctas, FINISH_THREADS, 0, s>>>(tile_rows, num_fused, tpb, general_rows, gtpb, num_rows, cta_rows,
+            impl->d_counters + (slot & 1), impl->d_stage + slot, impl->d_fail + slot, result_target(slot), prep);
     ++launches;
     M3B_CUDA(cudaGetLastError());
     if (finish_mode == 1) M3B_CUDA(cudaEventRecord(impl->side_finish_done, impl->finish_stream));
