@@ -119,10 +119,22 @@ namespace
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = THREADS / 32;
 
-        for (int k = 0; k < NUM_SUMS; ++k)
         {
-            double v = warp_sum(sums[k]);
-            if (lane == 0) red[warp * (NUM_SUMS + 1) + k] = v;
+            // sixteen sums over 32 lanes by recursive halving (a lane keeps half of its values and trades the other half at
+            // distances 16, 8, 4, 2; one butterfly step finishes): 16 shuffled doubles per lane instead of 80.
+            // Lane 2 j ends with the total of sum j.
+            static_assert(NUM_SUMS == 16, "the halving below is written for sixteen values");
+            double v8[8], v4[4], v2[2], v1;
+            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) v8[k] = (b16 ? sums[8 + k] : sums[k]) + __shfl_xor_sync(0xffffffffu, b16 ? sums[k] : sums[8 + k], 16);
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) v4[k] = (b8 ? v8[4 + k] : v8[k]) + __shfl_xor_sync(0xffffffffu, b8 ? v8[k] : v8[4 + k], 8);
+            #pragma unroll
+            for (int k = 0; k < 2; ++k) v2[k] = (b4 ? v4[2 + k] : v4[k]) + __shfl_xor_sync(0xffffffffu, b4 ? v4[k] : v4[2 + k], 4);
+            v1 = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? v2[0] : v2[1], 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            if ((lane & 1) == 0) red[warp * (NUM_SUMS + 1) + (lane >> 1)] = v1;
         }
         double m = warp_min(dtmin);
         if (lane == 0) red[warp * (NUM_SUMS + 1) + NUM_SUMS] = m;
@@ -371,9 +383,8 @@ namespace
     }
 
     /** Primitive at cell (i, j) of block b with guard fill: extend(p0, axis, 1) (scheme.cpp:132-142). */
-    __device__ __forceinline__ prim_t prim_at(const mesh_dev_t& m, const double* U, int b, int i, int j)
+    __device__ __forceinline__ prim_t prim_from_ref(const mesh_dev_t& m, const double* U, const cell_ref_t& r)
     {
-        cell_ref_t r = resolve_cell(m, b, i, j);
         if (r.kind == 0) return load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
         prim_t p00 = load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
         prim_t p10 = load_prim(m, U, r.leaf[1], r.ci[1], r.cj[1]);
@@ -385,6 +396,11 @@ namespace
                 ((p00.vy + p10.vy) * 0.5 + (p01.vy + p11.vy) * 0.5) * 0.5};
     }
 
+    __device__ __forceinline__ prim_t prim_at(const mesh_dev_t& m, const double* U, int b, int i, int j)
+    {
+        return prim_from_ref(m, U, resolve_cell(m, b, i, j));
+    }
+
     __device__ __forceinline__ prim_t load_grad(const mesh_dev_t& m, const double* G, int axis, int leaf, int i, int j)
     {
         size_t c = (size_t(m.gslot[leaf]) * m.N + i) * m.N + j;
@@ -393,9 +409,8 @@ namespace
     }
 
     /** Gradient (d/d axis) at cell (i, j) of block b with guard fill: extend(gx, ...) etc. (scheme.cpp:810-813). */
-    __device__ __forceinline__ prim_t grad_at(const mesh_dev_t& m, const double* G, int axis, int b, int i, int j)
+    __device__ __forceinline__ prim_t grad_from_ref(const mesh_dev_t& m, const double* G, int axis, const cell_ref_t& r)
     {
-        cell_ref_t r = resolve_cell(m, b, i, j);
         if (r.kind == 0) return load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
         prim_t g00 = load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
         prim_t g10 = load_grad(m, G, axis, r.leaf[1], r.ci[1], r.cj[1]);
@@ -404,6 +419,11 @@ namespace
         return {((g00.s + g10.s) * 0.5 + (g01.s + g11.s) * 0.5) * 0.5,
                 ((g00.vx + g10.vx) * 0.5 + (g01.vx + g11.vx) * 0.5) * 0.5,
                 ((g00.vy + g10.vy) * 0.5 + (g01.vy + g11.vy) * 0.5) * 0.5};
+    }
+
+    __device__ __forceinline__ prim_t grad_at(const mesh_dev_t& m, const double* G, int axis, int b, int i, int j)
+    {
+        return grad_from_ref(m, G, axis, resolve_cell(m, b, i, j));
     }
 
     /** P2 + P3 for the listed blocks: physical PLM gradients at the block's own spacing. */
@@ -613,6 +633,10 @@ namespace
         const int tid = threadIdx.x;
         const double h = mesh.spacing[b];
 
+        // which block sides border a finer neighbour (their faces take the flux-correction path): loaded now, used after the barrier
+        const bool finer_lo_x = i0 == 0 && mesh.nbr[b * 4 + 0].kind == 2, finer_hi_x = i0 + TX == N && mesh.nbr[b * 4 + 1].kind == 2;
+        const bool finer_lo_y = j0 == 0 && mesh.nbr[b * 4 + 2].kind == 2, finer_hi_y = j0 + TY == N && mesh.nbr[b * 4 + 3].kind == 2;
+
         // ---- tile + 1 guard layer (no corners: a face only needs its two cells): primitives and physical gradients
         for (int k = tid; k < (TX + 2) * (TY + 2); k += THREADS)
         {
@@ -620,8 +644,9 @@ namespace
             const bool edge_i = li == 0 || li == TX + 1, edge_j = lj == 0 || lj == TY + 1;
             if (edge_i && edge_j) continue;
             const int gi = i0 - 1 + li, gj = j0 - 1 + lj;
-            const prim_t p = prim_at(mesh, Uin, b, gi, gj);
-            const prim_t gx = grad_at(mesh, G, 0, b, gi, gj), gy = grad_at(mesh, G, 1, b, gi, gj);
+            const cell_ref_t ref = resolve_cell(mesh, b, gi, gj);       // once for the primitive and both gradients
+            const prim_t p = prim_from_ref(mesh, Uin, ref);
+            const prim_t gx = grad_from_ref(mesh, G, 0, ref), gy = grad_from_ref(mesh, G, 1, ref);
             T.P[0][li][lj] = p.s;  T.P[1][li][lj] = p.vx;  T.P[2][li][lj] = p.vy;
             T.G[0][li][lj] = gx.s; T.G[1][li][lj] = gx.vx; T.G[2][li][lj] = gx.vy;
             T.G[3][li][lj] = gy.s; T.G[4][li][lj] = gy.vx; T.G[5][li][lj] = gy.vy;
@@ -631,8 +656,6 @@ namespace
         __syncthreads();
 
         // ---- fluxes (times face length, as block_fluxes_u, scheme.cpp:472-516)
-        const bool finer_lo_x = i0 == 0 && mesh.nbr[b * 4 + 0].kind == 2, finer_hi_x = i0 + TX == N && mesh.nbr[b * 4 + 1].kind == 2;
-        const bool finer_lo_y = j0 == 0 && mesh.nbr[b * 4 + 2].kind == 2, finer_hi_y = j0 + TY == N && mesh.nbr[b * 4 + 3].kind == 2;
 
         auto x_face = [&] (int li, int lj)      // between tile cells (li - 1, lj) and (li, lj), 0 <= li <= TX
         {
