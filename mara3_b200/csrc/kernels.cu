@@ -615,7 +615,7 @@ namespace
      * Rows: one per tile, folded per block by finish_stage like the fused kernels' rows.
      */
     template<int TX, int TY>
-    __global__ void __launch_bounds__(THREADS, 2) general_update_tiled(
+    __global__ void __launch_bounds__(THREADS, 3) general_update_tiled(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
         const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
         double* __restrict__ partials, fail_dev_t* fail)
