@@ -311,7 +311,6 @@ namespace
 
 
 }
-#include "stage_strip.cuh"
 namespace
 {
     // =======================================================================
@@ -740,6 +739,10 @@ namespace
     }
 
 
+}
+#include "stage_strip.cuh"      // after the any-tree helpers: its JUMP variant fetches guard cells through them
+namespace
+{
     // =======================================================================
     // Stand-alone CFL pass, row folding, layout changes
     // =======================================================================
@@ -1448,6 +1451,8 @@ struct device_solver_t::impl_t
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
+    tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
+    bool jump_strip = false;                // blocks at jumps take stage_strip<.., JUMP> (M3B_JUMP_STRIP=0: the 16 x 16 any-tree kernels)
     std::vector<int> regular, irregular, gradient_blocks;
     int* d_regular = nullptr;
     int* d_irregular = nullptr;
@@ -1678,6 +1683,32 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             }
         impl->d_tile_info = device_upload(info);
     }
+    impl->jump_strip = N % 32 == 0 && ! tiled_kernel && sd.conserve_linear_p;
+    if (const char* e = std::getenv("M3B_JUMP_STRIP")) impl->jump_strip = impl->jump_strip && std::atoi(e) != 0;
+    if (impl->jump_strip)
+    {
+        // the any-tree list (blocks at refinement jumps, or every owned block with general_only) in 16 x 32 strip tiles
+        const int tiles_y = N / 32, tpb = (N / 16) * tiles_y;
+        auto list = std::vector<int>();
+        if (general_only) for (int b = 0; b < BO; ++b) list.push_back(b);
+        else list = impl->irregular;
+        auto info = std::vector<tile_info_t>(std::max<size_t>(1, list.size() * tpb));
+        for (size_t r = 0; r < list.size(); ++r)
+            for (int t = 0; t < tpb; ++t)
+            {
+                auto& ti = info[r * tpb + t];
+                const int i0 = (t / tiles_y) * 16, j0 = (t % tiles_y) * 32;
+                ti.b = list[r];
+                for (int k = 0; k < 9; ++k) ti.n9[k] = ti.b;        // cells beyond the block come through resolve_cell
+                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t];
+                if (i0 == 0       && nbr[size_t(ti.b) * 4 + 0].kind == 2) ti.flags |= 2;
+                if (i0 + 16 == N  && nbr[size_t(ti.b) * 4 + 1].kind == 2) ti.flags |= 4;
+                if (j0 == 0       && nbr[size_t(ti.b) * 4 + 2].kind == 2) ti.flags |= 8;
+                if (j0 + 32 == N  && nbr[size_t(ti.b) * 4 + 3].kind == 2) ti.flags |= 16;
+                ti.pad = 0;
+            }
+        impl->d_jump_tile_info = device_upload(info);
+    }
     impl->d_irregular = device_upload(impl->irregular);
     impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
 
@@ -1820,6 +1851,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         set_smem(stage_strip<4, 64, true, 0>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 1>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 2>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, false, 0, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, true, 0, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, false, 0, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 0, true>, sizeof(strip_smem_t));
         impl->fast_eos = ! sd.axisymmetric_cs2 && sd.nu == 0.0 && sd.alpha_cutoff_radius == 0.0 && sd.density_floor == 0.0;
     }
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
@@ -1834,7 +1869,7 @@ device_solver_t::~device_solver_t()
     for (auto p : {(void*) impl->mesh.xv, (void*) impl->mesh.yv, (void*) impl->mesh.spacing, (void*) impl->mesh.inv_spacing, (void*) impl->mesh.nbr,
                    (void*) impl->mesh.nbr9, (void*) impl->mesh.gslot, (void*) impl->mesh.U0, (void*) impl->mesh.br,
                    (void*) impl->d_regular, (void*) impl->d_irregular, (void*) impl->d_gradient_blocks, (void*) impl->d_gradients,
-                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_tile_info, (void*) impl->d_fail})
+                   (void*) impl->d_partials, (void*) impl->d_staging, (void*) impl->d_tile_flags, (void*) impl->d_tile_info, (void*) impl->d_jump_tile_info, (void*) impl->d_fail})
         if (p) cudaFree(p);
     for (auto p : impl->owned) cudaFree(p);
     for (auto p : {(void*) impl->d_send_entries, (void*) impl->d_recv_entries, (void*) impl->d_send_buffer, (void*) impl->d_recv_buffer,
@@ -2076,7 +2111,9 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
     int fused_ctas = num_fused * tpb;
     // the any-tree path in 16 x 16 tiles where the block size allows (one row per tile), else one CTA and one row per block
-    const int gtpb = N % 16 == 0 && ! impl->untiled_general ? (N / 16) * (N / 16) : 1;
+    const bool jump_strip = impl->jump_strip && impl->strip && ! impl->untiled_general;
+    const int ggtpb = N % 16 == 0 && ! impl->untiled_general ? (N / 16) * (N / 16) : 1;     // tiles of general_gradients_tiled
+    const int gtpb = jump_strip ? tpb : ggtpb;
     double* general_rows = gtpb > 1 ? impl->d_general_tile_rows[slot & 1] : block_rows;
     exchange = exchange && num_ranks > 1;
     impl->mark(s, "stage begin");
@@ -2111,7 +2148,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             mesh.ready_flag = impl->d_ready;
             mesh.ready_value = impl->exchange_counter;
             kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(mesh, impl->model, st, impl->d_tile_info + size_t(first) * tpb,
-                in.data, un_data, out.data, tiles, impl->d_fail + slot);
+                in.data, un_data, out.data, tiles, impl->d_fail + slot, nullptr);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
@@ -2161,9 +2198,19 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         // gradients are needed for the general blocks and every block they can fetch from
         int ng = int(impl->gradient_blocks.size());
-        if (gtpb > 1) general_gradients_tiled<16, 16><<<ng * gtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        if (ggtpb > 1) general_gradients_tiled<16, 16><<<ng * ggtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
         else general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        if (gtpb > 1)
+        if (jump_strip)
+        {
+            // the strip kernel with guard cells and gradients beyond the block sides through the tree operators
+            auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true> : stage_strip<4, 64, false, 0, true>)
+                                  : (impl->fast_eos ? stage_strip<4, 0, true, 0, true> : stage_strip<4, 0, false, 0, true>);
+            mesh_dev_t mesh = impl->mesh;
+            mesh.first_wait_cta = 0x7fffffff;
+            kernel<<<num_general * tpb, STRIP_THREADS, sizeof(strip_smem_t), s>>>(mesh, impl->model, st, impl->d_jump_tile_info,
+                in.data, un_data, out.data, general_rows, impl->d_fail + slot, impl->d_gradients);
+        }
+        else if (gtpb > 1)
             general_update_tiled<16, 16><<<num_general * gtpb, THREADS, sizeof(tile_t<16, 16>), s>>>(impl->mesh, impl->model, st, d_general,
                 in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
         else

@@ -16,6 +16,13 @@
  *        through two small shared arrays.  Cells are written once; 16 running sums, the CFL minimum and the
  *        negative-density count are folded per CTA.
  *
+ * JUMP = true is the same kernel for blocks at refinement jumps (any 2:1 balanced tree): cells beyond a block side
+ * are not recomputed from the neighbour's state but taken as the reference's guard fill delivers them -- primitives
+ * through get_cell_block (injection from a coarser block, 2 x 2 mean of finer ones, mesh_tree_operators.hpp:223-252)
+ * and PLM gradients from general_gradients' per-block arrays through the same operator (scheme.cpp:810-813) -- and
+ * the faces on a side whose neighbour is finer are replaced by the sum of the two fine fluxes (correct_fluxes_*,
+ * scheme.cpp:614-720).  Everything inside the block runs exactly as in the regular variant.
+ *
  * The loop is rolled on purpose: fully unrolled the kernel is 110 KB of SASS and a fifth of all
  * issue slots stall on instruction fetch (profiles/); rolled it stays inside the instruction cache.
  */
@@ -31,6 +38,7 @@ namespace
         double G[6][SX + 2][SY + 2];        // un-divided PLM differences d/dx (3), d/dy (3) on tile + 1 halo
         double XB[3][5][SY];                // x-face fluxes at rows 4, 8, 12 (strip starts) and 16 (tile boundary)
         double YB[3][SX];                   // y-face fluxes at the tile's high-y boundary
+        double YLo[3][SX];                  // JUMP: corrected y-face fluxes at a low-y block side with a finer neighbour
         double xv[SX + 1];
         double yv[SY + 1];
         // squared-distance tables of the tile's face / centre coordinates to the two bodies (k = 0, 1) and
@@ -78,11 +86,11 @@ namespace
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
     }
 
-    template<int MIN_CTAS, int NB, bool FAST, int MODE>
+    template<int MIN_CTAS, int NB, bool FAST, int MODE, bool JUMP = false>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* partials, fail_dev_t* fail)
+        double* partials, fail_dev_t* fail, const double* __restrict__ Gphys = nullptr)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         strip_smem_t& T = *reinterpret_cast<strip_smem_t*>(smem_raw);
@@ -101,6 +109,9 @@ namespace
         const size_t FS = mesh.FS;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const bool has_buffer = tiC.z & 1;
+        // JUMP: block sides of this tile whose neighbour is finer (tile_info flags, bits 1-4: low-x, high-x, low-y, high-y)
+        const bool finer_lo_x = JUMP && (tiC.z & 2), finer_hi_x = JUMP && (tiC.z & 4);
+        const bool finer_lo_y = JUMP && (tiC.z & 8), finer_hi_y = JUMP && (tiC.z & 16);
 
         // one "generation" of resident CTAs ahead: pull the tile that a later CTA of this SM slot will load from HBM into L2
         {
@@ -160,6 +171,7 @@ namespace
             const double* __restrict__ U1 = Uin + FS;
             const double* __restrict__ U2 = Uin + 2 * FS;
             double2 uc[3][3];
+            bool inside[3] = {true, true, true};    // JUMP: chunks beyond a block side are not loaded here (guard ring below)
 
             #pragma unroll
             for (int k = 0; k < 3; ++k)
@@ -171,9 +183,13 @@ namespace
                     const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
                     const int nb = di < 0 ? nlo : (di > 0 ? nhi : nmid);
                     const long c = (long(nb) * N + (gi - di * N)) * N + col;
-                    uc[k][0] = *reinterpret_cast<const double2*>(Uin + c);
-                    uc[k][1] = *reinterpret_cast<const double2*>(U1 + c);
-                    uc[k][2] = *reinterpret_cast<const double2*>(U2 + c);
+                    if (JUMP) inside[k] = di == 0 && dj == 0;
+                    if (inside[k])
+                    {
+                        uc[k][0] = *reinterpret_cast<const double2*>(Uin + c);
+                        uc[k][1] = *reinterpret_cast<const double2*>(U1 + c);
+                        uc[k][2] = *reinterpret_cast<const double2*>(U2 + c);
+                    }
                 }
             }
             // coordinate tables while the loads are in flight
@@ -221,7 +237,7 @@ namespace
             for (int k = 0; k < 3; ++k)
             {
                 const int row = rr + 7 * k;
-                if (rr < 7 && row < SX + 4)
+                if (rr < 7 && row < SX + 4 && inside[k])
                 {
                     // iso2d::recover_primitive (physics_iso2d.hpp:351-362) for the chunk's two cells
                     const double ia = fast_rcp(uc[k][0].x), ib = fast_rcp(uc[k][0].y);
@@ -229,6 +245,32 @@ namespace
                     *reinterpret_cast<double2*>(&T.P[1][row][2 * cc]) = make_double2(uc[k][1].x * ia, uc[k][1].y * ib);
                     *reinterpret_cast<double2*>(&T.P[2][row][2 * cc]) = make_double2(uc[k][2].x * ia, uc[k][2].y * ib);
                 }
+            }
+        }
+        // JUMP: the one-cell guard ring beyond the block's sides (no corners: a face only needs its two cells).  Primitives
+        // now; the neighbours' gradients, scaled to this block's un-divided differences, replace what phase 1 computes there.
+        int ring_g = -1, ring_c = -1;
+        double ring_grad[6];
+        if (JUMP)
+        {
+            const int k = threadIdx.x;          // 2 (SY + 2) + 2 SX = 100 ring cells
+            int li, lj;
+            if      (k < SY + 2)           { li = -1; lj = k - 1; }
+            else if (k < 2 * (SY + 2))     { li = SX; lj = k - (SY + 2) - 1; }
+            else if (k < 2 * (SY + 2) + SX){ li = k - 2 * (SY + 2); lj = -1; }
+            else                           { li = k - 2 * (SY + 2) - SX; lj = SY; }
+            const int gi = i0 + li, gj = j0 + lj;
+            const bool out_i = gi < 0 || gi >= N, out_j = gj < 0 || gj >= N;
+            if (k < 2 * (SY + 2) + 2 * SX && (out_i != out_j))
+            {
+                const cell_ref_t ref = resolve_cell(mesh, b, gi, gj);
+                const prim_t p = prim_from_ref(mesh, Uin, ref);
+                const prim_t gx = grad_from_ref(mesh, Gphys, 0, ref), gy = grad_from_ref(mesh, Gphys, 1, ref);
+                const double hb = mesh.spacing[b];
+                T.P[0][li + 2][lj + 2] = p.s; T.P[1][li + 2][lj + 2] = p.vx; T.P[2][li + 2][lj + 2] = p.vy;
+                ring_g = li + 1; ring_c = lj + 1;
+                ring_grad[0] = gx.s * hb; ring_grad[1] = gx.vx * hb; ring_grad[2] = gx.vy * hb;
+                ring_grad[3] = gy.s * hb; ring_grad[4] = gy.vx * hb; ring_grad[5] = gy.vy * hb;
             }
         }
         __syncthreads();
@@ -272,6 +314,15 @@ namespace
                     T.G[q][g][c]     = plm_from_differences(ctr - T.P[q][g][c + 1], T.P[q][g + 2][c + 1] - ctr, S.theta);
                     T.G[3 + q][g][c] = plm_from_differences(ctr - T.P[q][g + 1][c], T.P[q][g + 1][c + 2] - ctr, S.theta);
                 }
+            }
+        }
+        if (JUMP)
+        {
+            __syncthreads();
+            if (ring_g >= 0)
+            {
+                #pragma unroll
+                for (int q = 0; q < 6; ++q) T.G[q][ring_g][ring_c] = ring_grad[q];
             }
         }
         __syncthreads();
@@ -341,24 +392,46 @@ namespace
 
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
         // faces of strip row 0, whose x-flux is also the high-x flux of the strip below
+        // JUMP: on a block side whose neighbour is finer the face flux is the sum of the two fine faces' (length-weighted)
+        // fluxes as the fine blocks compute them (correct_fluxes_*, scheme.cpp:614-720), here per unit length of this block
+        auto corrected_x = [&] (int f, double F[3])
+        {
+            general_face_flux_corrected<0>(mesh, model, S, Uin, Gphys, b, f, j0 + lj, F);
+            F[0] *= inv_h; F[1] *= inv_h; F[2] *= inv_h;
+        };
+        auto corrected_y = [&] (int f, int li, double F[3])
+        {
+            general_face_flux_corrected<1>(mesh, model, S, Uin, Gphys, b, f, i0 + li, F);
+            F[0] *= inv_h; F[1] *= inv_h; F[2] *= inv_h;
+        };
         if (warp == 0)
         {
             double F[3];
-            strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
+            if (JUMP && finer_hi_x) corrected_x(N, F);
+            else strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
             T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
         }
         else if (warp == 1 && lane < SX)
         {
             double F[3];
-            strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
+            if (JUMP && finer_hi_y) corrected_y(N, lane, F);
+            else strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
             T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
         }
+        else if (JUMP && warp == 2 && lane < SX && finer_lo_y)
+        {
+            double F[3];
+            corrected_y(0, lane, F);
+            T.YLo[0][lane] = F[0]; T.YLo[1][lane] = F[1]; T.YLo[2][lane] = F[2];
+        }
         double FxLo[3], FyLo[3];
-        strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
+        if (JUMP && finer_lo_x && warp == 0) corrected_x(0, FxLo);
+        else strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
         strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FyLo);
 
         if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
         __syncthreads();
+        if (JUMP && finer_lo_y && lane == 0) { FyLo[0] = T.YLo[0][li0]; FyLo[1] = T.YLo[1][li0]; FyLo[2] = T.YLo[2][li0]; }
 
         // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
         // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
@@ -368,6 +441,7 @@ namespace
             double FxNew[3], FyNew[3];
             strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew);
             strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew);
+            if (JUMP && finer_lo_y && lane == 0) { FyNew[0] = T.YLo[0][li0 + r]; FyNew[1] = T.YLo[1][li0 + r]; FyNew[2] = T.YLo[2][li0 + r]; }
             update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
             load_cell(r, u, u0, br, un);
             #pragma unroll
