@@ -487,6 +487,38 @@ namespace
     }
 
     /**
+     * The same for the two outermost cell layers along each side of the listed blocks only, one CTA per (block, side):
+     * all that stage_strip<.., JUMP> reads from a neighbour (guard gradients are injected from / averaged over cells at
+     * most two deep, and the fine faces of the flux correction touch the outermost layer).
+     */
+    __global__ void __launch_bounds__(128) general_gradients_ring(
+        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
+        const double* __restrict__ Uin, double* __restrict__ G)
+    {
+        const stage_t S = *stage_ptr;
+        const int N = mesh.N, b = list[blockIdx.x >> 2], side = blockIdx.x & 3;
+        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
+        const size_t base = size_t(mesh.gslot[b]) * N * N;
+
+        for (int k = threadIdx.x; k < 2 * N; k += 128)
+        {
+            const int d = k / N, a = k - d * N;             // layer, position along the side
+            const int i = side == 0 ? d : (side == 1 ? N - 1 - d : a);
+            const int j = side == 2 ? d : (side == 3 ? N - 1 - d : a);
+            const prim_t c  = prim_at(mesh, Uin, b, i, j);
+            const prim_t xl = prim_at(mesh, Uin, b, i - 1, j), xr = prim_at(mesh, Uin, b, i + 1, j);
+            const prim_t yl = prim_at(mesh, Uin, b, i, j - 1), yr = prim_at(mesh, Uin, b, i, j + 1);
+            const size_t cell = base + size_t(i) * N + j;
+            G[0 * mesh.GS + cell] = plm_diff(xl.s,  c.s,  xr.s,  theta) * inv_h;
+            G[1 * mesh.GS + cell] = plm_diff(xl.vx, c.vx, xr.vx, theta) * inv_h;
+            G[2 * mesh.GS + cell] = plm_diff(xl.vy, c.vy, xr.vy, theta) * inv_h;
+            G[3 * mesh.GS + cell] = plm_diff(yl.s,  c.s,  yr.s,  theta) * inv_h;
+            G[4 * mesh.GS + cell] = plm_diff(yl.vx, c.vx, yr.vx, theta) * inv_h;
+            G[5 * mesh.GS + cell] = plm_diff(yl.vy, c.vy, yr.vy, theta) * inv_h;
+        }
+    }
+
+    /**
      * Flux (times face length) through face f (0..N) of block b along AXIS at transverse index k,
      * as block b computes it: block_fluxes_u (scheme.cpp:472-516).
      */
@@ -1452,6 +1484,9 @@ struct device_solver_t::impl_t
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
+    cudaStream_t jump_stream = nullptr;     // stage_strip<.., JUMP> runs here, beside the regular blocks' launch
+    cudaEvent_t gradients_done = nullptr, jump_done = nullptr;
+    bool serial_jump = false;               // M3B_SERIAL_JUMP=1: the jump blocks' launch follows the regular blocks' on the compute stream
     bool jump_strip = false;                // blocks at jumps take stage_strip<.., JUMP> (M3B_JUMP_STRIP=0: the 16 x 16 any-tree kernels)
     std::vector<int> regular, irregular, gradient_blocks;
     int* d_regular = nullptr;
@@ -1685,6 +1720,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     }
     impl->jump_strip = N % 32 == 0 && ! tiled_kernel && sd.conserve_linear_p;
     if (const char* e = std::getenv("M3B_JUMP_STRIP")) impl->jump_strip = impl->jump_strip && std::atoi(e) != 0;
+    if (const char* e = std::getenv("M3B_SERIAL_JUMP")) impl->serial_jump = std::atoi(e) != 0;
     if (impl->jump_strip)
     {
         // the any-tree list (blocks at refinement jumps, or every owned block with general_only) in 16 x 32 strip tiles
@@ -1748,6 +1784,9 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     // (default priority: with the highest one the first stage's finish_stage displaces CTAs of the second stage kernel, +2 us)
     M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->stage_done, cudaEventDisableTiming));
+    M3B_CUDA(cudaStreamCreateWithFlags(&impl->jump_stream, cudaStreamNonBlocking));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->gradients_done, cudaEventDisableTiming));
+    M3B_CUDA(cudaEventCreateWithFlags(&impl->jump_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->side_finish_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->fast_prepare_done, cudaEventDisableTiming));
     for (auto& e : impl->positions_done) M3B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2170,6 +2209,34 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         e0 = impl->event_pool.back(); impl->event_pool.pop_back();
         e1 = impl->event_pool.back(); impl->event_pool.pop_back();
     }
+    // Blocks at refinement jumps through the strip kernel: their launch runs on its own stream beside the regular blocks'
+    // (two partial waves of CTAs fill each other's tails); the gradients both read come first.
+    auto launch_jump_strip = [&] (cudaStream_t js)
+    {
+        auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true> : stage_strip<4, 64, false, 0, true>)
+                              : (impl->fast_eos ? stage_strip<4, 0, true, 0, true> : stage_strip<4, 0, false, 0, true>);
+        mesh_dev_t mesh = impl->mesh;
+        mesh.first_wait_cta = 0x7fffffff;
+        kernel<<<num_general * tpb, STRIP_THREADS, sizeof(strip_smem_t), js>>>(mesh, impl->model, st, impl->d_jump_tile_info,
+            in.data, un_data, out.data, general_rows, impl->d_fail + slot, impl->d_gradients);
+        ++launches;
+        M3B_CUDA(cudaGetLastError());
+    };
+    const int ng = int(impl->gradient_blocks.size());
+    bool jump_forked = false;
+    if (jump_strip && num_general > 0 && ! exchange)
+    {
+        general_gradients_ring<<<ng * 4, 128, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        ++launches;
+        if (num_fused > 0 && ! impl->serial_jump)
+        {
+            M3B_CUDA(cudaEventRecord(impl->gradients_done, s));
+            M3B_CUDA(cudaStreamWaitEvent(impl->jump_stream, impl->gradients_done, 0));
+            launch_jump_strip(impl->jump_stream);
+            M3B_CUDA(cudaEventRecord(impl->jump_done, impl->jump_stream));
+            jump_forked = true;
+        }
+    }
     if (exchange)
     {
         // guard zones travel on their own stream while the interior blocks are updated
@@ -2194,23 +2261,22 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         M3B_CUDA(cudaEventRecord(e1, s));
         impl->timing_events.emplace_back(e0, e1);
     }
-    if (num_general > 0)
+    if (jump_forked) M3B_CUDA(cudaStreamWaitEvent(s, impl->jump_done, 0));
+    else if (num_general > 0 && jump_strip)
+    {
+        if (exchange)       // (overlapped exchange: the guard zones have only just arrived)
+        {
+            general_gradients_ring<<<ng * 4, 128, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+            ++launches;
+        }
+        launch_jump_strip(s);
+    }
+    else if (num_general > 0)
     {
         // gradients are needed for the general blocks and every block they can fetch from
-        int ng = int(impl->gradient_blocks.size());
         if (ggtpb > 1) general_gradients_tiled<16, 16><<<ng * ggtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
         else general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        if (jump_strip)
-        {
-            // the strip kernel with guard cells and gradients beyond the block sides through the tree operators
-            auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true> : stage_strip<4, 64, false, 0, true>)
-                                  : (impl->fast_eos ? stage_strip<4, 0, true, 0, true> : stage_strip<4, 0, false, 0, true>);
-            mesh_dev_t mesh = impl->mesh;
-            mesh.first_wait_cta = 0x7fffffff;
-            kernel<<<num_general * tpb, STRIP_THREADS, sizeof(strip_smem_t), s>>>(mesh, impl->model, st, impl->d_jump_tile_info,
-                in.data, un_data, out.data, general_rows, impl->d_fail + slot, impl->d_gradients);
-        }
-        else if (gtpb > 1)
+        if (gtpb > 1)
             general_update_tiled<16, 16><<<num_general * gtpb, THREADS, sizeof(tile_t<16, 16>), s>>>(impl->mesh, impl->model, st, d_general,
                 in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
         else
