@@ -46,13 +46,15 @@ namespace
     constexpr int FINISH_ROWS_PER_CTA = 32;     // block rows folded by one finish_stage CTA
     constexpr int stage_ring_size = 64;
 
-    struct face_nbr_dev_t
+    struct __align__(16) face_nbr_dev_t
     {
         int kind;                       // 0 same, 1 coarser, 2 finer
         int leaf[4];
         int bx, by;
         int pad;
+        int gs[4];                      // gslot of leaf[q]: where its gradients live in the scratch (stage_strip<.., JUMP> reads the record as three int4)
     };
+    static_assert(sizeof(face_nbr_dev_t) == 48, "stage_strip reads face_nbr_dev_t as three int4");
 
     struct mesh_dev_t
     {
@@ -1611,6 +1613,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             d.kind = int(fn.kind);
             for (int q = 0; q < 4; ++q) d.leaf[q] = local(fn.leaf[q]);
             d.bx = fn.bx; d.by = fn.by; d.pad = 0;
+            for (int q = 0; q < 4; ++q) d.gs[q] = -1;
         }
         if (b >= BO) continue;          // ghost blocks are only read from
         bool regular = true;
@@ -1666,6 +1669,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             for (int side = 0; side < 4; ++side) for (int q = 0; q < 4; ++q) mark(nbr[size_t(b) * 4 + side].leaf[q]);
         }
     for (int b = 0; b < B; ++b) if (in_gradient_set[b]) { gslot[b] = int(impl->gradient_blocks.size()); impl->gradient_blocks.push_back(b); }
+    for (auto& d : nbr) for (int q = 0; q < 4; ++q) d.gs[q] = d.leaf[q] >= 0 ? gslot[d.leaf[q]] : -1;
 
     impl->mesh.B = B;
     impl->mesh.N = N;

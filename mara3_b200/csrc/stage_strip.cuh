@@ -39,6 +39,7 @@ namespace
         double XB[3][5][SY];                // x-face fluxes at rows 4, 8, 12 (strip starts) and 16 (tile boundary)
         double YB[3][SX];                   // y-face fluxes at the tile's high-y boundary
         double YLo[3][SX];                  // JUMP: corrected y-face fluxes at a low-y block side with a finer neighbour
+        double XLo[3][SY];                  // JUMP: the same at a low-x block side
         double xv[SX + 1];
         double yv[SY + 1];
         // squared-distance tables of the tile's face / centre coordinates to the two bodies (k = 0, 1) and
@@ -86,6 +87,71 @@ namespace
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
     }
 
+    /**
+     * JUMP: flux through the face of tile cell `t` on block side `side` (0 low-x, 1 high-x for AXIS 0; 2 low-y, 3 high-y for
+     * AXIS 1) whose neighbour is finer, per unit length of this block: the sum of the two fine faces' fluxes times their
+     * lengths as the fine blocks compute them (correct_fluxes_*, scheme.cpp:614-720; block_fluxes_u, :472-516).  The fine
+     * blocks' guard cell there is this block's cell by injection (mesh_prolong_restrict.hpp:161-196), primitives and
+     * gradients alike, so that side comes from shared memory; the fine cells and their gradients are read directly.
+     */
+    template<int AXIS>
+    __device__ __forceinline__ void jump_corrected_face(const strip_smem_t& T, const mesh_dev_t& mesh, const model_t& model, const stage_t& S,
+        const double* __restrict__ Uin, const double* __restrict__ Gphys, int b, int side, int t, int i0, int j0, int N, double h, double inv_h, double F[3])
+    {
+        const int4* np = reinterpret_cast<const int4*>(mesh.nbr + size_t(b) * 4 + side);
+        const int4 nA = __ldg(np), nB = __ldg(np + 1), nC = __ldg(np + 2);
+        const bool lo = (side & 1) == 0;            // the fine blocks lie on this block's low side: they are the left state
+        const int near = lo ? 1 : 0;
+        const int li = AXIS == 0 ? (lo ? 0 : SX - 1) : t;
+        const int lj = AXIS == 0 ? t : (lo ? 0 : SY - 1);
+        const int kt = 2 * (AXIS == 0 ? j0 + lj : i0 + li);
+        const int hi = kt >= N;
+        const int child = AXIS == 0 ? near + 2 * hi : hi + 2 * near;
+        const int leaf = child == 0 ? nA.y : (child == 1 ? nA.z : (child == 2 ? nA.w : nB.x));
+        const int gs   = child == 0 ? nC.x : (child == 1 ? nC.y : (child == 2 ? nC.z : nC.w));
+        const int kf = kt - hi * N, ff = lo ? N - 1 : 0;
+        const double* __restrict__ xvf = mesh.xv + size_t(leaf) * (N + 1);
+        const double* __restrict__ yvf = mesh.yv + size_t(leaf) * (N + 1);
+        const size_t FS = mesh.FS, GS = mesh.GS;
+
+        // all loads of both fine faces first
+        double u[2][3], g[2][5], va[2], vb[2];
+        const double fixed = AXIS == 0 ? xvf[lo ? N : 0] : yvf[lo ? N : 0];
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+        {
+            const int fi = AXIS == 0 ? ff : kf + m, fj = AXIS == 0 ? kf + m : ff;
+            const size_t c  = (size_t(leaf) * N + fi) * N + fj;
+            const size_t gc = (size_t(gs) * N + fi) * N + fj;
+            u[m][0] = Uin[c]; u[m][1] = Uin[FS + c]; u[m][2] = Uin[2 * FS + c];
+            #pragma unroll
+            for (int q = 0; q < 3; ++q) g[m][q] = Gphys[(3 * AXIS + q) * GS + gc];              // longitudinal
+            g[m][3] = Gphys[(3 * (1 - AXIS) + 1) * GS + gc];                                     // transverse, vx and vy
+            g[m][4] = Gphys[(3 * (1 - AXIS) + 2) * GS + gc];
+            va[m] = AXIS == 0 ? yvf[kf + m] : xvf[kf + m];
+            vb[m] = AXIS == 0 ? yvf[kf + m + 1] : xvf[kf + m + 1];
+        }
+        const prim_t pc = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
+        const prim_t gc = {T.G[3 * AXIS][li + 1][lj + 1] * inv_h, T.G[3 * AXIS + 1][li + 1][lj + 1] * inv_h, T.G[3 * AXIS + 2][li + 1][lj + 1] * inv_h};
+        const double hcx = T.G[3 * (1 - AXIS) + 1][li + 1][lj + 1] * inv_h, hcy = T.G[3 * (1 - AXIS) + 2][li + 1][lj + 1] * inv_h;
+
+        double acc[3] = {0.0, 0.0, 0.0};
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+        {
+            const prim_t pf = cons_to_prim(u[m][0], u[m][1], u[m][2]);
+            const prim_t gf = {g[m][0], g[m][1], g[m][2]};
+            const double mid = 0.5 * (va[m] + vb[m]), len = vb[m] - va[m];
+            const eos_t e = eos_at_face(model, S, AXIS == 0 ? fixed : mid, AXIS == 0 ? mid : fixed);
+            double Fm[3];
+            if (lo) face_flux<AXIS>(e, pf, pc, gf, gc, g[m][3], g[m][4], hcx, hcy, 0.25 * h, 1.0, Fm);
+            else    face_flux<AXIS>(e, pc, pf, gc, gf, hcx, hcy, g[m][3], g[m][4], 0.25 * h, 1.0, Fm);
+            if (m == 0) { acc[0] = Fm[0] * len; acc[1] = Fm[1] * len; acc[2] = Fm[2] * len; }
+            else        { acc[0] += Fm[0] * len; acc[1] += Fm[1] * len; acc[2] += Fm[2] * len; }
+        }
+        F[0] = acc[0] * inv_h; F[1] = acc[1] * inv_h; F[2] = acc[2] * inv_h;
+    }
+
     template<int MIN_CTAS, int NB, bool FAST, int MODE, bool JUMP = false>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info,
@@ -112,6 +178,31 @@ namespace
         // JUMP: block sides of this tile whose neighbour is finer (tile_info flags, bits 1-4: low-x, high-x, low-y, high-y)
         const bool finer_lo_x = JUMP && (tiC.z & 2), finer_hi_x = JUMP && (tiC.z & 4);
         const bool finer_lo_y = JUMP && (tiC.z & 8), finer_hi_y = JUMP && (tiC.z & 16);
+
+        // JUMP: the one-cell guard ring beyond the block's sides (no corners: a face only needs its two cells), one thread per
+        // ring cell.  The side's neighbour record is requested now; the cells it points at are loaded beside the tile.
+        bool ring_on = false;
+        int ring_li = 0, ring_lj = 0, ring_ii = 0, ring_jj = 0;
+        int4 rnA = make_int4(0, 0, 0, 0), rnB = rnA, rnC = rnA;
+        if (JUMP)
+        {
+            const int k = threadIdx.x;          // 2 (SY + 2) + 2 SX = 100 ring cells
+            if      (k < SY + 2)            { ring_li = -1; ring_lj = k - 1; }
+            else if (k < 2 * (SY + 2))      { ring_li = SX; ring_lj = k - (SY + 2) - 1; }
+            else if (k < 2 * (SY + 2) + SX) { ring_li = k - 2 * (SY + 2); ring_lj = -1; }
+            else                            { ring_li = k - 2 * (SY + 2) - SX; ring_lj = SY; }
+            const int gi = i0 + ring_li, gj = j0 + ring_lj;
+            const bool out_i = gi < 0 || gi >= N, out_j = gj < 0 || gj >= N;
+            ring_on = k < 2 * (SY + 2) + 2 * SX && (out_i != out_j);
+            if (ring_on)
+            {
+                const int side = gi < 0 ? 0 : (gi >= N ? 1 : (gj < 0 ? 2 : 3));
+                ring_ii = gi < 0 ? N - 1 : (gi >= N ? 0 : gi);
+                ring_jj = gj < 0 ? N - 1 : (gj >= N ? 0 : gj);
+                const int4* np = reinterpret_cast<const int4*>(mesh.nbr + size_t(b) * 4 + side);
+                rnA = __ldg(np); rnB = __ldg(np + 1); rnC = __ldg(np + 2);
+            }
+        }
 
         // one "generation" of resident CTAs ahead: pull the tile that a later CTA of this SM slot will load from HBM into L2
         {
@@ -157,6 +248,7 @@ namespace
         }
 
         // ------------------------------------------------------------------ phase 0: load + primitives
+        double ring_grad[6];
         {
             // The (SX + 4) x (SY + 4) region is 20 rows of 18 sixteen-byte chunks (two cells in y); columns j0 - 2 and
             // N are even, so a chunk never straddles two blocks.  Thread <-> (row rr + 7 k, chunk cc), k = 0, 1, 2:
@@ -191,6 +283,57 @@ namespace
                         uc[k][2] = *reinterpret_cast<const double2*>(U2 + c);
                     }
                 }
+            }
+            // JUMP: guard ring, second half: get_cell_block (mesh_tree_operators.hpp:223-252) for the ring cell -- the neighbour's
+            // own cell, the coarser neighbour's cell by injection, or the mean of the finer neighbour's 2 x 2 cells (axis 0 first,
+            // mesh_prolong_restrict.hpp:124-132, 262-272) -- for the primitives and, scaled to this block's un-divided differences,
+            // for the neighbour's gradients, which replace what phase 1 computes at the ring cells.
+            if (JUMP && ring_on)
+            {
+                const int kind = rnA.x;
+                const size_t GS = mesh.GS;
+                const double hb = mesh.spacing[b];
+                prim_t p;
+                if (kind != 2)
+                {
+                    const int ci = kind == 0 ? ring_ii : (rnB.y * N + ring_ii) / 2, cj = kind == 0 ? ring_jj : (rnB.z * N + ring_jj) / 2;
+                    const size_t c  = (size_t(rnA.y) * N + ci) * N + cj;
+                    const size_t gc = (size_t(rnC.x) * N + ci) * N + cj;
+                    const double u0 = Uin[c], u1 = Uin[FS + c], u2 = Uin[2 * FS + c];
+                    #pragma unroll
+                    for (int q = 0; q < 6; ++q) ring_grad[q] = Gphys[q * GS + gc] * hb;
+                    p = cons_to_prim(u0, u1, u2);
+                }
+                else
+                {
+                    // the four fine cells lie in one child: rows fi, fi + 1, columns fj, fj + 1 (fj even: 16-byte loads)
+                    const int fi = 2 * ring_ii, fj = 2 * ring_jj;
+                    const int child = (fi >= N) + 2 * (fj >= N);
+                    const int leaf = child == 0 ? rnA.y : (child == 1 ? rnA.z : (child == 2 ? rnA.w : rnB.x));
+                    const int gs   = child == 0 ? rnC.x : (child == 1 ? rnC.y : (child == 2 ? rnC.z : rnC.w));
+                    const size_t c  = (size_t(leaf) * N + (fi % N)) * N + (fj % N);
+                    const size_t gc = (size_t(gs) * N + (fi % N)) * N + (fj % N);
+                    double2 a[3], d[3];
+                    #pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                    {
+                        a[q] = *reinterpret_cast<const double2*>(Uin + q * FS + c);
+                        d[q] = *reinterpret_cast<const double2*>(Uin + q * FS + c + N);
+                    }
+                    #pragma unroll
+                    for (int q = 0; q < 6; ++q)
+                    {
+                        const double2 ga = *reinterpret_cast<const double2*>(Gphys + q * GS + gc);
+                        const double2 gd = *reinterpret_cast<const double2*>(Gphys + q * GS + gc + N);
+                        ring_grad[q] = (((ga.x + gd.x) * 0.5 + (ga.y + gd.y) * 0.5) * 0.5) * hb;
+                    }
+                    const prim_t p00 = cons_to_prim(a[0].x, a[1].x, a[2].x), p01 = cons_to_prim(a[0].y, a[1].y, a[2].y);
+                    const prim_t p10 = cons_to_prim(d[0].x, d[1].x, d[2].x), p11 = cons_to_prim(d[0].y, d[1].y, d[2].y);
+                    p = {((p00.s + p10.s) * 0.5 + (p01.s + p11.s) * 0.5) * 0.5,
+                         ((p00.vx + p10.vx) * 0.5 + (p01.vx + p11.vx) * 0.5) * 0.5,
+                         ((p00.vy + p10.vy) * 0.5 + (p01.vy + p11.vy) * 0.5) * 0.5};
+                }
+                T.P[0][ring_li + 2][ring_lj + 2] = p.s; T.P[1][ring_li + 2][ring_lj + 2] = p.vx; T.P[2][ring_li + 2][ring_lj + 2] = p.vy;
             }
             // coordinate tables while the loads are in flight
             {
@@ -247,32 +390,6 @@ namespace
                 }
             }
         }
-        // JUMP: the one-cell guard ring beyond the block's sides (no corners: a face only needs its two cells).  Primitives
-        // now; the neighbours' gradients, scaled to this block's un-divided differences, replace what phase 1 computes there.
-        int ring_g = -1, ring_c = -1;
-        double ring_grad[6];
-        if (JUMP)
-        {
-            const int k = threadIdx.x;          // 2 (SY + 2) + 2 SX = 100 ring cells
-            int li, lj;
-            if      (k < SY + 2)           { li = -1; lj = k - 1; }
-            else if (k < 2 * (SY + 2))     { li = SX; lj = k - (SY + 2) - 1; }
-            else if (k < 2 * (SY + 2) + SX){ li = k - 2 * (SY + 2); lj = -1; }
-            else                           { li = k - 2 * (SY + 2) - SX; lj = SY; }
-            const int gi = i0 + li, gj = j0 + lj;
-            const bool out_i = gi < 0 || gi >= N, out_j = gj < 0 || gj >= N;
-            if (k < 2 * (SY + 2) + 2 * SX && (out_i != out_j))
-            {
-                const cell_ref_t ref = resolve_cell(mesh, b, gi, gj);
-                const prim_t p = prim_from_ref(mesh, Uin, ref);
-                const prim_t gx = grad_from_ref(mesh, Gphys, 0, ref), gy = grad_from_ref(mesh, Gphys, 1, ref);
-                const double hb = mesh.spacing[b];
-                T.P[0][li + 2][lj + 2] = p.s; T.P[1][li + 2][lj + 2] = p.vx; T.P[2][li + 2][lj + 2] = p.vy;
-                ring_g = li + 1; ring_c = lj + 1;
-                ring_grad[0] = gx.s * hb; ring_grad[1] = gx.vx * hb; ring_grad[2] = gx.vy * hb;
-                ring_grad[3] = gy.s * hb; ring_grad[4] = gy.vx * hb; ring_grad[5] = gy.vy * hb;
-            }
-        }
         __syncthreads();
 
         // ------------------------------------------------------------------ phase 1: PLM differences
@@ -319,10 +436,10 @@ namespace
         if (JUMP)
         {
             __syncthreads();
-            if (ring_g >= 0)
+            if (ring_on)
             {
                 #pragma unroll
-                for (int q = 0; q < 6; ++q) T.G[q][ring_g][ring_c] = ring_grad[q];
+                for (int q = 0; q < 6; ++q) T.G[q][ring_li + 1][ring_lj + 1] = ring_grad[q];
             }
         }
         __syncthreads();
@@ -392,46 +509,48 @@ namespace
 
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the
         // faces of strip row 0, whose x-flux is also the high-x flux of the strip below
-        // JUMP: on a block side whose neighbour is finer the face flux is the sum of the two fine faces' (length-weighted)
-        // fluxes as the fine blocks compute them (correct_fluxes_*, scheme.cpp:614-720), here per unit length of this block
-        auto corrected_x = [&] (int f, double F[3])
+        // JUMP: faces on a block side whose neighbour is finer, one side per warp (0: high-x, 1: high-y, 2: low-y, 3: low-x)
+        if (JUMP)
         {
-            general_face_flux_corrected<0>(mesh, model, S, Uin, Gphys, b, f, j0 + lj, F);
-            F[0] *= inv_h; F[1] *= inv_h; F[2] *= inv_h;
-        };
-        auto corrected_y = [&] (int f, int li, double F[3])
-        {
-            general_face_flux_corrected<1>(mesh, model, S, Uin, Gphys, b, f, i0 + li, F);
-            F[0] *= inv_h; F[1] *= inv_h; F[2] *= inv_h;
-        };
-        if (warp == 0)
+            const int side = warp == 0 ? 1 : (warp == 1 ? 3 : (warp == 2 ? 2 : 0));
+            if ((tiC.z >> (1 + side)) & 1)
+            {
+                double F[3];
+                if (side < 2)
+                {
+                    jump_corrected_face<0>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
+                    double (*dst)[SY] = side == 1 ? T.XB[0] + 4 : T.XLo;     // row 4 of XB[q], or XLo[q], q-stride below
+                    const int qs = side == 1 ? 5 : 1;
+                    dst[0][lane] = F[0]; dst[qs][lane] = F[1]; dst[2 * qs][lane] = F[2];
+                }
+                else if (lane < SX)
+                {
+                    jump_corrected_face<1>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
+                    double (*dst)[SX] = side == 3 ? T.YB : T.YLo;
+                    dst[0][lane] = F[0]; dst[1][lane] = F[1]; dst[2][lane] = F[2];
+                }
+            }
+        }
+        if (warp == 0 && ! finer_hi_x)
         {
             double F[3];
-            if (JUMP && finer_hi_x) corrected_x(N, F);
-            else strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
+            strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
             T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
         }
-        else if (warp == 1 && lane < SX)
+        else if (warp == 1 && lane < SX && ! finer_hi_y)
         {
             double F[3];
-            if (JUMP && finer_hi_y) corrected_y(N, lane, F);
-            else strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
+            strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
             T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
         }
-        else if (JUMP && warp == 2 && lane < SX && finer_lo_y)
-        {
-            double F[3];
-            corrected_y(0, lane, F);
-            T.YLo[0][lane] = F[0]; T.YLo[1][lane] = F[1]; T.YLo[2][lane] = F[2];
-        }
         double FxLo[3], FyLo[3];
-        if (JUMP && finer_lo_x && warp == 0) corrected_x(0, FxLo);
-        else strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
+        strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
         strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FyLo);
 
         if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
         __syncthreads();
         if (JUMP && finer_lo_y && lane == 0) { FyLo[0] = T.YLo[0][li0]; FyLo[1] = T.YLo[1][li0]; FyLo[2] = T.YLo[2][li0]; }
+        if (JUMP && finer_lo_x && warp == 0) { FxLo[0] = T.XLo[0][lj]; FxLo[1] = T.XLo[1][lj]; FxLo[2] = T.XLo[2][lj]; }
 
         // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
         // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
