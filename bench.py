@@ -294,11 +294,12 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": ncu_traffic(wl_name, local_cells), "kernel": "stage_strip", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
                 "algorithmic_bytes_per_launch": fused_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH, "cells_per_launch": fused_cells, "per": "GPU (rank 0)", "peak_source": peak_how,
-                "step_frac_of_hbm_roofline": value * 1e6 * ALGORITHMIC_BYTES_PER_CELL_STEP / (peak * 1e9)}
+                "step_frac_of_hbm_roofline": value / world * 1e6 * ALGORITHMIC_BYTES_PER_CELL_STEP / (peak * 1e9)}
 
     # ---- end to end through the C ABI with host buffers (H2D + step + D2H inside the timed region)
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
+        # every rank moves the blocks it owns: host -> device, one full step, device -> host; wall clock between barriers
         shape = (solver.num_blocks, 3, solver.block_size, solver.block_size)
         u_in = torch.empty(shape, dtype=torch.float64).pin_memory()
         u_out = torch.empty(shape, dtype=torch.float64).pin_memory()
@@ -307,21 +308,29 @@ def main():
         n_e2e = max(3, min(args.steps, 20))
         for _ in range(2):
             solver.next_solution_host(u_in.numpy(), scalars, out=u_out.numpy())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             _, scalars_out, _, _ = solver.next_solution_host(u_in.numpy(), scalars, out=u_out.numpy())
             u_in, u_out = u_out, u_in
             scalars = scalars_out
-        dt_e2e = time.perf_counter() - t0
-        nbytes = int(np.prod(shape)) * 8 + 43 * 8
-        e2e = {"value": cells * n_e2e / dt_e2e * 1e-6, "unit": "Mzps", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "steps": n_e2e, "api": "m3b_next_solution_host (pinned host buffers)"}
+        torch.cuda.synchronize()
+        dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        nbytes = torch.tensor([int(np.prod(shape)) * 8 + 43 * 8], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
+        e2e = {"value": cells * n_e2e / float(dt_e2e) * 1e-6, "unit": "Mzps", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
+               "steps": n_e2e, "api": "m3b_next_solution_host (pinned host buffers; every rank moves the blocks it owns, bytes summed over ranks)"}
 
     exchange = None
     if world > 1:
         # NVLink side of the step: two guard-zone exchanges (one per RK stage) + one result all-gather
         exchange = {"halo_bytes_sent_per_exchange_rank0": solver.halo_bytes_per_exchange, "exchanges_per_step": 2,
-                    "transport": "NCCL send/recv, grouped per stage, on the compute stream"}
+                    "transport": {"peer": "peer memory over NVLink (CUDA IPC mailboxes): halo_push / halo_wait_unpack kernels, no NCCL call in the step loop",
+                                  "nccl": "NCCL send/recv, grouped per stage, on the compute stream"}.get(solver.exchange_transport, solver.exchange_transport)}
         dist.barrier()
         if rank != 0:
             dist.destroy_process_group()

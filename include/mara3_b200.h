@@ -89,6 +89,8 @@ void        m3b_neighbor_table(const m3b_solver_t* s, int* out);
  * the face-neighbour table the any-tree kernels read guard cells through (mesh_tree_operators.hpp:223-252) */
 void        m3b_face_neighbor_table(const m3b_solver_t* s, int* out);
 uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
+/* guard-zone transport in use: 0 none (one rank), 1 NCCL send / recv, 2 peer memory over NVLink (CUDA IPC mailboxes) */
+int         m3b_exchange_transport(const m3b_solver_t* s);
 /* ---- HDF5 products and the subprogram itself (no libhdf5 needed: mara3_b200/csrc/h5lite.cpp) ----
  * (with several ranks the writers are collective calls: every rank hands its blocks to rank 0, which writes the file)
  * m3b_write_checkpoint   replaces mara::write<state_t> into chkpt.NNNN.h5 (subprog_binary_io.cpp:131-158) for a solution

@@ -91,6 +91,8 @@ def load_library():
     L.m3b_time_series_sample.argtypes = [vp, vp, dp]
     L.m3b_binary_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
     L.m3b_binary_main_distributed.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.m3b_exchange_transport.argtypes = [vp]
+    L.m3b_exchange_transport.restype = C.c_int
     L.m3b_halo_bytes_per_exchange.argtypes = [vp]
     L.m3b_halo_bytes_per_exchange.restype = C.c_uint64
     L.m3b_solver_destroy.argtypes = [vp]
@@ -269,6 +271,7 @@ class Solver:
     num_regular_blocks = property(lambda s: _lib.m3b_num_regular_blocks(s._h))
     kernel_launches = property(lambda s: int(_lib.m3b_kernel_launches(s._h)))
 
+    exchange_transport = property(lambda s: ("none", "nccl", "peer")[int(_lib.m3b_exchange_transport(s._h))])
     halo_bytes_per_exchange = property(lambda s: int(_lib.m3b_halo_bytes_per_exchange(s._h)))
 
     @property

@@ -284,6 +284,7 @@ int m3b_h5_selftest(const char* write_path, const char* read_path, char* report,
     }
 }
 
+int m3b_exchange_transport(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().exchange_transport() : 0; }
 uint64_t m3b_halo_bytes_per_exchange(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().halo_bytes_per_exchange() : 0; }
 int m3b_block_size(const m3b_solver_t* s) { return s->solver->solver_data().block_size; }
 int64_t m3b_num_cells(const m3b_solver_t* s) { return int64_t(s->solver->solver_data().num_cells()); }

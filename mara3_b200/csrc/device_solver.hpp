@@ -117,6 +117,7 @@ namespace m3b
         /** One double from every rank, in rank order (blocking). */
         std::vector<double> all_gather_scalar(double value);
         std::uint64_t halo_bytes_per_exchange() const;
+        int exchange_transport() const;     // 0 none, 1 NCCL send / recv, 2 peer memory (CUDA IPC)
         unsigned int local_num_negative(int slot) const;
 
         void sync();

@@ -493,30 +493,44 @@ namespace
      * all that stage_strip<.., JUMP> reads from a neighbour (guard gradients are injected from / averaged over cells at
      * most two deep, and the fine faces of the flux correction touch the outermost layer).
      */
-    __global__ void __launch_bounds__(128) general_gradients_ring(
+    __global__ void __launch_bounds__(128, 8) general_gradients_ring(
         mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
         const double* __restrict__ Uin, double* __restrict__ G)
     {
+        // Region cell (r, a): r = 0..3 counts layers from the guard layer (r = 0) inwards, a = 0..N+1 runs along the side
+        // from the guard cell before its first cell to the one after its last; primitives go through shared memory once.
+        extern __shared__ double ring_P[];              // [3][4][N + 2]
         const stage_t S = *stage_ptr;
-        const int N = mesh.N, b = list[blockIdx.x >> 2], side = blockIdx.x & 3;
+        const int N = mesh.N, W = N + 2, b = list[blockIdx.x >> 2], side = blockIdx.x & 3;
+        const bool high = side & 1, along_x = side >= 2;        // along_x: the side runs along i (sides in y)
         const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
         const size_t base = size_t(mesh.gslot[b]) * N * N;
 
+        for (int k = threadIdx.x; k < 4 * W; k += 128)
+        {
+            const int r = k / W, a = k - r * W;
+            const int n = high ? N - r : r - 1, t = a - 1;
+            if (r == 0 && (t < 0 || t >= N)) continue;          // corners are not part of the stencil
+            const prim_t p = along_x ? prim_at(mesh, Uin, b, t, n) : prim_at(mesh, Uin, b, n, t);
+            ring_P[(0 * 4 + r) * W + a] = p.s; ring_P[(1 * 4 + r) * W + a] = p.vx; ring_P[(2 * 4 + r) * W + a] = p.vy;
+        }
+        __syncthreads();
         for (int k = threadIdx.x; k < 2 * N; k += 128)
         {
-            const int d = k / N, a = k - d * N;             // layer, position along the side
-            const int i = side == 0 ? d : (side == 1 ? N - 1 - d : a);
-            const int j = side == 2 ? d : (side == 3 ? N - 1 - d : a);
-            const prim_t c  = prim_at(mesh, Uin, b, i, j);
-            const prim_t xl = prim_at(mesh, Uin, b, i - 1, j), xr = prim_at(mesh, Uin, b, i + 1, j);
-            const prim_t yl = prim_at(mesh, Uin, b, i, j - 1), yr = prim_at(mesh, Uin, b, i, j + 1);
-            const size_t cell = base + size_t(i) * N + j;
-            G[0 * mesh.GS + cell] = plm_diff(xl.s,  c.s,  xr.s,  theta) * inv_h;
-            G[1 * mesh.GS + cell] = plm_diff(xl.vx, c.vx, xr.vx, theta) * inv_h;
-            G[2 * mesh.GS + cell] = plm_diff(xl.vy, c.vy, xr.vy, theta) * inv_h;
-            G[3 * mesh.GS + cell] = plm_diff(yl.s,  c.s,  yr.s,  theta) * inv_h;
-            G[4 * mesh.GS + cell] = plm_diff(yl.vx, c.vx, yr.vx, theta) * inv_h;
-            G[5 * mesh.GS + cell] = plm_diff(yl.vy, c.vy, yr.vy, theta) * inv_h;
+            const int d = k / N, t = k - d * N, r = d + 1, a = t + 1;
+            const int n = high ? N - r : r - 1;
+            const size_t cell = base + (along_x ? size_t(t) * N + n : size_t(n) * N + t);
+            #pragma unroll
+            for (int q = 0; q < 3; ++q)
+            {
+                const double* Pq = ring_P + size_t(q) * 4 * W;
+                const double c = Pq[r * W + a];
+                const double below = Pq[(high ? r + 1 : r - 1) * W + a], above = Pq[(high ? r - 1 : r + 1) * W + a];
+                const double gn = plm_diff(below, c, above, theta) * inv_h;                         // across the layers
+                const double gt = plm_diff(Pq[r * W + a - 1], c, Pq[r * W + a + 1], theta) * inv_h; // along the side
+                G[(along_x ? 3 + q : q) * mesh.GS + cell] = gn;
+                G[(along_x ? q : 3 + q) * mesh.GS + cell] = gt;
+            }
         }
     }
 
@@ -1487,7 +1501,7 @@ struct device_solver_t::impl_t
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
     cudaStream_t jump_stream = nullptr;     // stage_strip<.., JUMP> runs here, beside the regular blocks' launch
-    cudaEvent_t gradients_done = nullptr, jump_done = nullptr;
+    cudaEvent_t gradients_done = nullptr, jump_done = nullptr;   // fork (stage input ready on the compute stream) and join
     bool serial_jump = false;               // M3B_SERIAL_JUMP=1: the jump blocks' launch follows the regular blocks' on the compute stream
     bool jump_strip = false;                // blocks at jumps take stage_strip<.., JUMP> (M3B_JUMP_STRIP=0: the 16 x 16 any-tree kernels)
     std::vector<int> regular, irregular, gradient_blocks;
@@ -2230,14 +2244,20 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     bool jump_forked = false;
     if (jump_strip && num_general > 0 && ! exchange)
     {
-        general_gradients_ring<<<ng * 4, 128, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        ++launches;
-        if (num_fused > 0 && ! impl->serial_jump)
+        // fork: gradients and the jump blocks' update on the side stream, the regular blocks' update on the compute stream
+        const bool fork = num_fused > 0 && ! impl->serial_jump;
+        cudaStream_t js = fork ? impl->jump_stream : s;
+        if (fork)
         {
             M3B_CUDA(cudaEventRecord(impl->gradients_done, s));
-            M3B_CUDA(cudaStreamWaitEvent(impl->jump_stream, impl->gradients_done, 0));
-            launch_jump_strip(impl->jump_stream);
-            M3B_CUDA(cudaEventRecord(impl->jump_done, impl->jump_stream));
+            M3B_CUDA(cudaStreamWaitEvent(js, impl->gradients_done, 0));
+        }
+        general_gradients_ring<<<ng * 4, 128, size_t(12) * (N + 2) * sizeof(double), js>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+        ++launches;
+        if (fork)
+        {
+            launch_jump_strip(js);
+            M3B_CUDA(cudaEventRecord(impl->jump_done, js));
             jump_forked = true;
         }
     }
@@ -2270,7 +2290,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         if (exchange)       // (overlapped exchange: the guard zones have only just arrived)
         {
-            general_gradients_ring<<<ng * 4, 128, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
+            general_gradients_ring<<<ng * 4, 128, size_t(12) * (N + 2) * sizeof(double), s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
             ++launches;
         }
         launch_jump_strip(s);
@@ -2567,6 +2587,11 @@ void device_solver_t::set_communicator(communicator_t* comm)
     const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
     impl->in_kernel_wait = impl->strip && impl->irregular.empty() && impl->num_interior * tpb >= 2 * impl->sm_count * 4;
     if (const char* e = std::getenv("M3B_IN_KERNEL_WAIT")) impl->in_kernel_wait = impl->in_kernel_wait && std::atoi(e) != 0;
+}
+
+int device_solver_t::exchange_transport() const
+{
+    return num_ranks <= 1 ? 0 : (impl->peer_transport ? 2 : 1);
 }
 
 std::uint64_t device_solver_t::halo_bytes_per_exchange() const

@@ -53,7 +53,10 @@ STAGE_CASES = [
     (dict(depth=2, block_size=64, domain_radius=6.0), False),      # config 1 grid, warp-strip kernel (16x32 tiles)
     (dict(depth=2, block_size=64, domain_radius=6.0), "tiled"),    # same through the generic tiled kernel
     (dict(depth=2, block_size=64, domain_radius=6.0), True),       # same through the any-tree kernels
-    (dict(depth=5, block_size=32), False),                         # nested: strip kernel next to refinement jumps
+    (dict(depth=5, block_size=32), False),                         # nested: strip kernel, jump blocks through its JUMP variant
+    (dict(depth=4, block_size=64), False),                         # default nested tree in 64^2 blocks (the C4 block size)
+    (dict(depth=4, block_size=32, eccentricity=0.3, mass_ratio=0.5, nu=0.01, alpha_cutoff_radius=1.0,
+          density_floor=1e-2), False),                              # JUMP variant without the branch-free equation of state
     (dict(depth=4, block_size=24), False),                         # default nested tree, fused 12x24 + jumps
     (dict(depth=6, block_size=16), False),                         # five levels, fused 16x16 + jumps
     (dict(depth=5, block_size=8, focus_factor=3.0), False),        # fused 8x8 + jumps
@@ -93,7 +96,7 @@ def test_advance_matches_oracle(cfg, general_only):
 
 
 @pytest.mark.parametrize("seed", [1, 2])
-@pytest.mark.parametrize("cfg", [dict(depth=4, block_size=16), dict(depth=2, block_size=32, focus_factor=1e3)])
+@pytest.mark.parametrize("cfg", [dict(depth=4, block_size=16), dict(depth=2, block_size=32, focus_factor=1e3), dict(depth=4, block_size=32)])
 def test_advance_on_rough_seeded_states(cfg, seed):
     """Seeded multiplicative noise makes every limiter / wave-speed branch fire."""
     solver, u, o = make_pair(cfg)
@@ -113,6 +116,24 @@ def test_advance_on_rough_seeded_states(cfg, seed):
         assert status == 1
         g1 = e.solution
     assert block_rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
+
+
+def test_jump_strip_agrees_with_any_tree_kernels(monkeypatch):
+    """Blocks at refinement jumps: stage_strip<.., JUMP> against the 16 x 16 any-tree kernels it replaces
+    (M3B_JUMP_STRIP=0), two RK2 steps on a nested tree; both are within the oracle tolerance of each other."""
+    cfg = dict(depth=5, block_size=64)
+    new = m3.Solver(cfg)
+    monkeypatch.setenv("M3B_JUMP_STRIP", "0")
+    old = m3.Solver(cfg)
+    monkeypatch.delenv("M3B_JUMP_STRIP")
+    assert new.num_regular_blocks < new.num_blocks          # the tree has jumps
+    un, uo = new.create_solution(), old.create_solution()
+    for _ in range(2):
+        dn, _ = new.next_solution(un)
+        do, _ = old.next_solution(uo)
+        assert abs(dn - do) <= 1e-13 * do
+    assert block_rel_err(un.conserved_u, uo.conserved_u) <= 2 * CELL_TOL
+    assert_scalars(un.scalars, uo.scalars, 1e-10, un.time)
 
 
 @pytest.mark.parametrize("name", ["nested_d3_n8", "uniform_d2_n16", "live_ecc_d3_n8", "rk1_axisym_d3_n8",
