@@ -353,16 +353,27 @@ __device__ __forceinline__ void angmom_to_linear(double x, double y, double sr, 
     py = b;
 }
 
+/** The same with one fast reciprocal instead of two divisions (strip kernel). */
+__device__ __forceinline__ void angmom_to_linear_fast(double x, double y, double sr, double lz, double& px, double& py)
+{
+    const double inv = fast_rcp(fma(x, x, y * y));
+    const double a = (sr * x - lz * y) * inv, b = (sr * y + lz * x) * inv;
+    px = a;
+    py = b;
+}
+
 /**
  * source_terms_q (scheme.cpp:417-466) for one cell of the angular-momentum-conserving variable set: gravity and sinks
  * in (Sr, Lz) form, buffer towards the initial conserved_q, and the geometric term 2 (E_kin + p) of the radial
  * momentum with its ramp.  The running sums keep the meaning they have for source_terms_u (momentum accreted is the
  * sink term converted back to linear momentum, :446-447), so the host bookkeeping is shared; no work integral.
  */
+template<bool WARP_SINKS = false>
 __device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& S, double x, double y,
     double s, double sr, double lz, double vx, double vy, double q0s, double q0r, double q0l, double br,
-    double src[3], double sums[NUM_SUMS], double& y1, double& y2)
+    double src[3], double sums[NUM_SUMS], double& y1, double& y2, double* warp_sinks = nullptr)
 {
+    // WARP_SINKS: as in source_terms -- called by all 32 lanes of a converged warp, sink sums per warp in shared memory
     double dx1 = x - S.x1, dy1 = y - S.y1, dx2 = x - S.x2, dy2 = y - S.y2;
     double r1 = fma(dx1, dx1, dy1 * dy1);
     double r2 = fma(dx2, dx2, dy2 * dy2);
@@ -381,16 +392,35 @@ __device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& 
     double a2 = tq1 * S.dt + tq2 * S.dt;
 
     double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
-    if (e1 < 100.0 || e2 < 100.0)
+    const bool near_sink = e1 < 100.0 || e2 < 100.0;
+    if (WARP_SINKS ? __any_sync(0xffffffffu, near_sink) : near_sink)
     {
         double w1 = sink_weight(M.sink_rate, e1);
         double w2 = sink_weight(M.sink_rate, e2);
         double px, py;
         angmom_to_linear(x, y, sr, lz, px, py);
-        sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
-        sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
-        sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
-        sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        if (WARP_SINKS)
+        {
+            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+            #pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+            }
+        }
+        else
+        {
+            sums[ACC_MASS + 0] += s * w1;   sums[ACC_MASS + 1] += s * w2;
+            sums[ACC_PX + 0]   += px * w1;  sums[ACC_PX + 1]   += px * w2;
+            sums[ACC_PY + 0]   += py * w1;  sums[ACC_PY + 1]   += py * w2;
+            sums[ACC_LZ + 0]   += lz * w1;  sums[ACC_LZ + 1]   += lz * w2;
+        }
         double w = -(w1 + w2) * S.dt;
         a0 = fma(s, w, a0);  a1 = fma(sr, w, a1);  a2 = fma(lz, w, a2);
     }
@@ -404,7 +434,9 @@ __device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& 
     // source_terms_conserved_angmom (physics_iso2d.hpp:277-285): (0, 2 (E_kin + p), 0), ramped up away from the origin
     {
         double cs2 = M.axisymmetric_cs2 ? fast_rsqrt(fma(x, x, y * y)) * M.inv_mach2 : fma(S.m1, y1, S.m2 * y2) * M.inv_mach2;
-        double ramp = 1.0 - exp(-(x * x + y * y) / M.gst_suppr_radius2);
+        // (beyond a = 40 the exponential is below half an ulp of 1: the ramp is exactly 1)
+        const double a = (x * x + y * y) / M.gst_suppr_radius2;
+        double ramp = a > 40.0 ? 1.0 : 1.0 - exp(-a);
         double ek = 0.5 * s * (vx * vx + vy * vy);
         a1 += (ek + s * cs2) * 2.0 * ramp * S.dt;
     }

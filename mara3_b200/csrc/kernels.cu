@@ -1908,6 +1908,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         set_smem(stage_strip<4, 64, true, 0>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 1>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 2>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, false, 0, false, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, true, 0, false, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, false, 0, false, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 0, false, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, false, 0, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, true, 0, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, false, 0, true>, sizeof(strip_smem_t));
@@ -2200,6 +2204,9 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
                                   : (impl->fast_eos ? stage_strip<4, 0, true, 0> : stage_strip<4, 0, false, 0>);
             if (N == 64 && impl->fast_eos && stage_mode == 1) kernel = stage_strip<4, 64, true, 1>;
             if (N == 64 && impl->fast_eos && stage_mode == 2) kernel = stage_strip<4, 64, true, 2>;
+            if (impl->mesh.qmode)       // conserved_q = (sigma, Sr, Lz): advance_q (scheme.cpp:906-1020) through the same kernel
+                kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, false, true> : stage_strip<4, 64, false, 0, false, true>)
+                                 : (impl->fast_eos ? stage_strip<4, 0, true, 0, false, true> : stage_strip<4, 0, false, 0, false, true>);
             mesh_dev_t mesh = impl->mesh;
             mesh.first_wait_cta = waiting_tiles ? std::max(0, impl->num_interior - first) * tpb : 0x7fffffff;
             mesh.ready_flag = impl->d_ready;

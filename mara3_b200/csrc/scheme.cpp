@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "scheme.hpp"
 #include <algorithm>
 #include <cmath>
@@ -65,7 +66,10 @@ binary_solver_t::binary_solver_t(const config_t& run_config, int device, bool ge
     if (device >= 0)
     {
         // conserve_linear_p = 0 (advance_q, scheme.cpp:906-1020): the state is conserved_q and every block takes the any-tree kernels
-        gpu = std::make_unique<device_solver_t>(data, device, general_only || ! data.conserve_linear_p, tiled_kernel);
+        // (regular blocks whose size is a multiple of 32 take the strip kernel's QMODE variant; M3B_Q_STRIP=0: any-tree kernels only)
+        const char* qs = std::getenv("M3B_Q_STRIP");
+        const bool q_strip = data.block_size % 32 == 0 && ! tiled_kernel && ! (qs && std::atoi(qs) == 0);
+        gpu = std::make_unique<device_solver_t>(data, device, general_only || (! data.conserve_linear_p && ! q_strip), tiled_kernel);
         if (nranks > 1)
         {
             if (! nccl_unique_id) throw std::invalid_argument("a multi-rank solver needs the NCCL unique id of the job");

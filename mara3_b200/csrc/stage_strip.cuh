@@ -67,24 +67,28 @@ namespace
         return eos_from_distances<FAST>(model, S, T.x2c[0][li] + T.y2v[0][lj], T.x2c[1][li] + T.y2v[1][lj], T.x2c[2][li] + T.y2v[2][lj]);
     }
 
-    /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX */
-    __device__ __forceinline__ void strip_x_face(const strip_smem_t& T, const eos_t& e, double inv_h, int li, int lj, double F[3])
+    /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX.  QMODE: flux of (sigma, Sr, Lz), to_angmom_fluxes (scheme.cpp:199-214). */
+    template<bool QMODE = false>
+    __device__ __forceinline__ void strip_x_face(const strip_smem_t& T, const eos_t& e, double inv_h, int li, int lj, double F[3], const model_t* model = nullptr)
     {
         prim_t pl = {T.P[0][li + 1][lj + 2], T.P[1][li + 1][lj + 2], T.P[2][li + 1][lj + 2]};
         prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
         prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]};
         prim_t gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
         face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5, inv_h, F);
+        if (QMODE) to_angmom_fluxes<0>(*model, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]), F);
     }
 
     /** y-face between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= SY */
-    __device__ __forceinline__ void strip_y_face(const strip_smem_t& T, const eos_t& e, double inv_h, int li, int lj, double F[3])
+    template<bool QMODE = false>
+    __device__ __forceinline__ void strip_y_face(const strip_smem_t& T, const eos_t& e, double inv_h, int li, int lj, double F[3], const model_t* model = nullptr)
     {
         prim_t pl = {T.P[0][li + 2][lj + 1], T.P[1][li + 2][lj + 1], T.P[2][li + 2][lj + 1]};
         prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
         prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]};
         prim_t gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
         face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
+        if (QMODE) to_angmom_fluxes<1>(*model, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj], F);
     }
 
     /**
@@ -152,7 +156,7 @@ namespace
         F[0] = acc[0] * inv_h; F[1] = acc[1] * inv_h; F[2] = acc[2] * inv_h;
     }
 
-    template<int MIN_CTAS, int NB, bool FAST, int MODE, bool JUMP = false>
+    template<int MIN_CTAS, int NB, bool FAST, int MODE, bool JUMP = false, bool QMODE = false>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_strip(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
@@ -263,6 +267,7 @@ namespace
             const double* __restrict__ U1 = Uin + FS;
             const double* __restrict__ U2 = Uin + 2 * FS;
             double2 uc[3][3];
+            double qx[3], qy0[3], qy1[3];           // QMODE: centre coordinates of the chunk's two cells in THEIR block
             bool inside[3] = {true, true, true};    // JUMP: chunks beyond a block side are not loaded here (guard ring below)
 
             #pragma unroll
@@ -281,6 +286,13 @@ namespace
                         uc[k][0] = *reinterpret_cast<const double2*>(Uin + c);
                         uc[k][1] = *reinterpret_cast<const double2*>(U1 + c);
                         uc[k][2] = *reinterpret_cast<const double2*>(U2 + c);
+                    }
+                    if (QMODE)
+                    {
+                        const double* xn = mesh.xv + size_t(nb) * (N + 1) + (gi - di * N);
+                        const double* yn = mesh.yv + size_t(nb) * (N + 1) + col;
+                        const double ymid = yn[1];
+                        qx[k] = 0.5 * (xn[0] + xn[1]); qy0[k] = 0.5 * (yn[0] + ymid); qy1[k] = 0.5 * (ymid + yn[2]);
                     }
                 }
             }
@@ -385,8 +397,15 @@ namespace
                     // iso2d::recover_primitive (physics_iso2d.hpp:351-362) for the chunk's two cells
                     const double ia = fast_rcp(uc[k][0].x), ib = fast_rcp(uc[k][0].y);
                     *reinterpret_cast<double2*>(&T.P[0][row][2 * cc]) = uc[k][0];
-                    *reinterpret_cast<double2*>(&T.P[1][row][2 * cc]) = make_double2(uc[k][1].x * ia, uc[k][1].y * ib);
-                    *reinterpret_cast<double2*>(&T.P[2][row][2 * cc]) = make_double2(uc[k][2].x * ia, uc[k][2].y * ib);
+                    double2 v1 = make_double2(uc[k][1].x * ia, uc[k][1].y * ib), v2 = make_double2(uc[k][2].x * ia, uc[k][2].y * ib);
+                    if (QMODE)
+                    {
+                        // recover_primitive(Q, x) (physics_iso2d.hpp:376-389): velocity from (Sr, Lz) / sigma at the cell's own position
+                        angmom_to_linear_fast(qx[k], qy0[k], v1.x, v2.x, v1.x, v2.x);
+                        angmom_to_linear_fast(qx[k], qy1[k], v1.y, v2.y, v1.y, v2.y);
+                    }
+                    *reinterpret_cast<double2*>(&T.P[1][row][2 * cc]) = v1;
+                    *reinterpret_cast<double2*>(&T.P[2][row][2 * cc]) = v2;
                 }
             }
         }
@@ -473,7 +492,8 @@ namespace
             }
             const double x = 0.5 * (T.xv[li] + T.xv[li + 1]);
             double src[3], y1, y2;
-            source_terms<FAST, true>(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2, T.sinks[warp]);
+            if (QMODE) source_terms_q<true>(model, S, x, yc, u[0], u[1], u[2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2], u0[0], u0[1], u0[2], br, src, sums, y1, y2, T.sinks[warp]);
+            else source_terms<FAST, true>(model, S, x, yc, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, src, sums, y1, y2, T.sinks[warp]);
 
             double n0 = u[0] - ((FxHi[0] - FxLo[0]) + (hy[0] - FyLo[0])) * dt_over_h + src[0];
             double n1 = u[1] - ((FxHi[1] - FxLo[1]) + (hy[1] - FyLo[1])) * dt_over_h + src[1];
@@ -490,7 +510,12 @@ namespace
             }
             Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
 
-            if (compute_dt) amax = dmax(amax, max_wavespeed<FAST>(model, S, x, yc, y1, y2, n0, n1, n2));
+            if (compute_dt)
+            {
+                double mx = n1, my = n2;
+                if (QMODE) angmom_to_linear_fast(x, yc, n1, n2, mx, my);
+                amax = dmax(amax, max_wavespeed<FAST>(model, S, x, yc, y1, y2, n0, mx, my));
+            }
         };
         auto load_cell = [&] (int r, double* u, double* u0, double& br, double* un)
         {
@@ -534,18 +559,18 @@ namespace
         if (warp == 0 && ! finer_hi_x)
         {
             double F[3];
-            strip_x_face(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F);
+            strip_x_face<QMODE>(T, strip_x_eos<FAST>(T, model, S, SX, lj), inv_h, SX, lj, F, &model);
             T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
         }
         else if (warp == 1 && lane < SX && ! finer_hi_y)
         {
             double F[3];
-            strip_y_face(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F);
+            strip_y_face<QMODE>(T, strip_y_eos<FAST>(T, model, S, lane, SY), inv_h, lane, SY, F, &model);
             T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
         }
         double FxLo[3], FyLo[3];
-        strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo);
-        strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FyLo);
+        strip_x_face<QMODE>(T, strip_x_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FxLo, &model);
+        strip_y_face<QMODE>(T, strip_y_eos<FAST>(T, model, S, li0, lj), inv_h, li0, lj, FyLo, &model);
 
         if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
         __syncthreads();
@@ -558,8 +583,8 @@ namespace
         for (int r = 1; r < STRIP; ++r)
         {
             double FxNew[3], FyNew[3];
-            strip_x_face(T, strip_x_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew);
-            strip_y_face(T, strip_y_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew);
+            strip_x_face<QMODE>(T, strip_x_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FxNew, &model);
+            strip_y_face<QMODE>(T, strip_y_eos<FAST>(T, model, S, li0 + r, lj), inv_h, li0 + r, lj, FyNew, &model);
             if (JUMP && finer_lo_y && lane == 0) { FyNew[0] = T.YLo[0][li0 + r]; FyNew[1] = T.YLo[1][li0 + r]; FyNew[2] = T.YLo[2][li0 + r]; }
             update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
             load_cell(r, u, u0, br, un);

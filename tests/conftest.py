@@ -29,6 +29,18 @@ def block_rel_err(a, b):
     return float((np.abs(a - b) / scale).max())
 
 
+def block_rel_err_q(a, b):
+    """The same norm for conserved_q = (sigma, Sr, Lz) (conserve_linear_p=0): Sr = x.p is a difference of two O(r |p|)
+    terms that nearly cancel in a Keplerian disk (it can be 1e-3 of them over a whole block), so Sr and Lz = x cross p
+    are both measured against their common scale r |p| = hypot(Sr, Lz), maximised over the block."""
+    scale = np.abs(b).max(axis=(-2, -1), keepdims=True)
+    rp = np.hypot(b[:, 1], b[:, 2]).max(axis=(-2, -1))
+    scale[:, 1, 0, 0] = rp
+    scale[:, 2, 0, 0] = rp
+    scale = np.where(scale > 0, scale, 1.0)
+    return float((np.abs(a - b) / scale).max())
+
+
 @pytest.fixture(scope="session")
 def golden():
     return load_golden

@@ -8,7 +8,7 @@ covered on the CPU in test_host_layer.py."""
 import numpy as np
 import pytest
 import mara3_b200 as m3
-from conftest import load_golden, block_rel_err
+from conftest import load_golden, block_rel_err, block_rel_err_q
 from oracle_util import OracleMesh, OracleSolution, SCALAR_NAMES
 
 pytestmark = pytest.mark.gpu
@@ -69,7 +69,11 @@ STAGE_CASES = [
     # angular-momentum-conserving variables (advance_q, conserve_linear_p=0): state = conserved_q, any-tree kernels
     (dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1), False),                     # nested, 16x16 tiles
     (dict(depth=3, block_size=8, conserve_linear_p=0, fixed_dt=1), False),                      # nested, one CTA per block
-    (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), False),
+    (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), False),    # strip kernel, QMODE
+    (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), True),     # same through the any-tree kernels
+    (dict(depth=4, block_size=32, conserve_linear_p=0, fixed_dt=1), False),                     # nested: strip QMODE + any-tree at the jumps
+    (dict(depth=2, block_size=64, conserve_linear_p=0, fixed_dt=1, eccentricity=0.2, mass_ratio=0.5, nu=0.01,
+          begin_live_binary=0.0, focus_factor=1e3), False),                                      # strip QMODE, 64^2 blocks, general equation of state
     (dict(depth=2, block_size=16, domain_radius=6.0, conserve_linear_p=0, fixed_dt=1, rk_order=1, eccentricity=0.2,
           mass_ratio=0.5, begin_live_binary=0.0, nu=0.01), False),
 ]
@@ -86,13 +90,15 @@ def test_advance_matches_oracle(cfg, general_only):
     o1, status = o.advance(dt_o)
     assert status == 0
     g1 = solver.advance(u, dt_o)
-    assert block_rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
+    # (conserved_q: Sr nearly cancels in a Keplerian disk and is measured against r |p|, see block_rel_err_q)
+    rel_err = block_rel_err if cfg.get("conserve_linear_p", 1) else block_rel_err_q
+    assert rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
     assert_scalars(g1.scalars, o1.scalars, 1e-11, dt_o)
     assert np.array_equal(u.conserved_u, o.conserved_u)             # the input solution is untouched (value semantics)
     # safe mode: theta = 0 (piecewise constant)
     o2, _ = o1.advance(0.1 * dt_o, safe_mode=True)
     g2 = solver.advance(g1, 0.1 * dt_o, safe_mode=True)
-    assert block_rel_err(g2.conserved_u, o2.conserved_u) <= CELL_TOL
+    assert rel_err(g2.conserved_u, o2.conserved_u) <= CELL_TOL
 
 
 @pytest.mark.parametrize("seed", [1, 2])

@@ -38,7 +38,8 @@ def main():
              (dict(depth=4, block_size=64, focus_factor=1e3), 5, False),
              (dict(depth=4, block_size=32), 6, True),              # nested tree: refinement jumps across the rank boundary
              (dict(depth=6, block_size=64), 4, False),             # config-4-like nesting (136 leaves, levels 2-6)
-             (dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1), 4, True)]   # advance_q: whole-block ghosts everywhere
+             (dict(depth=3, block_size=16, conserve_linear_p=0, fixed_dt=1), 4, True),   # advance_q: whole-block ghosts everywhere
+             (dict(depth=4, block_size=32, conserve_linear_p=0, fixed_dt=1), 3, False)]  # advance_q: strip kernel (QMODE) + any-tree at the jumps
     if os.environ.get("MGC_QUICK"):
         cases = [(dict(depth=3, block_size=32, focus_factor=1e3, domain_radius=6.0), 6, False), (dict(depth=6, block_size=64), 3, False)]
     for cfg, steps, with_oracle in cases:
