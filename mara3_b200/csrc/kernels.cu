@@ -1736,7 +1736,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
             }
         impl->d_tile_info = device_upload(info);
     }
-    impl->jump_strip = N % 32 == 0 && ! tiled_kernel && sd.conserve_linear_p;
+    // (conserved_q with general_only keeps the any-tree kernels: the reference implementation of that variable set on the device)
+    impl->jump_strip = N % 32 == 0 && ! tiled_kernel && (sd.conserve_linear_p || ! general_only);
     if (const char* e = std::getenv("M3B_JUMP_STRIP")) impl->jump_strip = impl->jump_strip && std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_SERIAL_JUMP")) impl->serial_jump = std::atoi(e) != 0;
     if (impl->jump_strip)
@@ -1912,6 +1913,10 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         set_smem(stage_strip<4, 0, true, 0, false, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, false, 0, false, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 0, false, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, false, 0, true, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 0, true, 0, true, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, false, 0, true, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 0, true, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, false, 0, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, true, 0, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, false, 0, true>, sizeof(strip_smem_t));
@@ -2240,6 +2245,9 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true> : stage_strip<4, 64, false, 0, true>)
                               : (impl->fast_eos ? stage_strip<4, 0, true, 0, true> : stage_strip<4, 0, false, 0, true>);
+        if (impl->mesh.qmode)
+            kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true, true> : stage_strip<4, 64, false, 0, true, true>)
+                             : (impl->fast_eos ? stage_strip<4, 0, true, 0, true, true> : stage_strip<4, 0, false, 0, true, true>);
         mesh_dev_t mesh = impl->mesh;
         mesh.first_wait_cta = 0x7fffffff;
         kernel<<<num_general * tpb, STRIP_THREADS, sizeof(strip_smem_t), js>>>(mesh, impl->model, st, impl->d_jump_tile_info,

@@ -98,7 +98,7 @@ namespace
      * blocks' guard cell there is this block's cell by injection (mesh_prolong_restrict.hpp:161-196), primitives and
      * gradients alike, so that side comes from shared memory; the fine cells and their gradients are read directly.
      */
-    template<int AXIS>
+    template<int AXIS, bool QMODE>
     __device__ __forceinline__ void jump_corrected_face(const strip_smem_t& T, const mesh_dev_t& mesh, const model_t& model, const stage_t& S,
         const double* __restrict__ Uin, const double* __restrict__ Gphys, int b, int side, int t, int i0, int j0, int N, double h, double inv_h, double F[3])
     {
@@ -135,6 +135,8 @@ namespace
             va[m] = AXIS == 0 ? yvf[kf + m] : xvf[kf + m];
             vb[m] = AXIS == 0 ? yvf[kf + m + 1] : xvf[kf + m + 1];
         }
+        // QMODE: the fine cells' centre coordinate along AXIS (their velocity is recovered at their own position)
+        const double fc = QMODE ? 0.5 * ((AXIS == 0 ? xvf[ff] : yvf[ff]) + (AXIS == 0 ? xvf[ff + 1] : yvf[ff + 1])) : 0.0;
         const prim_t pc = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
         const prim_t gc = {T.G[3 * AXIS][li + 1][lj + 1] * inv_h, T.G[3 * AXIS + 1][li + 1][lj + 1] * inv_h, T.G[3 * AXIS + 2][li + 1][lj + 1] * inv_h};
         const double hcx = T.G[3 * (1 - AXIS) + 1][li + 1][lj + 1] * inv_h, hcy = T.G[3 * (1 - AXIS) + 2][li + 1][lj + 1] * inv_h;
@@ -143,13 +145,15 @@ namespace
         #pragma unroll
         for (int m = 0; m < 2; ++m)
         {
-            const prim_t pf = cons_to_prim(u[m][0], u[m][1], u[m][2]);
+            prim_t pf = cons_to_prim(u[m][0], u[m][1], u[m][2]);
             const prim_t gf = {g[m][0], g[m][1], g[m][2]};
             const double mid = 0.5 * (va[m] + vb[m]), len = vb[m] - va[m];
+            if (QMODE) angmom_to_linear_fast(AXIS == 0 ? fc : mid, AXIS == 0 ? mid : fc, pf.vx, pf.vy, pf.vx, pf.vy);
             const eos_t e = eos_at_face(model, S, AXIS == 0 ? fixed : mid, AXIS == 0 ? mid : fixed);
             double Fm[3];
             if (lo) face_flux<AXIS>(e, pf, pc, gf, gc, g[m][3], g[m][4], hcx, hcy, 0.25 * h, 1.0, Fm);
             else    face_flux<AXIS>(e, pc, pf, gc, gf, hcx, hcy, g[m][3], g[m][4], 0.25 * h, 1.0, Fm);
+            if (QMODE) to_angmom_fluxes<AXIS>(model, AXIS == 0 ? fixed : mid, AXIS == 0 ? mid : fixed, Fm);
             if (m == 0) { acc[0] = Fm[0] * len; acc[1] = Fm[1] * len; acc[2] = Fm[2] * len; }
             else        { acc[0] += Fm[0] * len; acc[1] += Fm[1] * len; acc[2] += Fm[2] * len; }
         }
@@ -315,6 +319,12 @@ namespace
                     #pragma unroll
                     for (int q = 0; q < 6; ++q) ring_grad[q] = Gphys[q * GS + gc] * hb;
                     p = cons_to_prim(u0, u1, u2);
+                    if (QMODE)
+                    {
+                        const double* xn = mesh.xv + size_t(rnA.y) * (N + 1) + ci;
+                        const double* yn = mesh.yv + size_t(rnA.y) * (N + 1) + cj;
+                        angmom_to_linear_fast(0.5 * (xn[0] + xn[1]), 0.5 * (yn[0] + yn[1]), p.vx, p.vy, p.vx, p.vy);
+                    }
                 }
                 else
                 {
@@ -339,8 +349,19 @@ namespace
                         const double2 gd = *reinterpret_cast<const double2*>(Gphys + q * GS + gc + N);
                         ring_grad[q] = (((ga.x + gd.x) * 0.5 + (ga.y + gd.y) * 0.5) * 0.5) * hb;
                     }
-                    const prim_t p00 = cons_to_prim(a[0].x, a[1].x, a[2].x), p01 = cons_to_prim(a[0].y, a[1].y, a[2].y);
-                    const prim_t p10 = cons_to_prim(d[0].x, d[1].x, d[2].x), p11 = cons_to_prim(d[0].y, d[1].y, d[2].y);
+                    prim_t p00 = cons_to_prim(a[0].x, a[1].x, a[2].x), p01 = cons_to_prim(a[0].y, a[1].y, a[2].y);
+                    prim_t p10 = cons_to_prim(d[0].x, d[1].x, d[2].x), p11 = cons_to_prim(d[0].y, d[1].y, d[2].y);
+                    if (QMODE)
+                    {
+                        const double* xn = mesh.xv + size_t(leaf) * (N + 1) + (fi % N);
+                        const double* yn = mesh.yv + size_t(leaf) * (N + 1) + (fj % N);
+                        const double xm = xn[1], ym = yn[1];
+                        const double x0 = 0.5 * (xn[0] + xm), x1 = 0.5 * (xm + xn[2]), y0 = 0.5 * (yn[0] + ym), y1 = 0.5 * (ym + yn[2]);
+                        angmom_to_linear_fast(x0, y0, p00.vx, p00.vy, p00.vx, p00.vy);
+                        angmom_to_linear_fast(x0, y1, p01.vx, p01.vy, p01.vx, p01.vy);
+                        angmom_to_linear_fast(x1, y0, p10.vx, p10.vy, p10.vx, p10.vy);
+                        angmom_to_linear_fast(x1, y1, p11.vx, p11.vy, p11.vx, p11.vy);
+                    }
                     p = {((p00.s + p10.s) * 0.5 + (p01.s + p11.s) * 0.5) * 0.5,
                          ((p00.vx + p10.vx) * 0.5 + (p01.vx + p11.vx) * 0.5) * 0.5,
                          ((p00.vy + p10.vy) * 0.5 + (p01.vy + p11.vy) * 0.5) * 0.5};
@@ -543,14 +564,14 @@ namespace
                 double F[3];
                 if (side < 2)
                 {
-                    jump_corrected_face<0>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
+                    jump_corrected_face<0, QMODE>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
                     double (*dst)[SY] = side == 1 ? T.XB[0] + 4 : T.XLo;     // row 4 of XB[q], or XLo[q], q-stride below
                     const int qs = side == 1 ? 5 : 1;
                     dst[0][lane] = F[0]; dst[qs][lane] = F[1]; dst[2 * qs][lane] = F[2];
                 }
                 else if (lane < SX)
                 {
-                    jump_corrected_face<1>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
+                    jump_corrected_face<1, QMODE>(T, mesh, model, S, Uin, Gphys, b, side, lane, i0, j0, N, h, inv_h, F);
                     double (*dst)[SX] = side == 3 ? T.YB : T.YLo;
                     dst[0][lane] = F[0]; dst[1][lane] = F[1]; dst[2][lane] = F[2];
                 }

@@ -71,7 +71,9 @@ STAGE_CASES = [
     (dict(depth=3, block_size=8, conserve_linear_p=0, fixed_dt=1), False),                      # nested, one CTA per block
     (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), False),    # strip kernel, QMODE
     (dict(depth=2, block_size=32, conserve_linear_p=0, fixed_dt=1, domain_radius=6.0, focus_factor=1e3), True),     # same through the any-tree kernels
-    (dict(depth=4, block_size=32, conserve_linear_p=0, fixed_dt=1), False),                     # nested: strip QMODE + any-tree at the jumps
+    (dict(depth=4, block_size=32, conserve_linear_p=0, fixed_dt=1), False),                     # nested: strip QMODE, JUMP + QMODE at the jumps
+    (dict(depth=4, block_size=32, conserve_linear_p=0, fixed_dt=1), True),                      # same through the any-tree kernels
+    (dict(depth=4, block_size=64, conserve_linear_p=0, fixed_dt=1, axisymmetric_cs2=1), False), # 64^2 blocks, JUMP + QMODE without the fast equation of state
     (dict(depth=2, block_size=64, conserve_linear_p=0, fixed_dt=1, eccentricity=0.2, mass_ratio=0.5, nu=0.01,
           begin_live_binary=0.0, focus_factor=1e3), False),                                      # strip QMODE, 64^2 blocks, general equation of state
     (dict(depth=2, block_size=16, domain_radius=6.0, conserve_linear_p=0, fixed_dt=1, rk_order=1, eccentricity=0.2,
