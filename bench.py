@@ -289,10 +289,13 @@ def main():
     peak, peak_how = measured_hbm_peak()
     kernel_ms = stage_ms / max(1, stage_launches)
     local_cells = solver.num_owned_cells
-    fused_cells = solver.num_regular_blocks * solver.block_size ** 2     # what the timed (fused) stage kernel updates on this rank
+    # what the timed stage kernels update on this rank: every owned cell (on a nested tree the timed region spans the regular
+    # blocks' launch, the jump blocks' launch beside it and the ring gradients they read)
+    fused_cells = local_cells
+    nested = solver.num_regular_blocks < solver.num_blocks
     achieved = fused_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH / (kernel_ms * 1e-3) * 1e-9 if stage_launches else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": ncu_traffic(wl_name, local_cells), "kernel": "stage_strip", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
+                "traffic": ncu_traffic(wl_name, local_cells), "kernel": "stage_strip + stage_strip<JUMP> + general_gradients_ring (one RK stage)" if nested else "stage_strip", "kernel_ms": kernel_ms, "launches_timed": stage_launches,
                 "algorithmic_bytes_per_launch": fused_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH, "cells_per_launch": fused_cells, "per": "GPU (rank 0)", "peak_source": peak_how,
                 "step_frac_of_hbm_roofline": value / world * 1e6 * ALGORITHMIC_BYTES_PER_CELL_STEP / (peak * 1e9)}
 

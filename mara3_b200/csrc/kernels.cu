@@ -2229,7 +2229,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     };
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (stage_timing && fused_ctas > 0)
+    if (stage_timing && (fused_ctas > 0 || num_general > 0))
     {
         // events come from a pool: creating them here would delay the launches behind this one
         if (impl->event_pool.size() < 2)
@@ -2256,12 +2256,13 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         M3B_CUDA(cudaGetLastError());
     };
     const int ng = int(impl->gradient_blocks.size());
-    bool jump_forked = false;
+    bool jump_forked = false, e0_recorded = false;
     if (jump_strip && num_general > 0 && ! exchange)
     {
         // fork: gradients and the jump blocks' update on the side stream, the regular blocks' update on the compute stream
         const bool fork = num_fused > 0 && ! impl->serial_jump;
         cudaStream_t js = fork ? impl->jump_stream : s;
+        if (e0) { M3B_CUDA(cudaEventRecord(e0, s)); e0_recorded = true; }      // the timed region covers the jump blocks' kernels
         if (fork)
         {
             M3B_CUDA(cudaEventRecord(impl->gradients_done, s));
@@ -2284,7 +2285,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         M3B_CUDA(cudaStreamWaitEvent(impl->comm_stream, impl->input_ready, 0));
         exchange_on(impl->comm_stream, field);
         M3B_CUDA(cudaEventRecord(impl->halo_ready, impl->comm_stream));
-        if (e0) M3B_CUDA(cudaEventRecord(e0, s));
+        if (e0 && ! e0_recorded) M3B_CUDA(cudaEventRecord(e0, s));
         launch_fused(0, impl->num_interior);
         M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));
         launch_fused(impl->num_interior, num_fused - impl->num_interior);
@@ -2292,13 +2293,8 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     }
     else
     {
-        if (e0) M3B_CUDA(cudaEventRecord(e0, s));
+        if (e0 && ! e0_recorded) M3B_CUDA(cudaEventRecord(e0, s));
         launch_fused(0, num_fused);
-    }
-    if (e0)
-    {
-        M3B_CUDA(cudaEventRecord(e1, s));
-        impl->timing_events.emplace_back(e0, e1);
     }
     if (jump_forked) M3B_CUDA(cudaStreamWaitEvent(s, impl->jump_done, 0));
     else if (num_general > 0 && jump_strip)
@@ -2323,6 +2319,11 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
                 in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
         launches += 2;
         M3B_CUDA(cudaGetLastError());
+    }
+    if (e0)         // after the join: regular blocks, jump blocks and their gradients
+    {
+        M3B_CUDA(cudaEventRecord(e1, s));
+        impl->timing_events.emplace_back(e0, e1);
     }
     if (waiting_tiles) M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));     // join the exchange stream
     impl->mark(s, "stage kernels done");
