@@ -1502,6 +1502,7 @@ struct device_solver_t::impl_t
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
     cudaStream_t jump_stream = nullptr;     // stage_strip<.., JUMP> runs here, beside the regular blocks' launch
     cudaEvent_t gradients_done = nullptr, jump_done = nullptr;   // fork (stage input ready on the compute stream) and join
+    bool jump_mode0 = false;                // M3B_JUMP_MODE0=1: run-time stage flags in the JUMP variant (experiment)
     bool serial_jump = false;               // M3B_SERIAL_JUMP=1: the jump blocks' launch follows the regular blocks' on the compute stream
     bool jump_strip = false;                // blocks at jumps take stage_strip<.., JUMP> (M3B_JUMP_STRIP=0: the 16 x 16 any-tree kernels)
     std::vector<int> regular, irregular, gradient_blocks;
@@ -1740,6 +1741,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     impl->jump_strip = N % 32 == 0 && ! tiled_kernel && (sd.conserve_linear_p || ! general_only);
     if (const char* e = std::getenv("M3B_JUMP_STRIP")) impl->jump_strip = impl->jump_strip && std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_SERIAL_JUMP")) impl->serial_jump = std::atoi(e) != 0;
+    if (const char* e = std::getenv("M3B_JUMP_MODE0")) impl->jump_mode0 = std::atoi(e) != 0;
     if (impl->jump_strip)
     {
         // the any-tree list (blocks at refinement jumps, or every owned block with general_only) in 16 x 32 strip tiles
@@ -1913,6 +1915,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         set_smem(stage_strip<4, 0, true, 0, false, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, false, 0, false, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 0, false, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 1, true>, sizeof(strip_smem_t));
+        set_smem(stage_strip<4, 64, true, 2, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, false, 0, true, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 0, true, 0, true, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, false, 0, true, true>, sizeof(strip_smem_t));
@@ -2245,6 +2249,8 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true> : stage_strip<4, 64, false, 0, true>)
                               : (impl->fast_eos ? stage_strip<4, 0, true, 0, true> : stage_strip<4, 0, false, 0, true>);
+        if (N == 64 && impl->fast_eos && stage_mode == 1 && ! impl->jump_mode0) kernel = stage_strip<4, 64, true, 1, true>;
+        if (N == 64 && impl->fast_eos && stage_mode == 2 && ! impl->jump_mode0) kernel = stage_strip<4, 64, true, 2, true>;
         if (impl->mesh.qmode)
             kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0, true, true> : stage_strip<4, 64, false, 0, true, true>)
                              : (impl->fast_eos ? stage_strip<4, 0, true, 0, true, true> : stage_strip<4, 0, false, 0, true, true>);

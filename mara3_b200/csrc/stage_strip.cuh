@@ -600,7 +600,7 @@ namespace
 
         // steady state: the inputs of a row's update are loaded one iteration ahead, at the end of the loop body
         // (live across the back edge, so they cannot be sunk below the face computations that hide their latency)
-        #pragma unroll
+        #pragma unroll (JUMP ? 1 : STRIP - 1)       // JUMP: rolled -- that variant is instruction-fetch bound (profiles/), the regular one is not
         for (int r = 1; r < STRIP; ++r)
         {
             double FxNew[3], FyNew[3];
