@@ -1805,7 +1805,14 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     // (default priority: with the highest one the first stage's finish_stage displaces CTAs of the second stage kernel, +2 us)
     M3B_CUDA(cudaStreamCreateWithFlags(&impl->finish_stream, cudaStreamNonBlocking));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->stage_done, cudaEventDisableTiming));
-    M3B_CUDA(cudaStreamCreateWithFlags(&impl->jump_stream, cudaStreamNonBlocking));
+    {
+        // above the compute stream's priority: ring gradients -> jump blocks is the critical path of a stage on a nested tree,
+        // the regular blocks' CTAs fill the slots it leaves (M3B_JUMP_PRIORITY=0: same priority)
+        int least = 0, greatest = 0;
+        M3B_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const char* e = std::getenv("M3B_JUMP_PRIORITY");
+        M3B_CUDA(cudaStreamCreateWithPriority(&impl->jump_stream, cudaStreamNonBlocking, e && std::atoi(e) == 0 ? least : greatest));
+    }
     M3B_CUDA(cudaEventCreateWithFlags(&impl->gradients_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->jump_done, cudaEventDisableTiming));
     M3B_CUDA(cudaEventCreateWithFlags(&impl->side_finish_done, cudaEventDisableTiming));
