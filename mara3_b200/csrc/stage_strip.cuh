@@ -23,8 +23,11 @@
  * the faces on a side whose neighbour is finer are replaced by the sum of the two fine fluxes (correct_fluxes_*,
  * scheme.cpp:614-720).  Everything inside the block runs exactly as in the regular variant.
  *
- * The loop is rolled on purpose: fully unrolled the kernel is 110 KB of SASS and a fifth of all
- * issue slots stall on instruction fetch (profiles/); rolled it stays inside the instruction cache.
+ * The strip loop is unrolled in the regular variants (59 KB of SASS, 6 % of the issue slots wait for instructions) and
+ * rolled in the JUMP variants, whose extra guard-ring and flux-correction code had pushed instruction fetch to the top
+ * stall (profiles/r01_jump_strip_ncu_summary.txt).  QMODE = true evolves conserved_q = (sigma, Sr, Lz) (advance_q,
+ * scheme.cpp:906-1020): velocities are recovered at each cell's position in its own block during the tile load, face
+ * fluxes are converted with to_angmom_fluxes, the sources are source_terms_q.
  */
 #pragma once
 
