@@ -137,3 +137,8 @@ def test_two_body_model_matches_oracle():
         fast = b.copy()
         fast[:, 3:] *= 10.0
         m3.orbital_elements(fast, 0.0)
+
+
+def test_exchange_transport_is_none_on_one_rank():
+    """m3b_exchange_transport: 0 / "none" without a device or with one rank (1 NCCL, 2 peer memory on several)."""
+    assert m3.Solver(dict(depth=1, block_size=8), host_only=True).exchange_transport == "none"
