@@ -57,6 +57,7 @@ STAGE_CASES = [
     (dict(depth=4, block_size=64), False),                         # default nested tree in 64^2 blocks (the C4 block size)
     (dict(depth=4, block_size=32, eccentricity=0.3, mass_ratio=0.5, nu=0.01, alpha_cutoff_radius=1.0,
           density_floor=1e-2), False),                              # JUMP variant without the branch-free equation of state
+    (dict(depth=3, block_size=128), False),                        # 128^2 blocks: tiles without any block side, run-time block size in both variants
     (dict(depth=4, block_size=24), False),                         # default nested tree, fused 12x24 + jumps
     (dict(depth=6, block_size=16), False),                         # five levels, fused 16x16 + jumps
     (dict(depth=5, block_size=8, focus_factor=3.0), False),        # fused 8x8 + jumps
