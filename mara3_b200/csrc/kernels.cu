@@ -1489,7 +1489,6 @@ struct device_solver_t::impl_t
     mesh_dev_t mesh {};
     model_t model {};
     int tile_x = 0, tile_y = 0;
-    int strip_min_ctas = 4;
     int num_global_blocks = 0;
     int num_interior = 0;                   // leading entries of `regular` that touch no ghost block
     bool overlap_exchange = false;          // M3B_OVERLAP_EXCHANGE=1: exchange on its own stream beside the interior update
@@ -1907,9 +1906,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     if (impl->tile_x == 16 && impl->tile_y == 32) set_smem(stage_fused<16, 32>, sizeof(tile_t<16, 32>));
     if (impl->strip)
     {
-        // experiment knob: registers per thread vs resident CTAs (default 4 CTAs x 128 threads, 128 registers)
-        const char* e = std::getenv("M3B_STRIP_MIN_CTAS");
-        impl->strip_min_ctas = e ? std::atoi(e) : 4;
+        // (3 CTAs x 168 registers and 2 x 220 were measured slower than 4 x 128: DESIGN.md section 3)
         const char* pa = std::getenv("M3B_PREFETCH_AHEAD");
         impl->mesh.prefetch_ahead = pa ? std::atoi(pa) : impl->sm_count * 4;
         set_smem(stage_strip<4, 0, false, 0>, sizeof(strip_smem_t));
