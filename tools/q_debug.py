@@ -1,3 +1,4 @@
+"""Development aid: where the conserved_q (advance_q) path differs most from the oracle on a nested tree, strip kernel against any-tree kernels."""
 import sys, os
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
