@@ -8,10 +8,12 @@ A "step" is one binary::next_solution: CFL dt + all RK stages + the RK combinati
 (reference kzps definition, Mara3 src/subprog_binary.cpp:394-404, I/O excluded).
 Mzps = leaf cells x steps / seconds / 1e6.  Rank 0 prints ONE JSON line.
 
-Timing: CUDA events around every step on the stream the kernels are launched on
-(max over ranks, summed over the K timed steps); L2 is flushed between steps by
-overwriting a 512 MiB buffer outside the event pairs, because the N=1 workload
-(1024^2 cells, 25 MB per state copy) would otherwise live in the 126 MB L2.
+Timing, N = 1: CUDA events around every step on the stream the kernels are launched
+on, summed over the K timed steps; L2 is flushed between steps by overwriting a
+512 MiB buffer outside the event pairs, because the N=1 workload (1024^2 cells, 25 MB
+per state copy) would otherwise live in the 126 MB L2.  N > 1 (4096^2 cells, per-rank
+working set larger than L2): one event pair around the K steps, queued back to back as
+the subprogram's run loop queues them; max over ranks (--sync-steps: the N = 1 procedure).
 """
 import argparse
 import json
