@@ -685,6 +685,27 @@ double m3o_plm_gradient(double yl, double y0, double yr, double theta)
     return 0.25 * fabs(sa + sb) * (sa + sc) * minabs;
 }
 
+/* primitive_t::to_conserved_angmom_per_area (physics_iso2d.hpp:263-272), the expression create_mesh uses for the initial state */
+void m3o_to_conserved_angmom(const double* p, double x, double y, double* q)
+{
+    q[0] = p[0];
+    q[1] = p[0] * (x * p[1] + y * p[2]);
+    q[2] = p[0] * (x * p[2] - y * p[1]);
+}
+
+/* recover_primitive(Q, x) (physics_iso2d.hpp:376-389), the expression advance_q uses for every cell */
+int m3o_recover_primitive_q(const double* q, double x, double y, double* p)
+{
+    double sigma = q[0];
+    double sr = q[1] / sigma;
+    double lz = q[2] / sigma;
+    double r2 = x * x + y * y;
+    p[0] = sigma;
+    p[1] = (sr * x - lz * y) / r2;
+    p[2] = (sr * y + lz * x) / r2;
+    return sigma < 0.0;
+}
+
 /* physics_iso2d.hpp:488-506 with flux (:299-307), wavespeeds (:320-328), to_conserved_per_area (:249-258).
  * nhat = on_axis(axis): (1,0,0) or (0,1,0) (core_geometric.hpp:62-74). */
 void m3o_riemann_hlle(const double* pl, const double* pr, double cs2, int axis, double* flux)
