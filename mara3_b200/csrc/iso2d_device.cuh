@@ -12,7 +12,24 @@
  * tests in tests/ measure it.
  */
 #pragma once
+#ifdef M3B_HOST_EMULATION
+// tests/ only (tests/device_math_host.cpp): the point-wise functions below compiled by the host compiler so that their
+// algebra can be checked against the oracle without a GPU.  Hardware seeds become exact library calls; nothing else changes.
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+static inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return int(b >> 32); }
+static inline int __double2loint(double x) { long long b; std::memcpy(&b, &x, 8); return int(b & 0xffffffffll); }
+static inline double __hiloint2double(int hi, int lo) { long long b = (static_cast<long long>(hi) << 32) | static_cast<unsigned int>(lo); double x; std::memcpy(&x, &b, 8); return x; }
+using std::fma; using std::fabs; using std::sqrt; using std::exp; using std::tanh;
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline double __shfl_xor_sync(unsigned, double, int) { return 0.0; }     // a "warp" of one lane: the others hold nothing
+static const struct { unsigned x; } threadIdx = {0};
+#else
 #include <cuda_runtime.h>
+#endif
 #include "iso2d_sums.hpp"
 
 namespace m3b { namespace dev {
@@ -55,6 +72,9 @@ struct prim_t { double s, vx, vy; };
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double x)
 {
+#ifdef M3B_HOST_EMULATION
+    return 1.0 / x;
+#endif
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
@@ -64,6 +84,9 @@ __device__ __forceinline__ double fast_rcp(double x)
 
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
+#ifdef M3B_HOST_EMULATION
+    return 1.0 / std::sqrt(x);
+#endif
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double t = x * y;
@@ -82,6 +105,19 @@ __device__ __forceinline__ prim_t cons_to_prim(double s, double px, double py)
 /** min / max by compare-and-select: no NaN canonicalisation (DSETP + 2 SEL instead of ~6 instructions). */
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
+/** max(0, x) and min(0, x) on the bit pattern (a shift and two ANDs on the integer pipes instead of DSETP + 2 SEL:
+ *  the stage kernels are bound by the fp64 pipe, so every compare moved off it is two issue cycles back). */
+__device__ __forceinline__ double dmax0(double x)
+{
+    const int hi = __double2hiint(x), m = ~(hi >> 31);
+    return __hiloint2double(hi & m, __double2loint(x) & m);
+}
+__device__ __forceinline__ double dmin0(double x)
+{
+    const int hi = __double2hiint(x), m = hi >> 31;
+    return __hiloint2double(hi & m, __double2loint(x) & m);
+}
 
 /**
  * Un-divided PLM difference: mara::plm_gradient (math_interpolation.hpp:85-94),
@@ -103,6 +139,16 @@ __device__ __forceinline__ double plm_from_differences(double dl, double dr, dou
 __device__ __forceinline__ double plm_diff(double yl, double y0, double yr, double theta)
 {
     return plm_from_differences(y0 - yl, yr - y0, theta);
+}
+
+/** TWICE the un-divided PLM difference (stage_tma keeps 2 g: the factor 1/2 of the central slope folds into the
+ *  half step of the face states and into the viscous coefficient).  theta2 = 2 theta. */
+__device__ __forceinline__ double plm2_from_differences(double dl, double dr, double theta2)
+{
+    double s = dl + dr;
+    double t = theta2 * (fabs(dl) < fabs(dr) ? dl : dr);
+    double r = fabs(t) < fabs(s) ? t : s;
+    return (__double2hiint(dl) ^ __double2hiint(dr)) >= 0 ? r : 0.0;
 }
 
 /** Sound speed squared and geometry-only viscosity factor at a point. */
@@ -128,7 +174,7 @@ __device__ __forceinline__ double sound_speed_squared(const model_t& M, const st
 }
 
 /** nu_at_position's cutoff profile / constant-nu branch (scheme.cpp:177-193): rare, kept out of line. */
-__device__ __noinline__ double viscosity_slow_path(double nu, double alpha, double alpha_cutoff_radius, double inv_mach, double cs, double r2)
+static __device__ __noinline__ double viscosity_slow_path(double nu, double alpha, double alpha_cutoff_radius, double inv_mach, double cs, double r2)
 {
     double r = sqrt(r2);
     double profile = alpha_cutoff_radius > 0.0 ? 0.5 * (1.0 + tanh(3.0 * (r - alpha_cutoff_radius))) : 1.0;
@@ -136,7 +182,7 @@ __device__ __noinline__ double viscosity_slow_path(double nu, double alpha, doub
 }
 
 /** sink_rate_field (scheme.cpp:117-126) where it is not negligible: rare, kept out of line. */
-__device__ __noinline__ double sink_weight(double rate, double a2)
+static __device__ __noinline__ double sink_weight(double rate, double a2)
 {
     return a2 < 100.0 ? rate * exp(-a2) : 0.0;
 }
@@ -198,40 +244,33 @@ __device__ __forceinline__ eos_t eos_at_face(const model_t& M, const stage_t& S,
  *   half_step    multiplies gl, gr to reach the face (0.5 * spacing for physical gradients)
  *   visc_scale   multiplies the gradients inside the viscous stress (1 for physical gradients)
  */
+/**
+ * The HLLE + viscous face flux from the reconstructed states L, R (riemann_hlle, physics_iso2d.hpp:488-506):
+ *   F = (ap Fl - am Fr - ap am (Ul - Ur)) / (ap - am),   ap = max(0, vl + cs, vr + cs), am = min(0, vl - cs, vr - cs)
+ * regrouped by side.  With wl = ap / (ap - am), wr = -am / (ap - am) (wl + wr = 1) and the mass fluxes
+ *   ml = sigma_l wl (vl - am),   mr = sigma_r wr (vr - ap)          (vl - am >= cs, vr - ap <= -cs: no cancellation)
+ * the three components are  ml + mr,  ml u_l + mr u_r  (+ cs2 (sigma_l wl + sigma_r wr) along the normal):
+ * 16 fp64 instructions after the reciprocal instead of 28.
+ *   mu_sum     mu = mu_coef (sigma_l + sigma_r) multiplies the summed gradients (0.5 nu x the scale of the gradients passed)
+ */
 template<int AXIS>
-__device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, prim_t gl, prim_t gr,
-    double hlx, double hly, double hrx, double hry, double half_step, double visc_scale, double F[3])
+__device__ __forceinline__ void hlle_viscous_core(double cs2, double cs, double mu_coef, const prim_t& L, const prim_t& R,
+    double long_x, double long_y, double tran_x, double tran_y, double F[3])
 {
-    prim_t L = {fma(gl.s, half_step, pl.s), fma(gl.vx, half_step, pl.vx), fma(gl.vy, half_step, pl.vy)};
-    prim_t R = {fma(-gr.s, half_step, pr.s), fma(-gr.vx, half_step, pr.vx), fma(-gr.vy, half_step, pr.vy)};
-
     double vl = AXIS == 0 ? L.vx : L.vy;
     double vr = AXIS == 0 ? R.vx : R.vy;
-    double ap = dmax(0.0, dmax(vl, vr) + e.cs);     // max(0, vl + cs, vr + cs)
-    double am = dmin(0.0, dmin(vl, vr) - e.cs);     // min(0, vl - cs, vr - cs)
-    double f0, f1, f2;
-    {
-        // (a warp-uniform short cut for all-supersonic faces was measured: the branches cost more than the
-        // arithmetic they save, 764 -> 719 us on the 4096^2 grid -- one straight-line block schedules better)
-        double inv = fast_rcp(ap - am);
-        double apam = ap * am;
-        double Ul1 = L.s * L.vx, Ul2 = L.s * L.vy, Ur1 = R.s * R.vx, Ur2 = R.s * R.vy;
-        double Fl0 = vl * L.s, Fr0 = vr * R.s;
-        double pgl = L.s * e.cs2, pgr = R.s * e.cs2;
-        double Fl1 = AXIS == 0 ? fma(Fl0, L.vx, pgl) : Fl0 * L.vx;
-        double Fl2 = AXIS == 0 ? Fl0 * L.vy : fma(Fl0, L.vy, pgl);
-        double Fr1 = AXIS == 0 ? fma(Fr0, R.vx, pgr) : Fr0 * R.vx;
-        double Fr2 = AXIS == 0 ? Fr0 * R.vy : fma(Fr0, R.vy, pgr);
-        f0 = fma(Fl0, ap, fma(-Fr0, am, -(L.s - R.s) * apam)) * inv;
-        f1 = fma(Fl1, ap, fma(-Fr1, am, -(Ul1 - Ur1) * apam)) * inv;
-        f2 = fma(Fl2, ap, fma(-Fr2, am, -(Ul2 - Ur2) * apam)) * inv;
-    }
+    double ap = dmax0(dmax(vl, vr) + cs);       // max(0, vl + cs, vr + cs)
+    double am = dmin0(dmin(vl, vr) - cs);       // min(0, vl - cs, vr - cs)
+    double inv = fast_rcp(ap - am);
+    double wl = ap * inv, wr = -am * inv;
+    double ml = L.s * (wl * (vl - am));
+    double mr = R.s * (wr * (vr - ap));
+    double pw = fma(L.s, wl, R.s * wr) * cs2;
+    double f0 = ml + mr;
+    double f1 = AXIS == 0 ? fma(ml, L.vx, fma(mr, R.vx, pw)) : fma(ml, L.vx, mr * R.vx);
+    double f2 = AXIS == 0 ? fma(ml, L.vy, mr * R.vy) : fma(ml, L.vy, fma(mr, R.vy, pw));
 
-    // mu = 0.5 nu (sigma_l + sigma_r); the stresses use face averages 0.5 (g_l + g_r)
-    double mu = (0.25 * visc_scale) * e.nu * (L.s + R.s);
-    double long_x = gl.vx + gr.vx, long_y = gl.vy + gr.vy;
-    double tran_x = hlx + hrx,     tran_y = hly + hry;
-
+    double mu = mu_coef * (L.s + R.s);
     if (AXIS == 0)
     {
         // tau_xx = mu (dx ux - dy uy), tau_xy = mu (dx uy + dy ux)
@@ -245,6 +284,27 @@ __device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, 
         f2 = fma( mu, tran_x - long_y, f2);
     }
     F[0] = f0; F[1] = f1; F[2] = f2;
+}
+
+/**
+ * HLLE + viscous flux through a face with normal along `AXIS`:
+ * intercell_flux_u (scheme.cpp:268-293) = iso2d::riemann_hlle (physics_iso2d.hpp:488-506)
+ * + viscous_flux (scheme.cpp:220-262).
+ *
+ *   pl, pr       cell-centre primitives left / right of the face
+ *   gl, gr       longitudinal gradients (all three components) of the left / right cell
+ *   hlx..hry     transverse gradients of vx, vy in the left / right cell
+ *   half_step    multiplies gl, gr to reach the face (0.5 * spacing for physical gradients)
+ *   visc_scale   multiplies the gradients inside the viscous stress (1 for physical gradients)
+ */
+template<int AXIS>
+__device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, prim_t gl, prim_t gr,
+    double hlx, double hly, double hrx, double hry, double half_step, double visc_scale, double F[3])
+{
+    prim_t L = {fma(gl.s, half_step, pl.s), fma(gl.vx, half_step, pl.vx), fma(gl.vy, half_step, pl.vy)};
+    prim_t R = {fma(-gr.s, half_step, pr.s), fma(-gr.vx, half_step, pr.vx), fma(-gr.vy, half_step, pr.vy)};
+    // mu = 0.5 nu (sigma_l + sigma_r); the stresses use face averages 0.5 (g_l + g_r)
+    hlle_viscous_core<AXIS>(e.cs2, e.cs, (0.25 * visc_scale) * e.nu, L, R, gl.vx + gr.vx, gl.vy + gr.vy, hlx + hrx, hly + hry, F);
 }
 
 /** Running sums behind source_term_total_t (scheme.cpp:22-35, 390-408), before the dt * dA factor. */
@@ -453,6 +513,120 @@ __device__ __forceinline__ double max_wavespeed(const model_t& M, const stage_t&
     double inv = fast_rcp(s);
     double vx = fabs(px * inv), vy = fabs(py * inv);
     return dmax(vx, vy) + cs;       // max(|v - cs|, |v + cs|) = |v| + cs for cs >= 0
+}
+
+
+// ---------------------------------------------------------------------------
+// stage_tma: the same physics with everything that is constant over a tile, a thread or a stage hoisted
+// ---------------------------------------------------------------------------
+
+/** Per-stage constants of stage_tma, derived once per CTA from model_t / stage_t. */
+struct strip_consts_t
+{
+    double m1s, m2s;        // G M_k / Mach^2: cs2 = m1s / sqrt(d1) + m2s / sqrt(d2)   (scheme.cpp:160-175)
+    double nm1, nm2;        // -G M_k (gravity, scheme.cpp:85-95)
+    double theta2;          // 2 plm_theta
+    double dt;
+};
+
+/** cs2, cs and the viscous coefficient of a face from tabulated squared distances (FAST: default equation of state).
+ *  q2 = (c r)^2 with c = 0.25 * gradient scale * alpha / Mach folded into the table, so that
+ *  mu = sqrt(cs2 q2) (sigma_l + sigma_r) = 0.5 nu (sigma_l + sigma_r) x the gradient scale (scheme.cpp:177-193, 284). */
+struct eos_face_t { double cs2, cs, mu_coef; };
+
+__device__ __forceinline__ eos_face_t eos_face_fast(const strip_consts_t& C, double d1, double d2, double q2)
+{
+    eos_face_t e;
+    e.cs2 = fma(C.m1s, fast_rsqrt(d1), C.m2s * fast_rsqrt(d2));
+    e.cs = e.cs2 * fast_rsqrt(e.cs2);
+    double q = e.cs2 * q2;
+    e.mu_coef = q * fast_rsqrt(q);
+    return e;
+}
+
+/** Running sums of one thread of stage_tma (lane <-> column: y and the y-distances to the bodies are constant, so the six
+ *  gravity totals of source_term_total_t follow from  S0_k = sum k_k  and  Sx_k = sum x k_k,  k_k = -G M_k sigma / d_k^(3/2):
+ *    force_x = Sx_k - x_k S0_k,  force_y = (y - y_k) S0_k,  torque = x_k y S0_k - y_k Sx_k        (scheme.cpp:390-408)
+ *  and the ejected angular momentum from  sum x b_py  and  sum b_px). */
+struct strip_sums_t
+{
+    double S0[2], Sx[2];
+    double buf_m, buf_xpy, buf_px;
+};
+
+/**
+ * source_terms_u (scheme.cpp:345-411) for stage_tma: returns acc = u + s (the caller subtracts the flux difference), the
+ * inverse softened distances y1, y2 for the fused time-step estimate, and adds to the thread's running sums.
+ *   x, dx1, dx2      cell-centre x and its distances to the bodies;  dy1, dy2, y: the thread's constants
+ *   d1, d2           softened squared distances (tabulated)
+ *   near_sink        warp-uniform: some cell of the tile lies within the sinks' reach (a2 < 100)
+ *   has_buffer       warp-uniform: the buffer-zone rate is non-zero somewhere in the tile
+ */
+template<bool FAST>
+__device__ __forceinline__ void source_terms_strip(const model_t& M, const strip_consts_t& C, double x, double y,
+    double dx1, double dy1, double dx2, double dy2, double d1, double d2, bool near_sink, bool has_buffer,
+    double s, double px, double py, double u0s, double u0x, double u0y, double br,
+    double acc[3], strip_sums_t& sums, double& y1, double& y2, double* warp_sinks)
+{
+    y1 = fast_rsqrt(d1);
+    y2 = fast_rsqrt(d2);
+    // grav_vdot_field * sigma (scheme.cpp:85-95, 377-378)
+    double k1 = ((y1 * y1) * y1) * (s * C.nm1);
+    double k2 = ((y2 * y2) * y2) * (s * C.nm2);
+    sums.S0[0] += k1;  sums.Sx[0] = fma(x, k1, sums.Sx[0]);
+    sums.S0[1] += k2;  sums.Sx[1] = fma(x, k2, sums.Sx[1]);
+    double fx = fma(dx1, k1, dx2 * k2), fy = fma(dy1, k1, dy2 * k2);
+    double a0 = s, a1 = fma(fx, C.dt, px), a2 = fma(fy, C.dt, py);
+
+    if (near_sink)
+    {
+        // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)), nothing representable beyond a2 = 100
+        double e1 = fma(dx1, dx1, dy1 * dy1) * M.sink_inv_2s2, e2 = fma(dx2, dx2, dy2 * dy2) * M.sink_inv_2s2;
+        if (__any_sync(0xffffffffu, e1 < 100.0 || e2 < 100.0))
+        {
+            double w1 = sink_weight(M.sink_rate, e1);
+            double w2 = sink_weight(M.sink_rate, e2);
+            double lz = fma(x, py, -y * px);
+            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+            #pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+            }
+            double w = -(w1 + w2) * C.dt;
+            a0 = fma(s, w, a0);  a1 = fma(px, w, a1);  a2 = fma(py, w, a2);
+        }
+    }
+    if (has_buffer)
+    {
+        // buffer zone (scheme.cpp:384): (U0 - u) * rate * dt
+        double b0 = (u0s - s) * br, b1 = (u0x - px) * br, b2 = (u0y - py) * br;
+        sums.buf_m += b0;
+        sums.buf_xpy = fma(x, b2, sums.buf_xpy);
+        sums.buf_px += b1;
+        a0 = fma(b0, C.dt, a0);  a1 = fma(b1, C.dt, a1);  a2 = fma(b2, C.dt, a2);
+    }
+    if (! FAST && s < M.density_floor)      // density floor (scheme.cpp:385-388): u * 0.01 where sigma < floor
+    {
+        a0 = fma(s, 1e-2, a0);  a1 = fma(px, 1e-2, a1);  a2 = fma(py, 1e-2, a2);
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2;
+}
+
+/** max_wavespeed with cs2 from the pre-scaled masses (FAST) */
+__device__ __forceinline__ double max_wavespeed_fast(const strip_consts_t& C, double y1, double y2, double s, double px, double py)
+{
+    double cs2 = fma(C.m1s, y1, C.m2s * y2);
+    double cs = cs2 * fast_rsqrt(cs2);
+    double inv = fast_rcp(s);
+    double vx = fabs(px * inv), vy = fabs(py * inv);
+    return dmax(vx, vy) + cs;
 }
 
 }} // namespace m3b::dev

@@ -1,0 +1,103 @@
+/**
+ * kernel_common.cuh -- device-side records shared by the translation units that hold kernels (kernels.cu, stage_tma.cu):
+ * the static mesh tables, the per-tile record of the strip kernels, the negative-density report.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "device_solver.hpp"
+#include "iso2d_device.cuh"
+
+namespace m3b { namespace dev
+{
+    constexpr int THREADS = 256;
+    constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
+    constexpr int FINISH_THREADS = 256;
+    constexpr int FINISH_ROWS_PER_CTA = 32;     // block rows folded by one finish_stage CTA
+    constexpr int stage_ring_size = 64;
+
+    struct __align__(16) face_nbr_dev_t
+    {
+        int kind;                       // 0 same, 1 coarser, 2 finer
+        int leaf[4];
+        int bx, by;
+        int pad;
+        int gs[4];                      // gslot of leaf[q]: where its gradients live in the scratch (stage_strip<.., JUMP> reads the record as three int4)
+    };
+    static_assert(sizeof(face_nbr_dev_t) == 48, "stage_strip reads face_nbr_dev_t as three int4");
+
+    struct mesh_dev_t
+    {
+        int B, N;
+        size_t FS;                      // field stride = B * N * N
+        const double* xv;               // [B][N+1]
+        const double* yv;               // [B][N+1]
+        const double* spacing;          // [B]
+        const double* inv_spacing;      // [B] 1 / spacing
+        const face_nbr_dev_t* nbr;      // [B][4]
+        const int* nbr9;                // [B][9] same-level neighbour leaf ids (regular blocks only)
+        const int* gslot;               // [B] slot of the block in the gradient scratch, or -1
+        const double* U0;               // [3][FS]
+        const double* br;               // [FS]
+        size_t GS;                      // gradient scratch stride
+        int qmode;                      // the state is conserved_q = (sigma, Sr, Lz): primitives need the cell position
+        int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
+        // multi-GPU: CTAs from first_wait_cta on update blocks with ghost neighbours and wait until the guard-zone
+        // unpack (running beside this kernel on the exchange stream) has published ready_value
+        int first_wait_cta;
+        const unsigned long long* ready_flag;
+        unsigned long long ready_value;
+    };
+
+    /** Everything a stage_strip CTA needs to find its data, in one 48-byte record per tile (one load instead of
+     *  the dependent chain regular list -> neighbour table / tile flags). */
+    struct __align__(16) tile_info_t
+    {
+        int b;                          // block
+        int n9[9];                      // same-level neighbour ids, (di + 1) * 3 + (dj + 1)
+        int flags;                      // bit 0: the buffer-zone rate is non-zero somewhere in the tile
+        int pad;
+    };
+
+    struct fail_dev_t
+    {
+        unsigned int count;
+        unsigned int pad;
+        m3b::offender_t list[m3b::device_solver_t::max_offenders];
+    };
+
+    __device__ __forceinline__ void report_negative(fail_dev_t* fail, int block, int cell, double sigma)
+    {
+        unsigned int n = atomicAdd(&fail->count, 1u);
+        if (n < m3b::device_solver_t::max_offenders) fail->list[n] = {block, cell, sigma};
+    }
+
+    // geometry of the strip kernels (stage_strip, stage_tma): CTA = 4 warps on a 16 x 32 tile, warp <-> strip of 4 rows
+    constexpr int SX = 16, SY = 32, STRIP = 4, STRIP_THREADS = 128;
+
+    __device__ __forceinline__ double shfl_down1(double v)
+    {
+        return __shfl_down_sync(0xffffffffu, v, 1);
+    }
+
+    /** stage_tma.cu: one launch of the persistent TMA-staged stage kernel over `num_tiles` entries of `tile_info`. */
+    struct stage_tma_launch_t
+    {
+        mesh_dev_t mesh;
+        model_t model;
+        const stage_t* stage;
+        const tile_info_t* tile_info;
+        int num_tiles;
+        const double* Uin;
+        const double* Un;
+        double* Uout;
+        double* partials;
+        fail_dev_t* fail;
+        int N;              // block size
+        bool fast;          // branch-free equation of state
+        int stage_mode;     // 0: flags from stage_t, 1 / 2: first / last stage of an adaptive RK2 step
+        int grid;           // resident CTAs
+    };
+    void stage_tma_configure();
+    void stage_tma_launch(const stage_tma_launch_t& a, cudaStream_t stream);
+    size_t stage_tma_shared_bytes();
+}} // namespace m3b::dev

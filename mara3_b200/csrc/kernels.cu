@@ -31,6 +31,7 @@
 #include "comm.hpp"
 #include "device_solver.hpp"
 #include "iso2d_device.cuh"
+#include "kernel_common.cuh"
 
 using namespace m3b;
 using namespace m3b::dev;
@@ -40,63 +41,6 @@ using namespace m3b::dev;
 
 namespace
 {
-    constexpr int THREADS = 256;
-    constexpr int ROW = 20;             // doubles per partial row: 16 sums, dt_min, pad
-    constexpr int FINISH_THREADS = 256;
-    constexpr int FINISH_ROWS_PER_CTA = 32;     // block rows folded by one finish_stage CTA
-    constexpr int stage_ring_size = 64;
-
-    struct __align__(16) face_nbr_dev_t
-    {
-        int kind;                       // 0 same, 1 coarser, 2 finer
-        int leaf[4];
-        int bx, by;
-        int pad;
-        int gs[4];                      // gslot of leaf[q]: where its gradients live in the scratch (stage_strip<.., JUMP> reads the record as three int4)
-    };
-    static_assert(sizeof(face_nbr_dev_t) == 48, "stage_strip reads face_nbr_dev_t as three int4");
-
-    struct mesh_dev_t
-    {
-        int B, N;
-        size_t FS;                      // field stride = B * N * N
-        const double* xv;               // [B][N+1]
-        const double* yv;               // [B][N+1]
-        const double* spacing;          // [B]
-        const double* inv_spacing;      // [B] 1 / spacing
-        const face_nbr_dev_t* nbr;      // [B][4]
-        const int* nbr9;                // [B][9] same-level neighbour leaf ids (regular blocks only)
-        const int* gslot;               // [B] slot of the block in the gradient scratch, or -1
-        const double* U0;               // [3][FS]
-        const double* br;               // [FS]
-        size_t GS;                      // gradient scratch stride
-        int qmode;                      // the state is conserved_q = (sigma, Sr, Lz): primitives need the cell position
-        int prefetch_ahead;             // stage_strip: CTAs resident at once (L2 prefetch distance), 0 = off
-        // multi-GPU: CTAs from first_wait_cta on update blocks with ghost neighbours and wait until the guard-zone
-        // unpack (running beside this kernel on the exchange stream) has published ready_value
-        int first_wait_cta;
-        const unsigned long long* ready_flag;
-        unsigned long long ready_value;
-    };
-
-    /** Everything a stage_strip CTA needs to find its data, in one 48-byte record per tile (one load instead of
-     *  the dependent chain regular list -> neighbour table / tile flags). */
-    struct __align__(16) tile_info_t
-    {
-        int b;                          // block
-        int n9[9];                      // same-level neighbour ids, (di + 1) * 3 + (dj + 1)
-        int flags;                      // bit 0: the buffer-zone rate is non-zero somewhere in the tile
-        int pad;
-    };
-
-    struct fail_dev_t
-    {
-        unsigned int count;
-        unsigned int pad;
-        offender_t list[device_solver_t::max_offenders];
-    };
-
-
     // =======================================================================
     // Block-wide reduction of the stage outputs
     // =======================================================================
@@ -156,11 +100,6 @@ namespace
         }
     }
 
-    __device__ __forceinline__ void report_negative(fail_dev_t* fail, int block, int cell, double sigma)
-    {
-        unsigned int n = atomicAdd(&fail->count, 1u);
-        if (n < device_solver_t::max_offenders) fail->list[n] = {block, cell, sigma};
-    }
 
 
     // =======================================================================
@@ -1496,6 +1435,9 @@ struct device_solver_t::impl_t
     cudaEvent_t input_ready = nullptr, halo_ready = nullptr;
     bool fast_eos = false;                  // default equation of state / viscosity: branch-free kernel variant
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
+    bool tma = false;                       // regular blocks through stage_tma (persistent, cp.async.bulk staging); M3B_STAGE=strip: stage_strip
+    bool tma_fast = false;                  // stage_tma's branch-free equation of state (fast_eos and alpha > 0)
+    int tma_ctas_per_sm = 3;                // M3B_TMA_CTAS
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
@@ -1930,6 +1872,12 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         set_smem(stage_strip<4, 64, false, 0, true>, sizeof(strip_smem_t));
         set_smem(stage_strip<4, 64, true, 0, true>, sizeof(strip_smem_t));
         impl->fast_eos = ! sd.axisymmetric_cs2 && sd.nu == 0.0 && sd.alpha_cutoff_radius == 0.0 && sd.density_floor == 0.0;
+        // stage_tma: linear-momentum variables only (conserved_q keeps stage_strip<.., QMODE>)
+        impl->tma = sd.conserve_linear_p;
+        if (const char* e = std::getenv("M3B_STAGE")) impl->tma = impl->tma && std::string(e) != "strip";
+        if (const char* e = std::getenv("M3B_TMA_CTAS")) impl->tma_ctas_per_sm = std::max(1, std::min(3, std::atoi(e)));
+        impl->tma_fast = impl->fast_eos && sd.alpha > 0.0;
+        stage_tma_configure();      // stage_tma.cu
     }
     if (impl->tile_x == 12 && impl->tile_y == 24) set_smem(stage_fused<12, 24>, sizeof(tile_t<12, 24>));
     if (impl->tile_x == 16 && impl->tile_y == 16) set_smem(stage_fused<16, 16>, sizeof(tile_t<16, 16>));
@@ -2211,7 +2159,20 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         double* tiles = partials + size_t(first) * tpb * ROW;
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
             impl->mesh, impl->model, st, list, in.data, un_data, out.data, tiles, impl->d_fail + slot)
-        if (impl->strip)
+        if (impl->strip && impl->tma)
+        {
+            stage_tma_launch_t a;
+            a.mesh = impl->mesh;
+            a.mesh.first_wait_cta = waiting_tiles ? std::max(0, impl->num_interior - first) * tpb : 0x7fffffff;
+            a.mesh.ready_flag = impl->d_ready;
+            a.mesh.ready_value = impl->exchange_counter;
+            a.model = impl->model; a.stage = st; a.tile_info = impl->d_tile_info + size_t(first) * tpb; a.num_tiles = ctas;
+            a.Uin = in.data; a.Un = un_data; a.Uout = out.data; a.partials = tiles; a.fail = impl->d_fail + slot;
+            a.N = N; a.fast = impl->tma_fast; a.stage_mode = stage_mode;
+            a.grid = std::min(ctas, impl->sm_count * impl->tma_ctas_per_sm);       // persistent: every CTA walks the tile list with stride `grid`
+            stage_tma_launch(a, s);
+        }
+        else if (impl->strip)
         {
             auto kernel = N == 64 ? (impl->fast_eos ? stage_strip<4, 64, true, 0> : stage_strip<4, 64, false, 0>)
                                   : (impl->fast_eos ? stage_strip<4, 0, true, 0> : stage_strip<4, 0, false, 0>);

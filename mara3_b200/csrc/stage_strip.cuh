@@ -33,8 +33,6 @@
 
 namespace
 {
-    constexpr int SX = 16, SY = 32, STRIP = 4, STRIP_THREADS = 128;
-
     struct strip_smem_t
     {
         double P[3][SX + 4][SY + 4];        // primitives sigma, vx, vy on tile + 2 halo
@@ -52,11 +50,6 @@ namespace
         double red[STRIP_THREADS / 32][NUM_SUMS + 1];
         double sinks[STRIP_THREADS / 32][8];     // per-warp sink sums (ACC_MASS .. ACC_LZ), see source_terms<.., WARP_SINKS>
     };
-
-    __device__ __forceinline__ double shfl_down1(double v)
-    {
-        return __shfl_down_sync(0xffffffffu, v, 1);
-    }
 
     template<bool FAST>
     __device__ __forceinline__ eos_t strip_x_eos(const strip_smem_t& T, const model_t& model, const stage_t& S, int li, int lj)
