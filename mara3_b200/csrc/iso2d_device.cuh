@@ -251,7 +251,61 @@ __device__ __forceinline__ eos_t eos_at_face(const model_t& M, const stage_t& S,
  *   ml = sigma_l wl (vl - am),   mr = sigma_r wr (vr - ap)          (vl - am >= cs, vr - ap <= -cs: no cancellation)
  * the three components are  ml + mr,  ml u_l + mr u_r  (+ cs2 (sigma_l wl + sigma_r wr) along the normal):
  * 16 fp64 instructions after the reciprocal instead of 28.
- *   mu_sum     mu = mu_coef (sigma_l + sigma_r) multiplies the summed gradients (0.5 nu x the scale of the gradients passed)
+ *   mu_coef    mu = mu_coef (sigma_l + sigma_r) multiplies d1, d2 (0.5 nu x 0.5 for the face average x the scale of the gradients passed)
+ */
+template<int AXIS>
+__device__ __forceinline__ void hlle_viscous_core(double cs2, double cs, double mu_coef, const prim_t& L, const prim_t& R,
+    double d1, double d2, double F[3])
+{
+    // d1, d2: sums over the two cells of D1 = dx ux - dy uy and D2 = dx uy + dy ux (in the scale mu_coef expects)
+    double vl = AXIS == 0 ? L.vx : L.vy;
+    double vr = AXIS == 0 ? R.vx : R.vy;
+    double ap = dmax0(dmax(vl, vr) + cs);       // max(0, vl + cs, vr + cs)
+    double am = dmin0(dmin(vl, vr) - cs);       // min(0, vl - cs, vr - cs)
+    double inv = fast_rcp(ap - am);
+    double wl = ap * inv, wr = -am * inv;
+    double ml = L.s * (wl * (vl - am));
+    double mr = R.s * (wr * (vr - ap));
+    double pw = fma(L.s, wl, R.s * wr) * cs2;
+    double f0 = ml + mr;
+    double f1 = AXIS == 0 ? fma(ml, L.vx, fma(mr, R.vx, pw)) : fma(ml, L.vx, mr * R.vx);
+    double f2 = AXIS == 0 ? fma(ml, L.vy, mr * R.vy) : fma(ml, L.vy, fma(mr, R.vy, pw));
+
+    double mu = mu_coef * (L.s + R.s);
+    if (AXIS == 0)
+    {
+        // tau_xx = mu (dx ux - dy uy), tau_xy = mu (dx uy + dy ux)
+        f1 = fma(-mu, d1, f1);
+        f2 = fma(-mu, d2, f2);
+    }
+    else
+    {
+        // tau_yx = mu (dx uy + dy ux), tau_yy = -mu (dx ux - dy uy)
+        f1 = fma(-mu, d2, f1);
+        f2 = fma( mu, d1, f2);
+    }
+    F[0] = f0; F[1] = f1; F[2] = f2;
+}
+
+/**
+ * HLLE + viscous flux through a face with normal along `AXIS`:
+ * intercell_flux_u (scheme.cpp:268-293) = iso2d::riemann_hlle (physics_iso2d.hpp:488-506)
+ * + viscous_flux (scheme.cpp:220-262).
+ *
+ *   pl, pr       cell-centre primitives left / right of the face
+ *   gl, gr       longitudinal gradients (all three components) of the left / right cell
+ *   hlx..hry     transverse gradients of vx, vy in the left / right cell
+ *   half_step    multiplies gl, gr to reach the face (0.5 * spacing for physical gradients)
+ *   visc_scale   multiplies the gradients inside the viscous stress (1 for physical gradients)
+ */
+/**
+ * The HLLE + viscous face flux from the reconstructed states L, R (riemann_hlle, physics_iso2d.hpp:488-506):
+ *   F = (ap Fl - am Fr - ap am (Ul - Ur)) / (ap - am),   ap = max(0, vl + cs, vr + cs), am = min(0, vl - cs, vr - cs)
+ * regrouped by side.  With wl = ap / (ap - am), wr = -am / (ap - am) (wl + wr = 1) and the mass fluxes
+ *   ml = sigma_l wl (vl - am),   mr = sigma_r wr (vr - ap)          (vl - am >= cs, vr - ap <= -cs: no cancellation)
+ * the three components are  ml + mr,  ml u_l + mr u_r  (+ cs2 (sigma_l wl + sigma_r wr) along the normal):
+ * 16 fp64 instructions after the reciprocal instead of 28.
+ *   mu_coef    mu = mu_coef (sigma_l + sigma_r) multiplies d1, d2 (0.5 nu x 0.5 for the face average x the scale of the gradients passed)
  */
 template<int AXIS>
 __device__ __forceinline__ void hlle_viscous_core(double cs2, double cs, double mu_coef, const prim_t& L, const prim_t& R,
@@ -304,7 +358,11 @@ __device__ __forceinline__ void face_flux(const eos_t& e, prim_t pl, prim_t pr, 
     prim_t L = {fma(gl.s, half_step, pl.s), fma(gl.vx, half_step, pl.vx), fma(gl.vy, half_step, pl.vy)};
     prim_t R = {fma(-gr.s, half_step, pr.s), fma(-gr.vx, half_step, pr.vx), fma(-gr.vy, half_step, pr.vy)};
     // mu = 0.5 nu (sigma_l + sigma_r); the stresses use face averages 0.5 (g_l + g_r)
-    hlle_viscous_core<AXIS>(e.cs2, e.cs, (0.25 * visc_scale) * e.nu, L, R, gl.vx + gr.vx, gl.vy + gr.vy, hlx + hrx, hly + hry, F);
+    const double long_x = gl.vx + gr.vx, long_y = gl.vy + gr.vy, tran_x = hlx + hrx, tran_y = hly + hry;
+    // AXIS 0: longitudinal = d/dx, transverse = d/dy; AXIS 1 the other way round
+    const double d1 = AXIS == 0 ? long_x - tran_y : tran_x - long_y;
+    const double d2 = AXIS == 0 ? long_y + tran_x : tran_y + long_x;
+    hlle_viscous_core<AXIS>(e.cs2, e.cs, (0.25 * visc_scale) * e.nu, L, R, d1, d2, F);
 }
 
 /** Running sums behind source_term_total_t (scheme.cpp:22-35, 390-408), before the dt * dA factor. */

@@ -1,6 +1,6 @@
 /**
- * stage_tma.cuh -- the fused RK-stage kernel for regular blocks (block size a multiple of 32), persistent, with the
- * tiles staged into shared memory by the TMA engine (cp.async.bulk + mbarrier), double-buffered.
+ * stage_tma.cuh -- the fused RK-stage kernel for regular blocks (block size a multiple of 32): persistent CTAs, tiles staged
+ * into shared memory asynchronously (cp.async, SASS LDGSTS) one tile ahead of the arithmetic, double-buffered.
  *
  * Same update as stage_strip (phases P1-P8 + P11 of binary::advance_u, Mara3 src/subprog_binary_scheme.cpp:790-904, plus the
  * CFL estimate of :1107-1126 and the RK combination of subprog_binary.cpp:272-275 in the last stage) and the same thread
@@ -8,13 +8,11 @@
  *
  *   * the grid is persistent: gridDim.x = SMs x CTAs per SM, CTA c takes tiles c, c + gridDim.x, ... of the launch's tile
  *     list (interior blocks first, blocks with ghost neighbours last), so a launch pays one ramp-up and one drain instead
- *     of one per wave, and the L1 / instruction cache / mbarriers stay warm;
- *   * while tile k is computed, warp 0 has already issued the bulk copies of tile k + 1: per field and row one
- *     cp.async.bulk of the row's cells in the tile's own block (272 or 288 bytes) and, where the tile touches a block side
- *     in y, one 16-byte copy of the two guard cells from the neighbour block.  The copies land in the other half of
- *     P[2][3][20][36] and complete on that half's mbarrier (expect_tx = 17 280 bytes); no thread holds a register or a
- *     scoreboard slot for them, and the only wait left is mbarrier.try_wait at the top of the next tile, which by then
- *     has had a whole tile time (~10 us) to complete;
+ *     of one per wave;
+ *   * while tile k is computed, the 16-byte chunks of tile k + 1 (20 rows x 18 chunks x 3 fields, each thread the <= 9 chunks
+ *     it will convert itself) are already in flight into the other half of P[2][3][20][36]: no register and no scoreboard
+ *     slot is held for them, and a thread only waits (cp.async.wait_group) for its OWN chunks at the top of the next tile,
+ *     a whole tile time (~10 us) after it asked for them;
  *   * conserved -> primitive happens in place in shared memory; the PLM phase keeps TWICE the un-divided difference (the
  *     1/2 of the central slope folds into the face states' half step and the viscous coefficient);
  *   * the arithmetic is regrouped for the fp64 pipe, which bounds this kernel (profiles/): HLLE by side (hlle_viscous_core),
@@ -22,22 +20,27 @@
  *     density on the integer pipes, gravity totals from two running sums per body instead of three, sink and buffer terms
  *     behind warp-uniform per-tile flags.
  *
- * Shared memory 71.9 KB per CTA -> 3 CTAs (12 warps) per SM with up to 168 registers per thread.
+ * A first version moved the rows with cp.async.bulk (UBLKCP, one copy per field and row): UBLKCP takes uniform-register
+ * operands, so per-lane addresses turn into a waterfall loop of ~8 instructions per copy on the issuing warp, ~120 copies per
+ * tile; the other warps waited for it at the barriers (793 us against stage_strip's 565 us on 4096^2,
+ * profiles/r02_stage_tma_bulk_rows_ncu_summary.txt).  Rows of 36 doubles that change block at every side are the wrong
+ * granularity for the TMA engine; 16-byte cp.async per thread is the right one.
+ *
+ * Shared memory 72 KB per CTA -> 3 CTAs (12 warps) per SM with up to 168 registers per thread.
  */
 #pragma once
 
 namespace m3b { namespace dev { namespace
 {
-    constexpr unsigned TMA_TILE_BYTES = 3u * (SX + 4) * (SY + 4) * sizeof(double);     // 17 280
-
     struct tma_smem_t
     {
         double P[2][3][SX + 4][SY + 4];     // raw conserved rows as the bulk copies deliver them, then primitives (in place); two tiles
         double G[6][SX + 2][SY + 2];        // 2 x un-divided PLM differences d/dx (3), d/dy (3) on tile + 1 halo
-        double XB[3][5][SY];                // x-face fluxes at rows 4, 8, 12 (strip starts) and 16 (tile boundary)
+        double XB[3][4][SY];                // x-face fluxes at rows 4, 8, 12 (strip starts) and 16 (tile boundary): the high-x flux of strip w is XB[.][w]
         double YB[3][SX];                   // y-face fluxes at the tile's high-y boundary
         double cx[2][SX + 2];               // vertex coordinates of the tile (17 + 33 used), two tiles
         double cy[2][SY + 2];
+        double hh[2][2];                    // spacing and 1 / spacing of the tile's block, two tiles
         // squared-distance tables of the tile's face / centre coordinates to the two bodies (k = 0, 1; the y tables hold the
         // softening rs^2) and to the origin (k = 2; FAST: scaled by the viscous coefficient, see eos_face_fast)
         double x2v[3][SX + 1], x2c[3][SX];
@@ -45,111 +48,111 @@ namespace m3b { namespace dev { namespace
         double xc[SX], dxc[2][SX];          // cell-centre x and its distance to the bodies
         double red[STRIP_THREADS / 32][NUM_SUMS + 1];
         double sinks[STRIP_THREADS / 32][8];
-        tile_info_t info[2];
-        unsigned long long mbar[2];
+        tile_info_t info[3];                // records of the tiles k, k + 1, k + 2 (slot = ordinal % 3)
+        double negbuf[STRIP_THREADS / 32][STRIP][32];     // new densities that came out negative, until the strip is done
         int near_sink;
     };
 
     __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
-    __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+    /** cp.async 16 bytes global -> shared, L2 only (SASS: LDGSTS.E.BYPASS.128) */
+    __device__ __forceinline__ void cp_async_16(void* dst, const void* src)
     {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
     }
-    __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
-    {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-    }
-    __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-    {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "M3B_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra M3B_DONE;\n"
-            "bra M3B_WAIT;\n"
-            "M3B_DONE:\n"
-            "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-    /** cp.async.bulk global -> shared (SASS: UBLKCP); size and both addresses are multiples of 16 bytes */
-    __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
-    {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-    }
+    __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
     /**
-     * Warp 0: start the bulk copies of tile `tile` into half `buf` and fetch the tile's vertex coordinates into registers
-     * (nx: xv[i0 + lane] for lane <= 16, ny: yv[j0 + lane], ny32: yv[j0 + 32] on lane 0; stored to shared memory later,
-     * when they have arrived).  60 (field, row) pairs over 32 lanes; a row is one copy from the tile's own block column
-     * range plus 16-byte copies of the two guard columns beyond a block side.
+     * Every thread: ask for the chunks of the tile described by `ti` that this thread will convert -- (row rr + 7 m, chunk cc),
+     * m = 0, 1, 2, of the (SX + 4) x (SY + 4) region = 20 rows of 18 sixteen-byte chunks (two cells in y; columns j0 - 2 and N
+     * are even, so a chunk never straddles two blocks), all three fields -- into half `buf`.
      */
-    __device__ __forceinline__ void tma_issue_tile(tma_smem_t& T, const mesh_dev_t& mesh, const tile_info_t* __restrict__ tile_info,
-        const double* __restrict__ Uin, int tile, int buf, int N, int tiles_y, int tpb, int lane, double& nx, double& ny, double& ny32)
+    __device__ __forceinline__ void stage_tile_async(tma_smem_t& T, const tile_info_t& ti, const double* __restrict__ Uin, size_t FS,
+        int t, int buf, int N, int tiles_y)
     {
-        // multi-GPU: tiles of blocks with ghost neighbours may only be fetched once the guard-zone unpack has finished
-        if (tile >= mesh.first_wait_cta)
+        const int rr = threadIdx.x / 18, cc = threadIdx.x - 18 * rr;
+        if (rr < 7)
         {
-            if (lane == 0)
+            const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
+            const int gj = j0 - 2 + 2 * cc;
+            const int dj = gj < 0 ? -1 : (gj >= N ? 1 : 0);
+            const long col = gj - dj * N;
+            const int nlo = ti.n9[dj + 1], nmid = ti.n9[3 + dj + 1], nhi = ti.n9[6 + dj + 1];
+            #pragma unroll
+            for (int m = 0; m < 3; ++m)
             {
-                unsigned long long v;
-                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); } while (v < mesh.ready_value);
+                const int row = rr + 7 * m;
+                if (row < SX + 4)
+                {
+                    const int gi = i0 - 2 + row;
+                    const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
+                    const int nb = di < 0 ? nlo : (di > 0 ? nhi : nmid);
+                    const double* src = Uin + (long(nb) * N + (gi - di * N)) * N + col;
+                    cp_async_16(&T.P[buf][0][row][2 * cc], src);
+                    cp_async_16(&T.P[buf][1][row][2 * cc], src + FS);
+                    cp_async_16(&T.P[buf][2][row][2 * cc], src + 2 * FS);
+                }
             }
-            __syncwarp();
         }
-        const int4* ti4 = reinterpret_cast<const int4*>(tile_info + tile);
-        const int4 tiA = __ldg(ti4), tiB = __ldg(ti4 + 1), tiC = __ldg(ti4 + 2);
-        if (lane == 0)
-        {
-            int4* d = reinterpret_cast<int4*>(&T.info[buf]);
-            d[0] = tiA; d[1] = tiB; d[2] = tiC;
-            mbar_arrive_expect_tx(&T.mbar[buf], TMA_TILE_BYTES);
-        }
-        __syncwarp();
-        const int b = tiA.x, t = tile % tpb;
-        const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
-        const size_t FS = mesh.FS;
-        {
-            const double* xvg = mesh.xv + size_t(b) * (N + 1) + i0;
-            const double* yvg = mesh.yv + size_t(b) * (N + 1) + j0;
-            nx = lane <= SX ? __ldg(xvg + lane) : 0.0;
-            ny = __ldg(yvg + lane);
-            ny32 = lane == 0 ? __ldg(yvg + SY) : 0.0;
-        }
-        const int* n9 = T.info[buf].n9;
-        const int c0 = j0 == 0 ? 0 : j0 - 2, c1 = j0 + SY == N ? N : j0 + SY + 2;      // the row's columns inside the tile's own block column
-        const int dcol = c0 - (j0 - 2);
-        const unsigned main_bytes = unsigned(c1 - c0) * sizeof(double);
-        #pragma unroll
-        for (int idx = lane; idx < 3 * (SX + 4); idx += 32)
-        {
-            const int f = idx / (SX + 4), row = idx - f * (SX + 4);
-            const int gi = i0 - 2 + row;
-            const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
-            const long ii = gi - di * N;
-            const double* field = Uin + f * FS;
-            double* drow = &T.P[buf][f][row][0];
-            bulk_copy_g2s(drow + dcol, field + (long(n9[(di + 1) * 3 + 1]) * N + ii) * N + c0, main_bytes, &T.mbar[buf]);
-            if (j0 == 0)      bulk_copy_g2s(drow,          field + (long(n9[(di + 1) * 3 + 0]) * N + ii) * N + (N - 2), 16u, &T.mbar[buf]);
-            if (j0 + SY == N) bulk_copy_g2s(drow + SY + 2, field + (long(n9[(di + 1) * 3 + 2]) * N + ii) * N,           16u, &T.mbar[buf]);
-        }
+        cp_async_commit();
     }
 
-    /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX; yd[k] = T.y2c[k][lj] */
+    /** multi-GPU: tiles of blocks with ghost neighbours may only be fetched once the guard-zone unpack has finished */
+    __device__ __forceinline__ void wait_for_ghosts(const mesh_dev_t& mesh)
+    {
+        if (threadIdx.x == 0)
+        {
+            unsigned long long v;
+            do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); } while (v < mesh.ready_value);
+        }
+        __syncthreads();
+    }
+
+    /** What the two low faces of a cell need from one of the three cells around them: primitives, the doubled PLM differences
+     *  along the face normal, and the viscous combinations D1 = dx ux - dy uy, D2 = dx uy + dy ux (doubled, un-divided). */
+    struct face_cell_t { double p[3], g[3], d1, d2; };
+
+    /** cell (li, lj) of the tile as the x-faces see it (AXIS 0: differences along x) or as the y-faces see it (AXIS 1) */
+    template<int AXIS>
+    __device__ __forceinline__ face_cell_t load_face_cell(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], int li, int lj)
+    {
+        face_cell_t c;
+        #pragma unroll
+        for (int q = 0; q < 3; ++q) { c.p[q] = P[q][li + 2][lj + 2]; c.g[q] = T.G[3 * AXIS + q][li + 1][lj + 1]; }
+        const double gx_vx = AXIS == 0 ? c.g[1] : T.G[1][li + 1][lj + 1], gx_vy = AXIS == 0 ? c.g[2] : T.G[2][li + 1][lj + 1];
+        const double gy_vx = AXIS == 1 ? c.g[1] : T.G[4][li + 1][lj + 1], gy_vy = AXIS == 1 ? c.g[2] : T.G[5][li + 1][lj + 1];
+        c.d1 = gx_vx - gy_vy;
+        c.d2 = gx_vy + gy_vx;
+        return c;
+    }
+
+    /** cs2, cs and the viscous coefficient at a face from the tabulated squared distances */
+    template<bool FAST>
+    __device__ __forceinline__ eos_face_t tma_eos(const model_t& model, const stage_t& S, const strip_consts_t& C, double cvis, double d1, double d2, double q2)
+    {
+        eos_face_t e;
+        if (FAST) e = eos_face_fast(C, d1, d2, q2);
+        else { const eos_t g = eos_from_distances<false>(model, S, d1, d2, q2); e.cs2 = g.cs2; e.cs = g.cs; e.mu_coef = cvis * g.nu; }
+        return e;
+    }
+
+    /** face between the cells l (low side) and r along AXIS: intercell_flux_u (scheme.cpp:268-293) */
+    template<int AXIS>
+    __device__ __forceinline__ void tma_face(const eos_face_t& e, const face_cell_t& l, const face_cell_t& r, double F[3])
+    {
+        const prim_t L = {fma(l.g[0], 0.25, l.p[0]), fma(l.g[1], 0.25, l.p[1]), fma(l.g[2], 0.25, l.p[2])};
+        const prim_t R = {fma(r.g[0], -0.25, r.p[0]), fma(r.g[1], -0.25, r.p[1]), fma(r.g[2], -0.25, r.p[2])};
+        hlle_viscous_core<AXIS>(e.cs2, e.cs, e.mu_coef, L, R, l.d1 + r.d1, l.d2 + r.d2, F);
+    }
+
+    /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX; yd[k] = T.y2c[k][lj] (tile-boundary faces: nothing to reuse) */
     template<bool FAST>
     __device__ __forceinline__ void tma_x_face(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
         const strip_consts_t& C, double cvis, const double yd[3], int li, int lj, double F[3])
     {
-        const double d1 = T.x2v[0][li] + yd[0], d2 = T.x2v[1][li] + yd[1], q2 = T.x2v[2][li] + yd[2];
-        eos_face_t e;
-        if (FAST) e = eos_face_fast(C, d1, d2, q2);
-        else { const eos_t g = eos_from_distances<false>(model, S, d1, d2, q2); e.cs2 = g.cs2; e.cs = g.cs; e.mu_coef = cvis * g.nu; }
-        const prim_t L = {fma(T.G[0][li][lj + 1], 0.25, P[0][li + 1][lj + 2]), fma(T.G[1][li][lj + 1], 0.25, P[1][li + 1][lj + 2]), fma(T.G[2][li][lj + 1], 0.25, P[2][li + 1][lj + 2])};
-        const prim_t R = {fma(T.G[0][li + 1][lj + 1], -0.25, P[0][li + 2][lj + 2]), fma(T.G[1][li + 1][lj + 1], -0.25, P[1][li + 2][lj + 2]), fma(T.G[2][li + 1][lj + 1], -0.25, P[2][li + 2][lj + 2])};
-        hlle_viscous_core<0>(e.cs2, e.cs, e.mu_coef, L, R,
-            T.G[1][li][lj + 1] + T.G[1][li + 1][lj + 1], T.G[2][li][lj + 1] + T.G[2][li + 1][lj + 1],
-            T.G[4][li][lj + 1] + T.G[4][li + 1][lj + 1], T.G[5][li][lj + 1] + T.G[5][li + 1][lj + 1], F);
+        const eos_face_t e = tma_eos<FAST>(model, S, C, cvis, T.x2v[0][li] + yd[0], T.x2v[1][li] + yd[1], T.x2v[2][li] + yd[2]);
+        tma_face<0>(e, load_face_cell<0>(T, P, li - 1, lj), load_face_cell<0>(T, P, li, lj), F);
     }
 
     /** y-face between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= SY; yd[k] = T.y2v[k][lj] */
@@ -157,15 +160,180 @@ namespace m3b { namespace dev { namespace
     __device__ __forceinline__ void tma_y_face(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
         const strip_consts_t& C, double cvis, const double yd[3], int li, int lj, double F[3])
     {
-        const double d1 = T.x2c[0][li] + yd[0], d2 = T.x2c[1][li] + yd[1], q2 = T.x2c[2][li] + yd[2];
-        eos_face_t e;
-        if (FAST) e = eos_face_fast(C, d1, d2, q2);
-        else { const eos_t g = eos_from_distances<false>(model, S, d1, d2, q2); e.cs2 = g.cs2; e.cs = g.cs; e.mu_coef = cvis * g.nu; }
-        const prim_t L = {fma(T.G[3][li + 1][lj], 0.25, P[0][li + 2][lj + 1]), fma(T.G[4][li + 1][lj], 0.25, P[1][li + 2][lj + 1]), fma(T.G[5][li + 1][lj], 0.25, P[2][li + 2][lj + 1])};
-        const prim_t R = {fma(T.G[3][li + 1][lj + 1], -0.25, P[0][li + 2][lj + 2]), fma(T.G[4][li + 1][lj + 1], -0.25, P[1][li + 2][lj + 2]), fma(T.G[5][li + 1][lj + 1], -0.25, P[2][li + 2][lj + 2])};
-        hlle_viscous_core<1>(e.cs2, e.cs, e.mu_coef, L, R,
-            T.G[4][li + 1][lj] + T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj] + T.G[5][li + 1][lj + 1],
-            T.G[1][li + 1][lj] + T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj] + T.G[2][li + 1][lj + 1], F);
+        const eos_face_t e = tma_eos<FAST>(model, S, C, cvis, T.x2c[0][li] + yd[0], T.x2c[1][li] + yd[1], T.x2c[2][li] + yd[2]);
+        tma_face<1>(e, load_face_cell<1>(T, P, li, lj - 1), load_face_cell<1>(T, P, li, lj), F);
+    }
+
+    /**
+     * Both low faces of cell (li, lj): the cell itself is read once for the two of them, and the cell above comes from the
+     * row before in registers (`up` in, this cell out) -- 17 shared-memory loads per cell instead of 32.
+     */
+    template<bool FAST>
+    __device__ __forceinline__ void tma_cell_faces(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
+        const strip_consts_t& C, double cvis, const double ydc[3], const double ydv[3], int li, int lj, face_cell_t& up, double Fx[3], double Fy[3])
+    {
+        const eos_face_t ex = tma_eos<FAST>(model, S, C, cvis, T.x2v[0][li] + ydc[0], T.x2v[1][li] + ydc[1], T.x2v[2][li] + ydc[2]);
+        const eos_face_t ey = tma_eos<FAST>(model, S, C, cvis, T.x2c[0][li] + ydv[0], T.x2c[1][li] + ydv[1], T.x2c[2][li] + ydv[2]);
+        // this cell for both faces: primitives once, all six differences once
+        face_cell_t cx, cy;
+        #pragma unroll
+        for (int q = 0; q < 3; ++q) { cx.p[q] = cy.p[q] = P[q][li + 2][lj + 2]; cx.g[q] = T.G[q][li + 1][lj + 1]; cy.g[q] = T.G[3 + q][li + 1][lj + 1]; }
+        cx.d1 = cy.d1 = cx.g[1] - cy.g[2];
+        cx.d2 = cy.d2 = cx.g[2] + cy.g[1];
+        tma_face<0>(ex, up, cx, Fx);
+        tma_face<1>(ey, load_face_cell<1>(T, P, li, lj - 1), cy, Fy);
+        up = cx;
+    }
+
+    /** what tma_rows needs to know about the tile */
+    struct rows_args_t
+    {
+        const double (*P)[SX + 4][SY + 4];
+        double dt_over_h, cvis, yc, dy1, dy2;
+        int b, i0, j0, N;
+        size_t FS;
+        const double* __restrict__ Uin; const double* __restrict__ Un; double* __restrict__ Uout;
+        const double* __restrict__ U0; const double* __restrict__ BR;
+        fail_dev_t* fail;
+    };
+
+    /**
+     * Phases 2 + 3 of a tile for one warp: the faces of its strip of 4 rows and the update of its cells (block_update_u,
+     * scheme.cpp:568-587), software-pipelined down the strip.  SINK: some cell of the tile lies within the sinks' reach
+     * (warp-uniform, decided per tile); has_buffer: the buffer-zone rate is non-zero somewhere in the tile (else its inputs are not loaded).  Contains ONE __syncthreads.
+     */
+    template<bool FAST, int MODE, bool SINK>
+    __device__ __forceinline__ void tma_rows(tma_smem_t& T, const model_t& model, const stage_t& S, const strip_consts_t& C, const rows_args_t& A,
+        bool has_buffer, bool combine, bool compute_dt, strip_sums_t& sums, double& amax)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int li0 = STRIP * warp, lj = lane, N = A.N;
+        const size_t FS = A.FS;
+        const double yc = A.yc, dy1 = A.dy1, dy2 = A.dy2, cvis = A.cvis, dt_over_h = A.dt_over_h;
+        const double ydc[3] = {T.y2c[0][lj], T.y2c[1][lj], T.y2c[2][lj]};      // x-faces and cell centres share the column's y-part
+        const double ydv[3] = {T.y2v[0][lj], T.y2v[1][lj], T.y2v[2][lj]};
+        const size_t c0 = (size_t(A.b) * N + (A.i0 + li0)) * N + (A.j0 + lj);
+        unsigned negative = 0;          // bit r: the new density of strip row r is negative (its value waits in T.negbuf)
+
+        auto update_cell = [&] (int r, const double* u, const double* u0, double br, const double* un,
+                                const double* FxLo, const double* FxHi, const double* FyLo)
+        {
+            const int li = li0 + r;
+            const size_t c = c0 + size_t(r) * N;
+            double hy[3];
+            #pragma unroll
+            for (int q = 0; q < 3; ++q)
+            {
+                double up = shfl_down1(FyLo[q]);        // the low-y face of lane + 1 is this cell's high-y face
+                hy[q] = lane == 31 ? T.YB[q][li] : up;
+            }
+            const double x = T.xc[li];
+            // The cell's state reaches the source terms through a select on a flux of this row (true for every finite flux):
+            // without it ptxas hoists the source terms to just behind the loads that deliver u, u0 and br, where the in-order
+            // warp then sits on the long scoreboard with a whole row of independent face arithmetic queued behind it.
+            const bool late = __double2hiint(FxHi[0]) != 0x7ff80001;
+            const double us = late ? u[0] : 0.0, upx = late ? u[1] : 0.0, upy = late ? u[2] : 0.0;
+            double acc[3], y1, y2;
+            source_terms_strip<FAST>(model, C, x, yc, T.dxc[0][li], dy1, T.dxc[1][li], dy2, T.x2c[0][li] + ydc[0], T.x2c[1][li] + ydc[1],
+                SINK, true, us, upx, upy, u0[0], u0[1], u0[2], br, acc, sums, y1, y2, T.sinks[warp]);
+
+            double n0 = fma(-((FxHi[0] - FxLo[0]) + (hy[0] - FyLo[0])), dt_over_h, acc[0]);
+            double n1 = fma(-((FxHi[1] - FxLo[1]) + (hy[1] - FyLo[1])), dt_over_h, acc[1]);
+            double n2 = fma(-((FxHi[2] - FxLo[2]) + (hy[2] - FyLo[2])), dt_over_h, acc[2]);
+
+#ifndef M3B_HOT_PATH_ONLY
+            // validate_u (scheme.cpp:726-752) without a branch in the strip: remember the value, report after the last row
+            const bool neg = __double2hiint(n0) < 0;
+            if (neg) T.negbuf[warp][r][lane] = n0;
+            negative |= neg ? 1u << r : 0u;
+#endif
+            if (combine)
+            {
+                const double w = 1.0 - S.rk_b0;         // (the loaded un only meets the late value: nothing to hoist)
+                n0 = fma(un[0], S.rk_b0, n0 * w);
+                n1 = fma(un[1], S.rk_b0, n1 * w);
+                n2 = fma(un[2], S.rk_b0, n2 * w);
+            }
+            A.Uout[c] = n0; A.Uout[FS + c] = n1; A.Uout[2 * FS + c] = n2;
+
+            if (compute_dt)
+                amax = dmax(amax, FAST ? max_wavespeed_fast(C, y1, y2, n0, n1, n2) : max_wavespeed<false>(model, S, x, yc, y1, y2, n0, n1, n2));
+        };
+        auto load_cell = [&] (int r, double* u, double* u0, double& br)
+        {
+            // volatile: issued here, a row of face arithmetic before their use
+            const size_t c = c0 + size_t(r) * N;
+            auto ldv = [] (const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; };
+            u[0] = ldv(A.Uin + c); u[1] = ldv(A.Uin + FS + c); u[2] = ldv(A.Uin + 2 * FS + c);
+            br = 0.0; u0[0] = u0[1] = u0[2] = 0.0;
+            if (has_buffer) { br = ldv(A.BR + c); u0[0] = ldv(A.U0 + c); u0[1] = ldv(A.U0 + FS + c); u0[2] = ldv(A.U0 + 2 * FS + c); }
+        };
+        // the step-start state for the RK combination only meets the finished update: one register set, asked for one row of
+        // faces ahead of its use
+        auto load_un = [&] (int r, double* un)
+        {
+            const size_t c = c0 + size_t(r) * N;
+            auto ldv = [] (const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; };
+            un[0] = un[1] = un[2] = 0.0;
+            if (combine) { un[0] = ldv(A.Un + c); un[1] = ldv(A.Un + FS + c); un[2] = ldv(A.Un + 2 * FS + c); }
+        };
+
+        // the update inputs of row r are asked for BEFORE the faces of row r and used after the faces of row r + 1
+        // (two register sets, alternating): at least a row of face arithmetic lies between every load and its use,
+        // also for the last row of the strip
+        double u[2][3], u0[2][3], un[3], un_last[3], br[2];
+        load_cell(0, u[0], u0[0], br[0]);        // in flight during the prologue
+
+        // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the faces of strip
+        // row 0, whose x-flux is also the high-x flux of the strip below
+        if (warp == 0)
+        {
+            double F[3];
+            tma_x_face<FAST>(T, A.P, model, S, C, cvis, ydc, SX, lj, F);
+            T.XB[0][3][lj] = F[0]; T.XB[1][3][lj] = F[1]; T.XB[2][3][lj] = F[2];
+        }
+        else if (warp == 1 && lane < SX)
+        {
+            double F[3];
+            const double ydhi[3] = {T.y2v[0][SY], T.y2v[1][SY], T.y2v[2][SY]};
+            tma_y_face<FAST>(T, A.P, model, S, C, cvis, ydhi, lane, SY, F);
+            T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
+        }
+        double FxLo[3], FyLo[3];
+        face_cell_t up = load_face_cell<0>(T, A.P, li0 - 1, lj);        // the cell above the strip, then each row's cell for the row below
+        tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0, lj, up, FxLo, FyLo);
+
+        if (warp > 0) { T.XB[0][warp - 1][lj] = FxLo[0]; T.XB[1][warp - 1][lj] = FxLo[1]; T.XB[2][warp - 1][lj] = FxLo[2]; }
+        __syncthreads();
+
+        #pragma unroll
+        for (int r = 1; r < STRIP; ++r)
+        {
+            double FxNew[3], FyNew[3];
+            load_cell(r, u[r & 1], u0[r & 1], br[r & 1]);
+            load_un(r - 1, un);
+            if (r == STRIP - 1) load_un(r, un_last);     // (the last row has no faces of a next row to hide behind)
+            tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0 + r, lj, up, FxNew, FyNew);
+            update_cell(r - 1, u[(r - 1) & 1], u0[(r - 1) & 1], br[(r - 1) & 1], un, FxLo, FxNew, FyLo);
+            #pragma unroll
+            for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
+        }
+        {
+            double FxHi[3];
+            FxHi[0] = T.XB[0][warp][lj]; FxHi[1] = T.XB[1][warp][lj]; FxHi[2] = T.XB[2][warp][lj];
+            update_cell(STRIP - 1, u[(STRIP - 1) & 1], u0[(STRIP - 1) & 1], br[(STRIP - 1) & 1], un_last, FxLo, FxHi, FyLo);
+        }
+#ifndef M3B_HOT_PATH_ONLY
+        if (negative)
+        {
+            for (int r = 0; r < STRIP; ++r)
+                if (negative >> r & 1)
+                {
+                    const double v = T.negbuf[warp][r][lane];
+                    if (v < 0.0) report_negative(A.fail, A.b, (A.i0 + li0 + r) * N + A.j0 + lj, v);      // (not -0.0)
+                }
+        }
+#endif
     }
 
     template<int MIN_CTAS, int NB, bool FAST, int MODE>
@@ -187,23 +355,26 @@ namespace m3b { namespace dev { namespace
         const double* __restrict__ U0 = mesh.U0;
         const double* __restrict__ BR = mesh.br;
 
-        if (threadIdx.x == 0)
-        {
-            mbar_init(&T.mbar[0], 1);
-            mbar_init(&T.mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-
+        // ordinal k of this CTA's tiles <-> tile blockIdx.x + k gridDim.x; record ring slot k % 3, P half k & 1
         int tile = blockIdx.x;
-        double nx = 0.0, ny = 0.0, ny32 = 0.0;
-        if (warp == 0 && tile < num_tiles)
+        if (tile >= num_tiles) return;
+        if (threadIdx.x < 6)
         {
-            tma_issue_tile(T, mesh, tile_info, Uin, tile, 0, N, tiles_y, tpb, lane, nx, ny, ny32);
-            if (lane <= SX) T.cx[0][lane] = nx;
-            T.cy[0][lane] = ny;
-            if (lane == 0) T.cy[0][SY] = ny32;
+            const int which = threadIdx.x / 3, part = threadIdx.x % 3;
+            const int tl = tile + which * int(gridDim.x);
+            if (tl < num_tiles) reinterpret_cast<int4*>(&T.info[which])[part] = __ldg(reinterpret_cast<const int4*>(tile_info + tl) + part);
+        }
+        if (tile >= mesh.first_wait_cta) wait_for_ghosts(mesh); else __syncthreads();
+        stage_tile_async(T, T.info[0], Uin, FS, tile % tpb, 0, N, tiles_y);
+        if (warp == 0)
+        {
+            const int b0 = T.info[0].b, t0 = tile % tpb;
+            const double* xvg = mesh.xv + size_t(b0) * (N + 1) + (t0 / tiles_y) * SX;
+            const double* yvg = mesh.yv + size_t(b0) * (N + 1) + (t0 % tiles_y) * SY;
+            if (lane <= SX) T.cx[0][lane] = __ldg(xvg + lane);
+            T.cy[0][lane] = __ldg(yvg + lane);
+            if (lane == 0) T.cy[0][SY] = __ldg(yvg + SY);
+            if (lane == 1) { T.hh[0][0] = __ldg(mesh.spacing + b0); T.hh[0][1] = __ldg(mesh.inv_spacing + b0); }
         }
         __syncthreads();
 
@@ -212,18 +383,33 @@ namespace m3b { namespace dev { namespace
             const int buf = k & 1;
             const int next = tile + int(gridDim.x);
             const bool has_next = next < num_tiles;
-            // the other half was released by the barrier that ended tile k - 1: refill it while this tile is computed
-            if (warp == 0 && has_next)
+            const tile_info_t& tin = T.info[(k + 1) % 3];
+            double nx = 0.0, ny = 0.0, ny32 = 0.0;      // warp 0: vertex coordinates of the next tile, stored when they have arrived
+            int4 rec = make_int4(0, 0, 0, 0);           // threads 32-34: the record of the tile after the next
+            // the other half of P was released by the barrier that ended tile k - 1: refill it while this tile is computed
+            if (has_next)
             {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                tma_issue_tile(T, mesh, tile_info, Uin, next, buf ^ 1, N, tiles_y, tpb, lane, nx, ny, ny32);
+                if (next >= mesh.first_wait_cta) wait_for_ghosts(mesh);
+                const int tn = next % tpb;
+                stage_tile_async(T, tin, Uin, FS, tn, buf ^ 1, N, tiles_y);
+                if (warp == 0)
+                {
+                    const double* xvg = mesh.xv + size_t(tin.b) * (N + 1) + (tn / tiles_y) * SX;
+                    const double* yvg = mesh.yv + size_t(tin.b) * (N + 1) + (tn % tiles_y) * SY;
+                    nx = lane <= SX ? __ldg(xvg + lane) : 0.0;
+                    ny = __ldg(yvg + lane);
+                    ny32 = lane == 0 ? __ldg(yvg + SY) : (lane == 1 ? __ldg(mesh.spacing + tin.b) : (lane == 2 ? __ldg(mesh.inv_spacing + tin.b) : 0.0));
+                }
+                else if (warp == 1 && lane < 3 && next + int(gridDim.x) < num_tiles)
+                    rec = __ldg(reinterpret_cast<const int4*>(tile_info + next + gridDim.x) + lane);
             }
+            else cp_async_commit();     // (an empty group keeps the wait below uniform)
 
-            const int b = T.info[buf].b, flags = T.info[buf].flags;
+            const int b = T.info[k % 3].b, flags = T.info[k % 3].flags;
             const int t = tile % tpb;
             const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
             const bool has_buffer = flags & 1;
-            const double h = mesh.spacing[b], inv_h = mesh.inv_spacing[b];
+            const double h = T.hh[buf][0], inv_h = T.hh[buf][1];
             const double cvis = 0.125 * inv_h;      // 0.5 nu x face average 0.5 x (1 / 2h) of the doubled differences
 
             // the update phase's inputs are first touched several us from now: pull their lines into L2 already
@@ -299,8 +485,9 @@ namespace m3b { namespace dev { namespace
                 }
             }
 
-            // ------------------------------------------------------------------ phase 0: wait for the tile, primitives in place
-            mbar_wait(&T.mbar[buf], (k >> 1) & 1);
+            // ------------------------------------------------------------------ phase 0: this thread's chunks of the tile, primitives in place
+            // (all but the newest group: the chunks asked for during tile k - 1)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
             double (*P)[SX + 4][SY + 4] = T.P[buf];
             {
                 // 20 rows of 18 sixteen-byte chunks (two cells in y): thread <-> (row rr + 7 m, chunk cc), m = 0, 1, 2
@@ -371,116 +558,30 @@ namespace m3b { namespace dev { namespace
                     if (lane <= SX) T.cx[buf ^ 1][lane] = nx;
                     T.cy[buf ^ 1][lane] = ny;
                     if (lane == 0) T.cy[buf ^ 1][SY] = ny32;
+                    if (lane == 1 || lane == 2) T.hh[buf ^ 1][lane - 1] = ny32;
                 }
+                else if (warp == 1 && lane < 3 && has_next && next + int(gridDim.x) < num_tiles)
+                    reinterpret_cast<int4*>(&T.info[(k + 2) % 3])[lane] = rec;
             }
             __syncthreads();
 
             // ------------------------------------------------------------------ phases 2 + 3: faces, update
-            const int li0 = STRIP * warp, lj = lane;
-            const double dt_over_h = S.dt * inv_h;
-            const double yc = 0.5 * (T.cy[buf][lj] + T.cy[buf][lj + 1]);
-            const double dy1 = yc - S.y1, dy2 = yc - S.y2;
-            const double ydc[3] = {T.y2c[0][lj], T.y2c[1][lj], T.y2c[2][lj]};      // x-faces and cell centres share the column's y-part
-            const double ydv[3] = {T.y2v[0][lj], T.y2v[1][lj], T.y2v[2][lj]};
-#ifdef M3B_HOT_PATH_ONLY        // tools/hot_path_count.sh: the instruction census of the common path (no sink within reach, no negative density)
-            const bool near_sink = false;
-#else
-            const bool near_sink = T.near_sink != 0;
-#endif
-            const size_t c0 = (size_t(b) * N + (i0 + li0)) * N + (j0 + lj);
-
             strip_sums_t sums = {{0.0, 0.0}, {0.0, 0.0}, 0.0, 0.0, 0.0};
             double amax = 0.0;                              // largest signal speed of the updated cells
-
-            // Update of the cell in strip row r from its four face fluxes (block_update_u, scheme.cpp:568-587).
-            auto update_cell = [&] (int r, const double* u, const double* u0, double br, const double* un,
-                                    const double* FxLo, const double* FxHi, const double* FyLo)
+            const double yc = 0.5 * (T.cy[buf][lane] + T.cy[buf][lane + 1]);
+            const double dy1 = yc - S.y1, dy2 = yc - S.y2;
             {
-                const int li = li0 + r;
-                const size_t c = c0 + size_t(r) * N;
-                double hy[3];
-                #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                {
-                    double up = shfl_down1(FyLo[q]);        // the low-y face of lane + 1 is this cell's high-y face
-                    hy[q] = lane == 31 ? T.YB[q][li] : up;
-                }
-                const double x = T.xc[li];
-                double acc[3], y1, y2;
-                source_terms_strip<FAST>(model, C, x, yc, T.dxc[0][li], dy1, T.dxc[1][li], dy2, T.x2c[0][li] + ydc[0], T.x2c[1][li] + ydc[1],
-                    near_sink, has_buffer, u[0], u[1], u[2], u0[0], u0[1], u0[2], br, acc, sums, y1, y2, T.sinks[warp]);
-
-                double n0 = fma(-((FxHi[0] - FxLo[0]) + (hy[0] - FyLo[0])), dt_over_h, acc[0]);
-                double n1 = fma(-((FxHi[1] - FxLo[1]) + (hy[1] - FyLo[1])), dt_over_h, acc[1]);
-                double n2 = fma(-((FxHi[2] - FxLo[2]) + (hy[2] - FyLo[2])), dt_over_h, acc[2]);
-
-#ifndef M3B_HOT_PATH_ONLY
-                if (__double2hiint(n0) < 0) { if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0); }
+                const rows_args_t A = {P, S.dt * inv_h, cvis, yc, dy1, dy2, b, i0, j0, N, FS, Uin, Un, Uout, U0, BR, fail};
+                // one straight-line variant per (sink within reach, buffer zone) so that the common path has no branch: ptxas
+                // schedules inside basic blocks, and only an unbroken strip lets it overlap a row's update with the next row's faces
+#ifdef M3B_HOT_PATH_ONLY
+                tma_rows<FAST, MODE, false>(T, model, S, C, A, has_buffer, combine, compute_dt, sums, amax);
+#else
+                // (the buffer terms are not a variant: without a rate they add exact zeros, and a second copy of the strip would
+                // have to share the instruction cache with the first)
+                if (T.near_sink != 0) tma_rows<FAST, MODE, true>(T, model, S, C, A, has_buffer, combine, compute_dt, sums, amax);
+                else                  tma_rows<FAST, MODE, false>(T, model, S, C, A, has_buffer, combine, compute_dt, sums, amax);
 #endif
-
-                if (combine)
-                {
-                    const double w = 1.0 - S.rk_b0;
-                    n0 = un[0] * S.rk_b0 + n0 * w;
-                    n1 = un[1] * S.rk_b0 + n1 * w;
-                    n2 = un[2] * S.rk_b0 + n2 * w;
-                }
-                Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
-
-                if (compute_dt)
-                    amax = dmax(amax, FAST ? max_wavespeed_fast(C, y1, y2, n0, n1, n2) : max_wavespeed<false>(model, S, x, yc, y1, y2, n0, n1, n2));
-            };
-            auto load_cell = [&] (int r, double* u, double* u0, double& br, double* un)
-            {
-                // volatile: issued here, a whole iteration before their use
-                const size_t c = c0 + size_t(r) * N;
-                auto ldv = [] (const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; };
-                u[0] = ldv(Uin + c); u[1] = ldv(Uin + FS + c); u[2] = ldv(Uin + 2 * FS + c);
-                br = 0.0; u0[0] = u0[1] = u0[2] = 0.0; un[0] = un[1] = un[2] = 0.0;
-                if (has_buffer) { br = ldv(BR + c); u0[0] = ldv(U0 + c); u0[1] = ldv(U0 + FS + c); u0[2] = ldv(U0 + 2 * FS + c); }
-                if (combine) { un[0] = ldv(Un + c); un[1] = ldv(Un + FS + c); un[2] = ldv(Un + 2 * FS + c); }
-            };
-
-            double u[3], u0[3], un[3], br;
-            load_cell(0, u, u0, br, un);        // in flight during the prologue
-
-            // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the faces of strip
-            // row 0, whose x-flux is also the high-x flux of the strip below
-            if (warp == 0)
-            {
-                double F[3];
-                tma_x_face<FAST>(T, P, model, S, C, cvis, ydc, SX, lj, F);
-                T.XB[0][4][lj] = F[0]; T.XB[1][4][lj] = F[1]; T.XB[2][4][lj] = F[2];
-            }
-            else if (warp == 1 && lane < SX)
-            {
-                double F[3];
-                const double ydhi[3] = {T.y2v[0][SY], T.y2v[1][SY], T.y2v[2][SY]};
-                tma_y_face<FAST>(T, P, model, S, C, cvis, ydhi, lane, SY, F);
-                T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
-            }
-            double FxLo[3], FyLo[3];
-            tma_x_face<FAST>(T, P, model, S, C, cvis, ydc, li0, lj, FxLo);
-            tma_y_face<FAST>(T, P, model, S, C, cvis, ydv, li0, lj, FyLo);
-
-            if (warp > 0) { T.XB[0][warp][lj] = FxLo[0]; T.XB[1][warp][lj] = FxLo[1]; T.XB[2][warp][lj] = FxLo[2]; }
-            __syncthreads();
-
-            #pragma unroll
-            for (int r = 1; r < STRIP; ++r)
-            {
-                double FxNew[3], FyNew[3];
-                tma_x_face<FAST>(T, P, model, S, C, cvis, ydc, li0 + r, lj, FxNew);
-                tma_y_face<FAST>(T, P, model, S, C, cvis, ydv, li0 + r, lj, FyNew);
-                update_cell(r - 1, u, u0, br, un, FxLo, FxNew, FyLo);
-                load_cell(r, u, u0, br, un);
-                #pragma unroll
-                for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
-            }
-            {
-                double FxHi[3];
-                FxHi[0] = T.XB[0][warp + 1][lj]; FxHi[1] = T.XB[1][warp + 1][lj]; FxHi[2] = T.XB[2][warp + 1][lj];
-                update_cell(STRIP - 1, u, u0, br, un, FxLo, FxHi, FyLo);
             }
 
             // ------------------------------------------------------------------ fold the CTA's sums

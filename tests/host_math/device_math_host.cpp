@@ -12,8 +12,8 @@ extern "C" {
 void dm_hlle(const double* pl, const double* pr, double cs2, int axis, double* F)
 {
     prim_t L = {pl[0], pl[1], pl[2]}, R = {pr[0], pr[1], pr[2]};
-    if (axis == 0) hlle_viscous_core<0>(cs2, std::sqrt(cs2), 0.0, L, R, 0, 0, 0, 0, F);
-    else           hlle_viscous_core<1>(cs2, std::sqrt(cs2), 0.0, L, R, 0, 0, 0, 0, F);
+    if (axis == 0) hlle_viscous_core<0>(cs2, std::sqrt(cs2), 0.0, L, R, 0, 0, F);
+    else           hlle_viscous_core<1>(cs2, std::sqrt(cs2), 0.0, L, R, 0, 0, F);
 }
 
 // intercell flux with viscosity through face_flux (physical gradients: half_step = 0.5 h, visc_scale = 1)
