@@ -172,6 +172,12 @@ uint64_t    m3b_kernel_launches(const m3b_solver_t* s);               /* kernels
 /* CUDA-event timing of the fused stage kernel on its own stream (for the roofline) */
 void        m3b_stage_timing(m3b_solver_t* s, int enable);
 int         m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches);
+/* Several ranks, with stage timing on: out8 = { steps instrumented, us the compute stream waited for ghost blocks (interior
+ * blocks done -> blocks with ghost neighbours may start), us the step's last finish kernel waited for the other ranks'
+ * results, us from "stage input ready" to "ghost blocks unpacked" on the exchange stream, exchanges, bytes pushed, 0, 0 },
+ * totals since the last call.  M3B_ERROR on one rank.  (The reference has no counterpart: subprog_binary_scheme.cpp:132-142
+ * reads its neighbours through shared memory.) */
+int         m3b_exchange_timing(m3b_solver_t* s, double* out8);
 /* launch on a caller-owned cudaStream_t from now on (NULL: back to the solver's own stream) */
 int         m3b_set_stream(m3b_solver_t* s, void* cuda_stream);
 void        m3b_synchronize(m3b_solver_t* s);

@@ -80,6 +80,7 @@ def load_library():
     for name in ("num_global_blocks", "first_block", "num_local_blocks"):
         getattr(L, "m3b_" + name).argtypes = [vp]
     L.m3b_num_owned_cells.argtypes = [vp]
+    L.m3b_exchange_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.m3b_num_owned_cells.restype = C.c_int64
     L.m3b_local_to_global.argtypes = [vp, ip]
     L.m3b_halo_plan_size.argtypes = [vp, C.c_int, C.c_int]
@@ -393,6 +394,28 @@ class Solver:
         ms, n = C.c_double(0.0), C.c_uint64(0)
         self._check(_lib.m3b_stage_timing_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
+
+    def exchange_timing(self):
+        """Device-clock instrumentation of the guard-zone / result exchange since the last call (multi-GPU): microseconds per
+        step that boundary tiles waited for ghost cells, that the result exchange waited for the slowest rank, and the achieved
+        NVLink rate of the guard-zone pushes.  Empty on one rank."""
+        a = np.zeros(8, dtype=np.float64)
+        if not hasattr(_lib, "m3b_exchange_timing") or _lib.m3b_exchange_timing(self._h, _dptr(a)) != 0:
+            return {}
+        steps = max(1.0, a[0])
+        out = {"steps_instrumented": int(a[0]), "result_exchange_us": a[2] / steps,
+               "clock": "%globaltimer inside the kernels (result exchange, fused guard-zone exchange) and CUDA events (split launch), rank 0"}
+        if a[7] > 0:
+            # fused exchange: every CTA of the stage kernel passes exchange_unpack once per stage (flag wait + its share of the unpack)
+            out["unpack_us_per_cta_visit"] = a[6] / a[7]
+            out["exposed_wait_us_per_step"] = 2.0 * a[6] / a[7]
+            out["how"] = "guard zones pushed and unpacked by the stage kernel itself (stage_tma: exchange_push / exchange_unpack)"
+        if a[4] > 0:
+            out["exposed_wait_us_per_step"] = a[1] / steps
+            out["push_to_unpacked_us_per_exchange"] = a[3] / a[4]
+            out["nvlink_gbs_achieved"] = a[5] / (a[3] * 1e-6) * 1e-9 if a[3] > 0 else None
+            out["how"] = "halo_push / halo_wait_unpack on the exchange stream beside the interior launch, boundary launch behind them"
+        return out
 
     def set_stream(self, cuda_stream):
         """Launch on a caller-owned CUDA stream (an integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""

@@ -502,6 +502,29 @@ int m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches)
     });
 }
 
+int m3b_exchange_timing(m3b_solver_t* s, double* out8)
+{
+    return guarded(s, [&]
+    {
+        auto& d = s->solver->device();
+        if (d.exchange_transport() == 0) return M3B_ERROR;      // one rank: nothing to report
+        d.collect_stage_timing();
+        // [0] steps, [1] exposed wait us, [2] result wait us, [3] exchange us, [4] exchanges, [5] bytes pushed, [6..7] reserved
+        out8[0] = double(d.result_waits_timed);
+        out8[1] = d.exposed_wait_us_total;
+        out8[2] = d.result_wait_us_total;
+        out8[3] = d.exchange_us_total;
+        out8[4] = double(d.exchanges_timed);
+        out8[5] = double(d.halo_bytes_per_exchange()) * double(d.exchanges_timed);
+        out8[6] = d.unpack_cta_wait_us_total;
+        out8[7] = double(d.unpack_cta_waits);
+        d.unpack_cta_wait_us_total = 0.0; d.unpack_cta_waits = 0;
+        d.exposed_wait_us_total = d.result_wait_us_total = d.exchange_us_total = 0.0;
+        d.exchanges_timed = d.result_waits_timed = 0;
+        return M3B_OK;
+    });
+}
+
 int m3b_set_stream(m3b_solver_t* s, void* cuda_stream)
 {
     return guarded(s, [&] { s->solver->device().set_stream(cuda_stream); return M3B_OK; });

@@ -135,6 +135,14 @@ namespace m3b
         double stage_kernel_ms_total() const { return stage_ms_total; }
         std::uint64_t stage_kernel_launches() const { return stage_timed_launches; }
         void collect_stage_timing();
+        /** Multi-GPU side of the stage timing (bench.py `exchange`): microseconds between "stage input ready" and "ghost blocks
+         *  unpacked" on the exchange stream (push over NVLink + wait for the neighbours' pushes + unpack); what the compute stream
+         *  saw of it (interior blocks done -> blocks with ghost neighbours may start); and the time the last finish_stage CTA of a
+         *  step waited for the other ranks' stage results. */
+        double exchange_us_total = 0.0, exposed_wait_us_total = 0.0, result_wait_us_total = 0.0;
+        std::uint64_t exchanges_timed = 0, result_waits_timed = 0;
+        double unpack_cta_wait_us_total = 0.0;      // fused exchange: time CTAs of the stage kernel spent waiting for flags / unpacking
+        std::uint64_t unpack_cta_waits = 0;
 
         static constexpr int num_slots = 8;
         static constexpr int first_async_slot = 2;      // slots 2..5: two steps in flight x two stages

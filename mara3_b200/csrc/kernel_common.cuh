@@ -79,6 +79,63 @@ namespace m3b { namespace dev
         return __shfl_down_sync(0xffffffffu, v, 1);
     }
 
+    // ---- multi-GPU transport records (peer memory over NVLink: kernels.cu sets the mailboxes up, see set_communicator)
+    constexpr int MAX_PEERS = 16;
+
+    /** Mapped (CUDA IPC) pointers into every rank's mailbox; index = rank.  [me] points at the local mailbox. */
+    struct peer_table_t
+    {
+        double* recv[MAX_PEERS][2];                     // guard-zone landing buffers, one per exchange parity
+        unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
+        stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
+        unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
+    };
+
+    __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
+    {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    }
+
+    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+
+
+    struct halo_entry_dev_t
+    {
+        int block;              // local block id
+        int i0, ni, j0, nj;     // cells [i0, i0 + ni) x [j0, j0 + nj)
+        int pad;
+        size_t offset;          // first double of this entry in the packed buffer (3 fields x ni x nj)
+    };
+
+
+    /**
+     * The guard-zone exchange of one stage, done by the persistent stage kernel itself (stage_tma.cuh): at its start every CTA
+     * stores its share of this rank's strips into the neighbours' landing buffers over NVLink and the last one raises this rank's
+     * flag there; the interior blocks are then updated; before the first block with ghost neighbours is fetched, the CTAs that
+     * get there first wait for the neighbours' flags and scatter the landed strips into the ghost blocks.  enabled = 0: no
+     * exchange in this launch.  counters: [parity][0] strips pushed, [1] next strip to unpack, [2] strips unpacked, [3] next strip to push; a launch
+     * zeroes the other set, which the previous fused launch used.
+     */
+    struct fused_exchange_t
+    {
+        int enabled;
+        const halo_entry_dev_t* push; int n_push;
+        const halo_entry_dev_t* recv; int n_recv;
+        peer_table_t peers;
+        int parity, me;                 // landing buffer of this exchange (exchange number & 1), this rank
+        int cset;                       // counter set of this launch (fused launch number & 1)
+        unsigned int dest_mask;
+        unsigned long long counter;
+        int* counters;                  // [2][4]
+        double* U;                      // the stage input, writable: the ghost blocks are filled in
+        unsigned long long* clock_words;    // stage timing: [2] ns CTAs spent waiting for neighbours' flags or for the unpack, [3] waits
+    };
+
     /** stage_tma.cu: one launch of the persistent TMA-staged stage kernel over `num_tiles` entries of `tile_info`. */
     struct stage_tma_launch_t
     {
@@ -96,6 +153,7 @@ namespace m3b { namespace dev
         bool fast;          // branch-free equation of state
         int stage_mode;     // 0: flags from stage_t, 1 / 2: first / last stage of an adaptive RK2 step
         int grid;           // resident CTAs
+        fused_exchange_t exchange;
     };
     void stage_tma_configure();
     void stage_tma_launch(const stage_tma_launch_t& a, cudaStream_t stream);

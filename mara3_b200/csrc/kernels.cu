@@ -818,29 +818,6 @@ namespace
     // =======================================================================
     // Peer-memory guard-zone exchange (NVLink loads / stores, no NCCL in the step loop)
     // =======================================================================
-    constexpr int MAX_PEERS = 16;
-
-    /** Mapped (CUDA IPC) pointers into every rank's mailbox; index = rank.  [me] points at the local mailbox. */
-    struct peer_table_t
-    {
-        double* recv[MAX_PEERS][2];                     // guard-zone landing buffers, one per exchange parity
-        unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
-        stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
-        unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
-    };
-
-    __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
-    {
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-    }
-
-    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p)
-    {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-        return v;
-    }
-
     /**
      * prepare_next for several ranks without NCCL (called by the >= 128 threads of one CTA): deliver this rank's
      * two stage results to every rank's mailbox, wait for everybody else's, fold them in rank order (every rank
@@ -848,7 +825,8 @@ namespace
      */
     __device__ void peer_prepare(const stage_result_t* __restrict__ local, const peer_table_t& peers, int me, int nranks,
         int slot_stride, int slot_a, int slot_b, unsigned long long counter,
-        const step_config_t& cfg, const stage_t* __restrict__ current_a, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
+        const step_config_t& cfg, const stage_t* __restrict__ current_a, stage_t* next_a, stage_t* next_b, stage_result_t* host_results,
+        unsigned long long* clock_words = nullptr)
     {
         __shared__ double dt_min_b;
         constexpr int words = sizeof(stage_result_t) / sizeof(double);
@@ -860,12 +838,22 @@ namespace
         }
         __threadfence_system();
         __syncthreads();
+        unsigned long long t_wait = 0;
+        if (threadIdx.x == 0 && clock_words) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait));
         if (threadIdx.x < nranks)
         {
             if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
             if (threadIdx.x != me) while (load_acquire_sys(peers.result_flag[me] + threadIdx.x) < counter) { }
         }
         __syncthreads();
+        if (threadIdx.x == 0 && clock_words)
+        {
+            // how long this rank waited for the slowest rank's results (bench.py: exchange.result_exchange_us)
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            clock_words[0] += t1 - t_wait;
+            clock_words[1] += 1;
+        }
 
         const int k = threadIdx.x;
         if (k < 2)
@@ -910,6 +898,7 @@ namespace
         stage_result_t* host_results;
         int me, nranks, slot_stride, slot_a, slot_b;
         unsigned long long counter;
+        unsigned long long* clock_words;       // stage timing: ns waited for the other ranks' results, calls
     };
 
     /**
@@ -1040,7 +1029,7 @@ namespace
             __threadfence();            // this launch's own result (written above) is read back through global memory
             __syncthreads();
             peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
-                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results);
+                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results, prep.clock_words);
             return;
         }
 
@@ -1176,7 +1165,7 @@ namespace
             __threadfence();
             __syncthreads();
             peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
-                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results);
+                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results, prep.clock_words);
             return;
         }
         if (tid == 96 || tid == 97)
@@ -1228,14 +1217,6 @@ namespace
     }
 
     /** One strip / corner of a block in the guard-zone exchange between ranks (partition.hpp). */
-    struct halo_entry_dev_t
-    {
-        int block;              // local block id
-        int i0, ni, j0, nj;     // cells [i0, i0 + ni) x [j0, j0 + nj)
-        int pad;
-        size_t offset;          // first double of this entry in the packed buffer (3 fields x ni x nj)
-    };
-
     /** Gather (pack = 1) the listed strips of U into the send buffer, or scatter (pack = 0) the receive
      *  buffer into the ghost blocks: the device side of extend() across GPUs (scheme.cpp:132-142). */
     __global__ void __launch_bounds__(128) halo_copy(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
@@ -1457,6 +1438,13 @@ struct device_solver_t::impl_t
     stage_result_t* d_results = nullptr;    // [num_slots]
     std::vector<void*> owned;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    // stage timing on several ranks: [input ready -> ghosts unpacked] on the exchange stream, and what of it the compute stream
+    // sees: [interior blocks done -> blocks with ghost neighbours may start]
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exchange_events, gap_events;
+    unsigned long long* d_exchange_clock = nullptr;     // [0] ns spent in peer_prepare's wait for the other ranks, [1] calls, [2] ns CTAs of stage_tma spent in exchange_unpack, [3] calls
+    int* d_fused_counters = nullptr;                    // fused_exchange_t::counters
+    unsigned long long fused_launches = 0;
+    bool fused_exchange = true;                         // M3B_FUSED_EXCHANGE=0: halo_push / halo_wait_unpack kernels beside a split stage launch
     std::vector<cudaEvent_t> event_pool;
     size_t fused_smem = 0;
     int sm_count = 148;
@@ -1786,6 +1774,11 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaHostGetDevicePointer(&impl->d_results, host_results, 0));
     M3B_CUDA(cudaMemset(impl->d_fail, 0, num_slots * sizeof(fail_dev_t)));
     M3B_CUDA(cudaMalloc(&impl->d_gradients, std::max<size_t>(1, 6 * impl->mesh.GS) * sizeof(double)));
+    M3B_CUDA(cudaMalloc(&impl->d_exchange_clock, 4 * sizeof(unsigned long long)));
+    M3B_CUDA(cudaMemset(impl->d_exchange_clock, 0, 4 * sizeof(unsigned long long)));
+    M3B_CUDA(cudaMalloc(&impl->d_fused_counters, 8 * sizeof(int)));
+    M3B_CUDA(cudaMemset(impl->d_fused_counters, 0, 8 * sizeof(int)));
+    if (const char* e = std::getenv("M3B_FUSED_EXCHANGE")) impl->fused_exchange = std::atoi(e) != 0;
 
     // ---- multi-GPU exchange plan (partition.hpp): per peer, the strips in the order both sides agree on
     if (part.is_distributed())
@@ -1915,7 +1908,7 @@ device_solver_t::~device_solver_t()
         for (size_t m = 1; m < n; ++m) std::fprintf(stderr, "  -> %-25s %8.1f\n", impl->trace_names[m], acc[m] / used * 1e3);
     }
     for (auto p : impl->peer_mailbox) if (p) cudaIpcCloseMemHandle(p);
-    for (auto p : {(void*) impl->mailbox, (void*) impl->d_push_entries, (void*) impl->d_push_ticket, (void*) impl->d_ready}) if (p) cudaFree(p);
+    for (auto p : {(void*) impl->mailbox, (void*) impl->d_push_entries, (void*) impl->d_push_ticket, (void*) impl->d_ready, (void*) impl->d_exchange_clock, (void*) impl->d_fused_counters}) if (p) cudaFree(p);
     if (impl->h_results_all) cudaFreeHost(impl->h_results_all);
     if (impl->h_stage_ring) cudaFreeHost(impl->h_stage_ring);
     for (auto p : {(void*) impl->d_stage, (void*) impl->d_partials2, (void*) impl->d_block_rows[0], (void*) impl->d_block_rows[1],
@@ -2096,6 +2089,29 @@ void device_solver_t::collect_stage_timing()
         impl->event_pool.push_back(ev.second);
     }
     impl->timing_events.clear();
+    auto fold = [&] (std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& list, double& total_us, std::uint64_t& count)
+    {
+        for (auto& ev : list)
+        {
+            float ms = 0.f;
+            M3B_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+            total_us += ms * 1e3;
+            ++count;
+            impl->event_pool.push_back(ev.first);
+            impl->event_pool.push_back(ev.second);
+        }
+        list.clear();
+    };
+    fold(impl->exchange_events, exchange_us_total, exchanges_timed);
+    std::uint64_t gaps = 0;
+    fold(impl->gap_events, exposed_wait_us_total, gaps);
+    unsigned long long words[4] = {0, 0, 0, 0};
+    M3B_CUDA(cudaMemcpy(words, impl->d_exchange_clock, sizeof(words), cudaMemcpyDeviceToHost));
+    M3B_CUDA(cudaMemset(impl->d_exchange_clock, 0, sizeof(words)));
+    result_wait_us_total += words[0] * 1e-3;
+    result_waits_timed += words[1];
+    unpack_cta_wait_us_total += words[2] * 1e-3;
+    unpack_cta_waits += words[3];
 }
 
 void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
@@ -2140,9 +2156,30 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     exchange = exchange && num_ranks > 1;
     impl->mark(s, "stage begin");
     bool waiting_tiles = false;
-    if (exchange && ! impl->overlap_exchange)
+    // stage_tma is persistent: its CTAs hold every register of the SM until the tile list is done, so a tile that waited inside
+    // the kernel for the guard-zone unpack could keep the unpack kernel from ever becoming resident.  Its launch is split
+    // instead: interior blocks beside the exchange (which runs on its own, higher-priority stream), then the blocks with
+    // ghost neighbours once the unpack has finished.  No kernel of this path waits for another kernel of the same GPU.
+    const bool tma_exchange = exchange && impl->strip && impl->tma && impl->peer_transport && num_general == 0 && num_fused > 0;
+    // (default) the stage kernel does the exchange itself: push first, interior blocks, unpack by the CTAs that reach the blocks
+    // with ghost neighbours first -- one launch, nothing on another stream
+    const bool fused = tma_exchange && impl->fused_exchange;
+    fused_exchange_t X = fused_exchange_t();
+    if (fused)
     {
-        waiting_tiles = impl->peer_transport && impl->in_kernel_wait && impl->strip && num_general == 0 && impl->num_recv_entries > 0;
+        const unsigned long long counter = ++impl->exchange_counter;
+        X.enabled = 1;
+        X.push = impl->d_push_entries; X.n_push = impl->num_send_entries;
+        X.recv = impl->d_recv_entries; X.n_recv = impl->num_recv_entries;
+        X.peers = impl->peers; X.parity = int(counter & 1); X.me = rank_; X.dest_mask = impl->dest_mask; X.counter = counter;
+        X.counters = impl->d_fused_counters; X.cset = int(++impl->fused_launches & 1); X.U = const_cast<double*>(in.data);
+        X.clock_words = stage_timing ? impl->d_exchange_clock : nullptr;
+        exchange = false;
+    }
+    const bool split_launch = tma_exchange && ! fused && impl->num_recv_entries > 0 && impl->num_interior > 0;
+    if (exchange && ! impl->overlap_exchange && ! split_launch)
+    {
+        waiting_tiles = impl->peer_transport && impl->in_kernel_wait && impl->strip && ! impl->tma && num_general == 0 && impl->num_recv_entries > 0;
         impl->defer_unpack = waiting_tiles;
         exchange_on(stream_, const_cast<device_field_t&>(in));     // plain ordering: exchange, then every block
         impl->defer_unpack = false;
@@ -2163,7 +2200,8 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         {
             stage_tma_launch_t a;
             a.mesh = impl->mesh;
-            a.mesh.first_wait_cta = waiting_tiles ? std::max(0, impl->num_interior - first) * tpb : 0x7fffffff;
+            a.mesh.first_wait_cta = (waiting_tiles || fused) ? std::max(0, impl->num_interior - first) * tpb : 0x7fffffff;
+            a.exchange = X;
             a.mesh.ready_flag = impl->d_ready;
             a.mesh.ready_value = impl->exchange_counter;
             a.model = impl->model; a.stage = st; a.tile_info = impl->d_tile_info + size_t(first) * tpb; a.num_tiles = ctas;
@@ -2252,14 +2290,22 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     {
         // guard zones travel on their own stream while the interior blocks are updated
         auto& field = const_cast<device_field_t&>(in);
+        auto pooled = [&] { cudaEvent_t e = impl->event_pool.back(); impl->event_pool.pop_back(); return e; };
+        const bool timed = stage_timing && impl->event_pool.size() >= 8;
         M3B_CUDA(cudaEventRecord(impl->input_ready, s));
         M3B_CUDA(cudaStreamWaitEvent(impl->comm_stream, impl->input_ready, 0));
+        cudaEvent_t x0 = nullptr, x1 = nullptr, g0 = nullptr, g1 = nullptr;
+        if (timed) { x0 = pooled(); x1 = pooled(); g0 = pooled(); g1 = pooled(); M3B_CUDA(cudaEventRecord(x0, impl->comm_stream)); }
         exchange_on(impl->comm_stream, field);
         M3B_CUDA(cudaEventRecord(impl->halo_ready, impl->comm_stream));
+        if (timed) M3B_CUDA(cudaEventRecord(x1, impl->comm_stream));
         if (e0 && ! e0_recorded) M3B_CUDA(cudaEventRecord(e0, s));
         launch_fused(0, impl->num_interior);
+        if (timed) M3B_CUDA(cudaEventRecord(g0, s));
         M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));
+        if (timed) M3B_CUDA(cudaEventRecord(g1, s));
         launch_fused(impl->num_interior, num_fused - impl->num_interior);
+        if (timed) { impl->exchange_events.emplace_back(x0, x1); impl->gap_events.emplace_back(g0, g1); }
         if (num_fused == 0) {}      // (general blocks below run after the wait as well)
     }
     else
@@ -2411,6 +2457,7 @@ void device_solver_t::launch_step_async(device_field_t& in, device_field_t& scra
         pp.host_results = impl->d_results;
         pp.me = rank_; pp.nranks = num_ranks; pp.slot_stride = num_slots; pp.slot_a = a; pp.slot_b = b;
         pp.counter = ++impl->step_counter;
+        pp.clock_words = stage_timing ? impl->d_exchange_clock : nullptr;
         launch_stage_kernels(in, nullptr, scratch, a, /*exchange*/ true, 1, 1);
         M3B_CUDA(cudaStreamWaitEvent(s, impl->positions_done[1 - parity], 0));
         launch_stage_kernels(scratch, &in, out, b, /*exchange*/ true, 2, fixed_dt ? 0 : 2);

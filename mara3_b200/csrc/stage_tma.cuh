@@ -51,6 +51,7 @@ namespace m3b { namespace dev { namespace
         tile_info_t info[3];                // records of the tiles k, k + 1, k + 2 (slot = ordinal % 3)
         double negbuf[STRIP_THREADS / 32][STRIP][32];     // new densities that came out negative, until the strip is done
         int near_sink;
+        int unpack_slot;                    // exchange_unpack: the strip this CTA has taken off the list
     };
 
     __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -98,13 +99,94 @@ namespace m3b { namespace dev { namespace
         cp_async_commit();
     }
 
-    /** multi-GPU: tiles of blocks with ghost neighbours may only be fetched once the guard-zone unpack has finished */
-    __device__ __forceinline__ void wait_for_ghosts(const mesh_dev_t& mesh)
+    /**
+     * Send side of extend() across GPUs (scheme.cpp:132-142), first thing in the kernel: the CTAs copy the strips / corners of
+     * owned blocks straight into the destination ranks' landing buffers (entry.pad = destination rank, entry.offset = position
+     * in ITS buffer); the CTA that completes the last strip raises this rank's flag on every destination.
+     */
+    __device__ __forceinline__ void exchange_push(const fused_exchange_t& X, size_t FS, int N, int* slot)
     {
+        int* cnt = X.counters + 4 * X.cset;
+        if (blockIdx.x == 0 && threadIdx.x < 4) X.counters[4 * (1 - X.cset) + threadIdx.x] = 0;       // the set the previous fused launch used
+        for (;;)
+        {
+            // strips are taken off the list, not dealt out: the flag below must not wait for a CTA that is not resident yet
+            if (threadIdx.x == 0) *slot = atomicAdd(cnt + 3, 1);
+            __syncthreads();
+            const int n = *slot;
+            __syncthreads();
+            if (n >= X.n_push) break;
+            const halo_entry_dev_t e = X.push[n];
+            const int cells = e.ni * e.nj;
+            double* __restrict__ dst = X.peers.recv[e.pad][X.parity] + e.offset;
+            for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
+            {
+                const int q = k / cells, c = k % cells;
+                const int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
+                dst[k] = X.U[q * FS + (size_t(e.block) * N + i) * N + j];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(cnt, 1) == X.n_push - 1)
+            {
+                // that was the last strip: everything this rank sends has left
+                __threadfence_system();
+                for (int p = 0; p < MAX_PEERS; ++p)
+                    if ((X.dest_mask >> p) & 1u) store_release_sys(X.peers.halo_flag[p] + X.me, X.counter);
+            }
+        }
+    }
+
+    /**
+     * Receive side, called by a whole CTA before it fetches its first tile of a block with ghost neighbours: take strips off
+     * the list (atomic counter) while there are any -- wait for the source rank's flag, scatter the landed strip into the ghost
+     * block -- then wait until every strip is in place.  All CTAs of the grid are resident (persistent launch), the neighbours'
+     * kernels push before they do anything else, and nothing here waits for a kernel that is not running: no deadlock.
+     */
+    __device__ __forceinline__ void exchange_unpack(const fused_exchange_t& X, size_t FS, int N, int* slot)
+    {
+        int* cnt = X.counters + 4 * X.cset;
+        unsigned long long t0 = 0;
+        if (threadIdx.x == 0 && X.clock_words) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const double* __restrict__ landing = X.peers.recv[X.me][X.parity];
+        const unsigned long long* flags = X.peers.halo_flag[X.me];
+        for (;;)
+        {
+            if (threadIdx.x == 0)
+            {
+                int done;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(cnt + 2) : "memory");
+                *slot = done >= X.n_recv ? X.n_recv : atomicAdd(cnt + 1, 1);
+            }
+            __syncthreads();
+            const int n = *slot;
+            __syncthreads();
+            if (n >= X.n_recv) break;
+            const halo_entry_dev_t e = X.recv[n];
+            if (threadIdx.x == 0) while (load_acquire_sys(flags + e.pad) < X.counter) { }
+            __syncthreads();
+            const int cells = e.ni * e.nj;
+            for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
+            {
+                const int q = k / cells, c = k % cells;
+                const int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
+                X.U[q * FS + (size_t(e.block) * N + i) * N + j] = __ldcg(landing + e.offset + k);     // written by a peer: not through L1
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(cnt + 2, 1);
+        }
         if (threadIdx.x == 0)
         {
-            unsigned long long v;
-            do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); } while (v < mesh.ready_value);
+            int done;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(cnt + 2) : "memory"); } while (done < X.n_recv);
+            if (X.clock_words)
+            {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                atomicAdd(X.clock_words + 2, t1 - t0);
+                atomicAdd(X.clock_words + 3, 1ull);
+            }
         }
         __syncthreads();
     }
@@ -339,7 +421,8 @@ namespace m3b { namespace dev { namespace
     template<int MIN_CTAS, int NB, bool FAST, int MODE>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_tma(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info, int num_tiles,
-        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout, double* partials, fail_dev_t* fail)
+        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout, double* partials, fail_dev_t* fail,
+        fused_exchange_t X)
     {
         extern __shared__ __align__(128) unsigned char smem_raw[];
         tma_smem_t& T = *reinterpret_cast<tma_smem_t*>(smem_raw);
@@ -357,14 +440,17 @@ namespace m3b { namespace dev { namespace
 
         // ordinal k of this CTA's tiles <-> tile blockIdx.x + k gridDim.x; record ring slot k % 3, P half k & 1
         int tile = blockIdx.x;
+        if (X.enabled) exchange_push(X, FS, N, &T.unpack_slot);       // (every CTA of the grid takes part, also one without tiles)
         if (tile >= num_tiles) return;
+        bool ghosts_ready = ! X.enabled;
         if (threadIdx.x < 6)
         {
             const int which = threadIdx.x / 3, part = threadIdx.x % 3;
             const int tl = tile + which * int(gridDim.x);
             if (tl < num_tiles) reinterpret_cast<int4*>(&T.info[which])[part] = __ldg(reinterpret_cast<const int4*>(tile_info + tl) + part);
         }
-        if (tile >= mesh.first_wait_cta) wait_for_ghosts(mesh); else __syncthreads();
+        __syncthreads();
+        if (! ghosts_ready && tile >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
         stage_tile_async(T, T.info[0], Uin, FS, tile % tpb, 0, N, tiles_y);
         if (warp == 0)
         {
@@ -389,7 +475,7 @@ namespace m3b { namespace dev { namespace
             // the other half of P was released by the barrier that ended tile k - 1: refill it while this tile is computed
             if (has_next)
             {
-                if (next >= mesh.first_wait_cta) wait_for_ghosts(mesh);
+                if (! ghosts_ready && next >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
                 const int tn = next % tpb;
                 stage_tile_async(T, tin, Uin, FS, tn, buf ^ 1, N, tiles_y);
                 if (warp == 0)

@@ -19,7 +19,8 @@
  * libstdc++ (SURVEY.md section 8c caveat 1).
  *
  * usage: mara_ref [--steps K] [--dump FILE] [--dump-steps a,b,c] [--mesh-only]
- *                 [--stages] [--timing] [--warmup W] key=value ...
+ *                 [--stages] [--timing] [--warmup W] [--max-seconds S] key=value ...
+ * --max-seconds: stop the timed steps early once S seconds have passed (at least one step is taken; bench.py --impl reference)
  * Tokens without '=' are ignored by the reference's argv parser
  * (src/app_config.hpp:223-245), so harness options never clash with config keys.
  */
@@ -224,6 +225,7 @@ int main(int argc, const char* argv[])
     bool mesh_only = false;
     bool stages = false;
     bool timing = false;
+    double max_seconds = 0.0;
     std::string dump_name;
     std::set<int> dump_steps;
 
@@ -238,6 +240,7 @@ int main(int argc, const char* argv[])
         else if (a == "--mesh-only") mesh_only = true;
         else if (a == "--stages")    stages = true;
         else if (a == "--timing")    timing = true;
+        else if (a == "--max-seconds") max_seconds = std::stod(next());
         else if (a == "--dump-steps")
         {
             auto ss = std::stringstream(next());
@@ -283,6 +286,11 @@ int main(int argc, const char* argv[])
         num_fallbacks += report.fell_back;
         dts.push_back(report.dt);
         if (want) dump_solution(dump, prefix, solution, N);
+        if (max_seconds > 0.0 && std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count() > max_seconds)
+        {
+            steps = n;
+            break;
+        }
     }
     auto t1 = std::chrono::high_resolution_clock::now();
     auto seconds = std::chrono::duration<double>(t1 - t0).count();
@@ -299,8 +307,8 @@ int main(int argc, const char* argv[])
 
     if (timing && steps > 0)
     {
-        std::printf("timing: threads=%d seconds=%.6f mzps=%.6f\n",
-            run_config.get_int("threaded"), seconds, double(B * N * N) * steps / seconds * 1e-6);
+        std::printf("timing: threads=%d seconds=%.6f mzps=%.6f steps=%d\n",
+            run_config.get_int("threaded"), seconds, double(B * N * N) * steps / seconds * 1e-6, steps);
     }
     return 0;
 }
