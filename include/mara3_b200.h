@@ -65,7 +65,8 @@ m3b_solver_t* m3b_solver_create(int argc, const char* const* argv, int device, i
  * ranks by any means (bench.py uses torch.distributed), and every rank creates its solver.  The leaf
  * blocks are cut into `nranks` Morton-contiguous ranges; each rank owns one range and keeps ghost
  * copies of the remote blocks its range touches.  Per-block queries below then refer to the OWNED
- * blocks of the calling rank.  Uniform-level trees only in this build. */
+ * blocks of the calling rank.  Any 2:1-balanced tree (uniform or nested): ranks keep whole ghost copies of the blocks
+ * their jump blocks read. */
 int         m3b_nccl_unique_id(unsigned char* out128);
 m3b_solver_t* m3b_solver_create_distributed(int argc, const char* const* argv, int device, int flags,
                                             int rank, int nranks, const unsigned char* nccl_unique_id);
@@ -174,7 +175,8 @@ void        m3b_stage_timing(m3b_solver_t* s, int enable);
 int         m3b_stage_timing_read(m3b_solver_t* s, double* total_ms, uint64_t* launches);
 /* Several ranks, with stage timing on: out8 = { steps instrumented, us the compute stream waited for ghost blocks (interior
  * blocks done -> blocks with ghost neighbours may start), us the step's last finish kernel waited for the other ranks'
- * results, us from "stage input ready" to "ghost blocks unpacked" on the exchange stream, exchanges, bytes pushed, 0, 0 },
+ * results, us from "stage input ready" to "ghost blocks unpacked" on the exchange stream, exchanges, bytes pushed,
+ * us CTAs of the stage kernel spent in its fused unpack (flag wait + their share of the scatter), number of such visits },
  * totals since the last call.  M3B_ERROR on one rank.  (The reference has no counterpart: subprog_binary_scheme.cpp:132-142
  * reads its neighbours through shared memory.) */
 int         m3b_exchange_timing(m3b_solver_t* s, double* out8);

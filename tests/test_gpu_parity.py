@@ -281,6 +281,69 @@ def test_config2_1024sq_stage_against_oracle():
     assert_scalars(g1.scalars, o1.scalars, 1e-11, dt)
 
 
+def test_config3_4096sq_stage_against_oracle():
+    """BASELINE.json configs[2], the workload bench.py times at every N: one RK stage of the whole 4096^2 grid against the
+    oracle, cell by cell (the oracle needs ~20 s for it; full steps at this size are covered by the conservation test below)."""
+    cfg = dict(depth=6, block_size=64, focus_factor=1e3, mach_number=10.0)
+    solver, u, o = make_pair(cfg)
+    assert solver.num_cells == 4096 ** 2 and solver.num_regular_blocks == 4096
+    dt = 0.4 * o.maximum_timestep()
+    assert abs(0.4 * solver.maximum_timestep(u) - dt) <= 1e-14 * dt
+    o1, status = o.advance(dt)
+    assert status == 0
+    g1 = solver.advance(u, dt)
+    assert block_rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
+    assert_scalars(g1.scalars, o1.scalars, 1e-11, dt)
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(conserve_linear_p=0, fixed_dt=1)])
+def test_config4_depth8_step_against_oracle(extra):
+    """BASELINE.json configs[3] as bench.py's `c4` runs it (depth 8, 64^2 blocks: 424 leaves on six levels, 77 % of them at
+    refinement jumps): one full step -- dt rule, both RK stages, combination -- against the oracle, in the linear-momentum
+    variables (advance_u, scheme.cpp:790-904) and in the angular-momentum variables (advance_q, :906-1020)."""
+    cfg = dict(depth=8, block_size=64, **extra)
+    solver, u, o = make_pair(cfg)
+    assert solver.num_blocks == 424 and 0 < solver.num_regular_blocks < 424
+    dt_o, fb_o = o.next_solution()
+    dt_g, fb_g = solver.next_solution(u)
+    assert fb_o == fb_g and abs(dt_g - dt_o) <= 1e-13 * dt_o
+    rel_err = block_rel_err_q if extra else block_rel_err
+    assert rel_err(u.conserved_u, o.conserved_u) <= CELL_TOL
+    assert_scalars(u.scalars, o.scalars, 1e-10, o.time)
+
+
+def test_nested_bench_workload_stage_against_oracle():
+    """bench.py's `c4x` (depth 8, focus_factor 12: 4552 leaves of 64^2 on levels 4-8, the nested workload with load for
+    8 GPUs): one RK stage against the oracle."""
+    cfg = dict(depth=8, block_size=64, focus_factor=12.0)
+    solver, u, o = make_pair(cfg)
+    assert solver.num_blocks == 4552
+    dt = 0.4 * o.maximum_timestep()
+    assert abs(0.4 * solver.maximum_timestep(u) - dt) <= 1e-14 * dt
+    o1, status = o.advance(dt)
+    assert status == 0
+    g1 = solver.advance(u, dt)
+    assert block_rel_err(g1.conserved_u, o1.conserved_u) <= CELL_TOL
+
+
+def test_persistent_and_one_shot_stage_kernels_agree(monkeypatch):
+    """stage_tma (persistent, cp.async staging, regrouped arithmetic) against stage_strip (M3B_STAGE=strip) over three steps of
+    the 1024^2 grid: two implementations of the same stage that share neither the tile loader nor the order of the flux
+    arithmetic; both lie within the oracle tolerance of each other."""
+    cfg = dict(depth=4, block_size=64, focus_factor=1e3, mach_number=10.0)
+    new = m3.Solver(cfg)
+    monkeypatch.setenv("M3B_STAGE", "strip")
+    old = m3.Solver(cfg)
+    monkeypatch.delenv("M3B_STAGE")
+    ua, ub = new.create_solution(), old.create_solution()
+    for _ in range(3):
+        dta, _ = new.next_solution(ua)
+        dtb, _ = old.next_solution(ub)
+        assert abs(dta - dtb) <= 1e-13 * dtb
+    assert block_rel_err(ua.conserved_u, ub.conserved_u) <= 3e-12
+    assert_scalars(ua.scalars, ub.scalars, 1e-10, ub.time)
+
+
 @pytest.mark.parametrize("cfg", [
     dict(depth=4, block_size=64, focus_factor=1e3),     # config 2: 1024^2 uniform
     dict(depth=6, block_size=64, focus_factor=1e3),     # config 3: 4096^2 uniform
