@@ -112,6 +112,9 @@ int         m3b_binary_main_distributed(int argc, const char* const* argv, int d
 /* test hook of the built-in HDF5 writer / reader (h5lite): write one file with every structure it emits and / or
  * list the root group of an existing file into `report`; 0 or -1 (message in `report`) */
 int         m3b_h5_selftest(const char* write_path, const char* read_path, char* report, int report_len);
+/* the same content written by one process into `whole_path` and by `parts` processes' roles (one after another) into
+ * `shared_path`: the files must be byte-identical (how the product writers share a file between ranks); 0 or -1 */
+int         m3b_h5_selftest_shared(const char* whole_path, const char* shared_path, int parts);
 int         m3b_block_size(const m3b_solver_t* s);
 int64_t     m3b_num_cells(const m3b_solver_t* s);
 int         m3b_num_regular_blocks(const m3b_solver_t* s);   /* blocks served by the fused kernel */

@@ -121,84 +121,121 @@ time_series_sample_t m3b::make_time_series_sample(binary_solver_t& solver, const
     return sample;
 }
 
+namespace
+{
+    /**
+     * One product file written by all ranks.  Every rank describes the same groups and datasets (the state is replicated apart
+     * from the blocks, whose datasets a rank fills only for the blocks it owns) and so computes the same layout; rank 0 then
+     * writes the structure, the small datasets and its own blocks, leaving holes for the others, and once it is done the other
+     * ranks store their blocks at their addresses in that file (h5lite writer roles root / part).  Nothing is gathered: at
+     * 16384^2 a rank moves its own 0.8 GB instead of rank 0 moving 6.4 GB three times.  The outcome is collective -- if any rank
+     * fails (directory not writable, disk full), every rank throws, so that no rank walks on into a step its peers never take.
+     */
+    template<typename Describe>
+    void write_shared_file(const std::string& filename, m3b::binary_solver_t& solver, Describe&& describe)
+    {
+        auto& device = solver.device();
+        const int rank = device.rank(), nranks = device.num_ranks_();
+        using role_t = m3b::h5::writer_t::role_t;
+        auto message = std::string();
+        auto attempt = [&] (auto&& fn) { try { fn(); return 1.0; } catch (const std::exception& e) { message = e.what(); return 0.0; } };
+        if (nranks == 1)
+        {
+            auto w = m3b::h5::writer_t(filename);
+            describe(w);
+            w.close();
+            return;
+        }
+        auto w = m3b::h5::writer_t(filename, rank == 0 ? role_t::root : role_t::part);
+        double ok = attempt([&] { describe(w); });
+        if (rank == 0 && ok == 1.0) ok = attempt([&] { w.close(); });
+        bool all_ok = true;
+        for (double v : device.all_gather_scalar(ok)) all_ok = all_ok && v == 1.0;          // (also orders the root's close before the parts')
+        if (all_ok && rank != 0) ok = attempt([&] { w.close(); });
+        for (double v : device.all_gather_scalar(all_ok ? ok : 0.0)) all_ok = all_ok && v == 1.0;
+        if (! all_ok) throw std::runtime_error("writing " + filename + " failed on " + (message.empty() ? std::string("another rank") : "this rank: " + message));
+    }
+}
+
 void m3b::write_checkpoint(const std::string& filename, binary_solver_t& solver, const state_t& state)
 {
     const auto& data = solver.solver_data();
     const auto& u = state.solution;
-    // several ranks: a collective -- every rank hands its blocks to rank 0, which writes the one file
-    const int N = data.block_size, B = data.num_blocks;
+    const int N = data.block_size, B = data.num_blocks, first = data.partition.first_owned, owned = data.num_owned;
     const std::size_t NN = std::size_t(N) * N;
-    const bool root = solver.device().rank() == 0;
-    auto planes = std::vector<double>(root ? std::size_t(B) * 3 * NN : 0);
-    solver.device().gather_state(*u.conserved_u, planes.data());
-    if (! root) return;
-    auto w = h5::writer_t(filename);
-    auto v2 = type_t::array(type_t::f64(), 2), v3 = type_t::array(type_t::f64(), 3), el = elements_type();
 
-    // ---- /solution
-    w.write_double("/solution/time", u.time);
-    int iteration[2] = {u.iteration_num, u.iteration_den};
-    w.write("/solution/iteration", type_t::array(type_t::i32(), 2), {}, iteration, true);
-
-    // conserved_u/<level:ii-jj>: (N, N) of double[3], the raw image of the reference's std::tuple<sigma, px, py>,
-    // which libstdc++ lays out in reverse: (py, px, sigma)  (SURVEY.md 8c caveat 1)
+    // this rank's blocks: conserved_u/<level:ii-jj> is (N, N) of double[3], the raw image of the reference's
+    // std::tuple<sigma, px, py>, which libstdc++ lays out in reverse: (py, px, sigma)  (SURVEY.md 8c caveat 1)
+    auto planes = std::vector<double>(std::size_t(owned) * 3 * NN);
+    solver.device().download(*u.conserved_u, planes.data());
     auto cells = std::vector<double>(planes.size());
-    for (int b = 0; b < B; ++b)
-        for (std::size_t c = 0; c < NN; ++c)
-            for (int q = 0; q < 3; ++q)
-                cells[(std::size_t(b) * NN + c) * 3 + (2 - q)] = planes[(std::size_t(b) * 3 + q) * NN + c];
-    // conserve_linear_p = 0: the state is conserved_q = (sigma, Sr, Lz) -- its tuple image is (Lz, Sr, sigma) all the same
-    const std::string used = data.conserve_linear_p ? "/solution/conserved_u" : "/solution/conserved_q";
-    const std::string unused = data.conserve_linear_p ? "/solution/conserved_q" : "/solution/conserved_u";
-    w.require_group(used);
-    for (int b = 0; b < B; ++b)
-        w.write(used + "/" + leaf_name(data, b), v3, {std::uint64_t(N), std::uint64_t(N)}, cells.data() + std::size_t(b) * NN * 3);
-    // the unused variable set is a default tree: one leaf "0:0-0" holding an empty array
-    w.write(unused + "/0:0-0", v3, {0, 0}, cells.data());
+    for (int b = 0; b < owned; ++b)
+        for (int q = 0; q < 3; ++q)
+        {
+            const double* src = planes.data() + (std::size_t(b) * 3 + q) * NN;
+            double* dst = cells.data() + std::size_t(b) * NN * 3 + (2 - q);
+            for (std::size_t c = 0; c < NN; ++c) dst[3 * c] = src[c];
+        }
+    planes = std::vector<double>();
 
-    w.write("/solution/mass_accreted_on", v2, {}, u.mass_accreted_on, true);
-    w.write("/solution/angular_momentum_accreted_on", v2, {}, u.angular_momentum_accreted_on, true);
-    w.write("/solution/integrated_torque_on", v2, {}, u.integrated_torque_on, true);
-    w.write("/solution/work_done_on", v2, {}, u.work_done_on, true);
-    w.write_double("/solution/mass_ejected", u.mass_ejected);
-    w.write_double("/solution/angular_momentum_ejected", u.angular_momentum_ejected);
-    w.write("/solution/orbital_elements_acc", el, {}, &u.orbital_elements_acc, true);
-    w.write("/solution/orbital_elements_grav", el, {}, &u.orbital_elements_grav, true);
-    w.write("/solution/orbital_elements", el, {}, &u.orbital_elements, true);
-
-    // ---- /schedule, /time_series, /run_config
-    w.require_group("/schedule");
-    for (const auto& t : state.schedule.tasks)
+    write_shared_file(filename, solver, [&] (h5::writer_t& w)
     {
-        w.write_string("/schedule/" + t.first + "/name", t.second.name);
-        w.write_int("/schedule/" + t.first + "/num_times_performed", t.second.num_times_performed);
-        w.write_double("/schedule/" + t.first + "/last_performed", t.second.last_performed);
-    }
-    w.write("/time_series", sample_type(), {std::uint64_t(state.time_series.size())}, state.time_series.data());
-    write_config(w, "/run_config", solver.run_config());
-    w.close();
+        auto v2 = type_t::array(type_t::f64(), 2), v3 = type_t::array(type_t::f64(), 3), el = elements_type();
+
+        // ---- /solution
+        w.write_double("/solution/time", u.time);
+        int iteration[2] = {u.iteration_num, u.iteration_den};
+        w.write("/solution/iteration", type_t::array(type_t::i32(), 2), {}, iteration, true);
+
+        // conserve_linear_p = 0: the state is conserved_q = (sigma, Sr, Lz) -- its tuple image is (Lz, Sr, sigma) all the same
+        const std::string used = data.conserve_linear_p ? "/solution/conserved_u" : "/solution/conserved_q";
+        const std::string unused = data.conserve_linear_p ? "/solution/conserved_q" : "/solution/conserved_u";
+        w.require_group(used);
+        for (int b = 0; b < B; ++b)
+        {
+            const bool mine = b >= first && b < first + owned;
+            w.write(used + "/" + leaf_name(data, b), v3, {std::uint64_t(N), std::uint64_t(N)},
+                    mine ? cells.data() + std::size_t(b - first) * NN * 3 : nullptr, false, mine);
+        }
+        // the unused variable set is a default tree: one leaf "0:0-0" holding an empty array
+        w.write(unused + "/0:0-0", v3, {0, 0}, cells.data());
+
+        w.write("/solution/mass_accreted_on", v2, {}, u.mass_accreted_on, true);
+        w.write("/solution/angular_momentum_accreted_on", v2, {}, u.angular_momentum_accreted_on, true);
+        w.write("/solution/integrated_torque_on", v2, {}, u.integrated_torque_on, true);
+        w.write("/solution/work_done_on", v2, {}, u.work_done_on, true);
+        w.write_double("/solution/mass_ejected", u.mass_ejected);
+        w.write_double("/solution/angular_momentum_ejected", u.angular_momentum_ejected);
+        w.write("/solution/orbital_elements_acc", el, {}, &u.orbital_elements_acc, true);
+        w.write("/solution/orbital_elements_grav", el, {}, &u.orbital_elements_grav, true);
+        w.write("/solution/orbital_elements", el, {}, &u.orbital_elements, true);
+
+        // ---- /schedule, /time_series, /run_config
+        w.require_group("/schedule");
+        for (const auto& t : state.schedule.tasks)
+        {
+            w.write_string("/schedule/" + t.first + "/name", t.second.name);
+            w.write_int("/schedule/" + t.first + "/num_times_performed", t.second.num_times_performed);
+            w.write_double("/schedule/" + t.first + "/last_performed", t.second.last_performed);
+        }
+        w.write("/time_series", sample_type(), {std::uint64_t(state.time_series.size())}, state.time_series.data());
+        write_config(w, "/run_config", solver.run_config());
+    });
 }
 
 void m3b::write_diagnostics(const std::string& filename, binary_solver_t& solver, const solution_t& u)
 {
     const auto& data = solver.solver_data();
-    const int N = data.block_size, B = data.num_blocks, V = N + 1;
+    const int N = data.block_size, B = data.num_blocks, V = N + 1, first = data.partition.first_owned, owned = data.num_owned;
     const std::size_t NN = std::size_t(N) * N;
-    const bool root = solver.device().rank() == 0;
-    auto fields = std::vector<double>(root ? std::size_t(B) * 3 * NN : 0);
-    solver.device().gather_diagnostic_fields(*u.conserved_u, fields.data());       // collective
-    if (! root) return;
-    auto w = h5::writer_t(filename);
-    auto v2 = type_t::array(type_t::f64(), 2);
 
-    write_config(w, "/run_config", solver.run_config());
-    w.write_double("/time", u.time);
-
-    // vertices/<idx>: (N + 1, N + 1) of (x, y)
-    auto verts = std::vector<double>(std::size_t(B) * V * V * 2);
-    for (int b = 0; b < B; ++b)
+    // this rank's blocks: sigma, v_r, v_phi (subprog_binary_diagnostics.cpp:48-82) and the vertices (N + 1, N + 1) of (x, y)
+    auto fields = std::vector<double>(std::size_t(owned) * 3 * NN);
+    solver.device().diagnostic_fields(*u.conserved_u, fields.data());
+    auto verts = std::vector<double>(std::size_t(owned) * V * V * 2);
+    for (int b = 0; b < owned; ++b)
     {
-        const auto& leaf = data.tree->leaf_node(b);             // the whole tree is known on every rank
+        const auto& leaf = data.tree->leaf_node(first + b);             // the whole tree is known on every rank
         for (int i = 0; i < V; ++i)
             for (int j = 0; j < V; ++j)
             {
@@ -206,21 +243,29 @@ void m3b::write_diagnostics(const std::string& filename, binary_solver_t& solver
                 verts[((std::size_t(b) * V + i) * V + j) * 2 + 1] = leaf.yv[j] * data.domain_radius;
             }
     }
-    const char* names[3] = {"sigma", "radial_velocity", "phi_velocity"};
-    for (const char* n : names) w.require_group(std::string("/") + n);
-    w.require_group("/vertices");
-    for (int b = 0; b < B; ++b)
+
+    write_shared_file(filename, solver, [&] (h5::writer_t& w)
     {
-        auto idx = leaf_name(data, b);
-        w.write("/vertices/" + idx, v2, {std::uint64_t(V), std::uint64_t(V)}, verts.data() + std::size_t(b) * V * V * 2);
-        for (int q = 0; q < 3; ++q)
-            w.write(std::string("/") + names[q] + "/" + idx, type_t::f64(), {std::uint64_t(N), std::uint64_t(N)}, fields.data() + (std::size_t(b) * 3 + q) * NN);
-    }
-    auto bodies = two_body_state(u.orbital_elements, u.time);
-    double p1[2] = {bodies.body1.x, bodies.body1.y}, p2[2] = {bodies.body2.x, bodies.body2.y};
-    w.write("/position_of_mass1", v2, {}, p1, true);
-    w.write("/position_of_mass2", v2, {}, p2, true);
-    w.close();
+        auto v2 = type_t::array(type_t::f64(), 2);
+        write_config(w, "/run_config", solver.run_config());
+        w.write_double("/time", u.time);
+        const char* names[3] = {"sigma", "radial_velocity", "phi_velocity"};
+        for (const char* n : names) w.require_group(std::string("/") + n);
+        w.require_group("/vertices");
+        for (int b = 0; b < B; ++b)
+        {
+            const bool mine = b >= first && b < first + owned;
+            auto idx = leaf_name(data, b);
+            w.write("/vertices/" + idx, v2, {std::uint64_t(V), std::uint64_t(V)}, mine ? verts.data() + std::size_t(b - first) * V * V * 2 : nullptr, false, mine);
+            for (int q = 0; q < 3; ++q)
+                w.write(std::string("/") + names[q] + "/" + idx, type_t::f64(), {std::uint64_t(N), std::uint64_t(N)},
+                        mine ? fields.data() + (std::size_t(b - first) * 3 + q) * NN : nullptr, false, mine);
+        }
+        auto bodies = two_body_state(u.orbital_elements, u.time);
+        double p1[2] = {bodies.body1.x, bodies.body1.y}, p2[2] = {bodies.body2.x, bodies.body2.y};
+        w.write("/position_of_mass1", v2, {}, p1, true);
+        w.write("/position_of_mass2", v2, {}, p2, true);
+    });
 }
 
 std::map<std::string, std::string> m3b::read_checkpoint_config(const std::string& filename)
@@ -402,7 +447,15 @@ int m3b::binary_main(int argc, const char* const argv[], int device, int rank, i
     }
     else state = read_checkpoint(restart, solver);
 
-    if (root) require_dir(config.get_string("outdir"));
+    {
+        // collective outcome: a rank whose peers could not create the output directory must not start stepping (it would wait
+        // for their guard zones until the deadline)
+        double ok = 1.0;
+        auto message = std::string();
+        if (root) { try { require_dir(config.get_string("outdir")); } catch (const std::exception& e) { ok = 0.0; message = e.what(); } }
+        if (solver.has_device()) for (double v : solver.device().all_gather_scalar(ok)) ok = std::min(ok, v);
+        if (ok != 1.0) throw std::runtime_error(message.empty() ? "rank 0 could not create the output directory " + config.get_string("outdir") : message);
+    }
     if (root) config.pretty_print(std::cout, "config");
     run_tasks(solver, state, root);
 

@@ -284,6 +284,43 @@ int m3b_h5_selftest(const char* write_path, const char* read_path, char* report,
     }
 }
 
+int m3b_h5_selftest_shared(const char* whole_path, const char* shared_path, int parts)
+{
+    // One file written by `parts` processes (h5lite writer roles root / part, as the multi-GPU product writers use them) must
+    // be byte-identical to the same content written by one process.  The roles run one after another here; tests/test_h5lite.py.
+    try
+    {
+        using m3b::h5::type_t;
+        using role_t = m3b::h5::writer_t::role_t;
+        const int blocks = 37, cells = 5 * 5 * 3;
+        std::vector<double> field(std::size_t(blocks) * cells);
+        for (std::size_t k = 0; k < field.size(); ++k) field[k] = 1.0 / double(k + 1);
+        auto describe = [&] (m3b::h5::writer_t& w, int me, int n)
+        {
+            // me < 0: everything; otherwise blocks [blocks me / n, blocks (me + 1) / n)
+            w.write_double("/solution/time", 1.5);
+            w.write_string("/run_config/outdir", "data");
+            for (int b = 0; b < blocks; ++b)
+            {
+                char name[32];
+                std::snprintf(name, sizeof(name), "6:%02d-%02d", b, blocks - b);
+                const bool mine = me < 0 || (b >= blocks * me / n && b < blocks * (me + 1) / n);
+                w.write(std::string("/solution/conserved_u/") + name, type_t::array(type_t::f64(), 3), {5, 5}, mine ? field.data() + std::size_t(b) * cells : nullptr, false, mine);
+            }
+            w.write("/solution/conserved_q/0:0-0", type_t::array(type_t::f64(), 3), {0, 0}, field.data());
+            w.write_int("/schedule/write_checkpoint/num_times_performed", 3);
+        };
+        { m3b::h5::writer_t w(whole_path); describe(w, -1, 1); w.close(); }
+        { m3b::h5::writer_t w(shared_path, role_t::root); describe(w, 0, parts); w.close(); }
+        for (int p = 1; p < parts; ++p) { m3b::h5::writer_t w(shared_path, role_t::part); describe(w, p, parts); w.close(); }
+        return 0;
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+}
+
 int m3b_exchange_transport(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().exchange_transport() : 0; }
 uint64_t m3b_halo_bytes_per_exchange(const m3b_solver_t* s) { return s->solver->has_device() ? s->solver->device().halo_bytes_per_exchange() : 0; }
 int m3b_block_size(const m3b_solver_t* s) { return s->solver->solver_data().block_size; }

@@ -74,6 +74,7 @@ namespace m3b
         void gather_state(const device_field_t& src, double* host_all);              // [global block][3][N][N] on rank 0
         void gather_diagnostic_fields(const device_field_t& src, double* host_all);  // sigma, v_r, v_phi, same layout
         int rank() const { return rank_; }
+        int num_ranks_() const { return num_ranks; }
         int ranks() const { return num_ranks; }
         /** disk_mass, disk_angular_momentum (subprog_binary_diagnostics.cpp:19-41); summed over the ranks (collective). */
         void disk_totals(const device_field_t& src, double out[2]);

@@ -1,4 +1,7 @@
 #include "h5lite.hpp"
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/types.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -137,9 +140,10 @@ struct writer_t::node_t
     // dataset
     type_t type;
     std::vector<std::uint64_t> shape;
-    const void* data = nullptr;
+    const void* data = nullptr;         // nullptr: another process stores these bytes (role root / part)
     bytes_t owned;
     std::uint64_t nbytes = 0;
+    bool mine = false;                  // role part: this process stores them
 
     // layout (filled by allocate)
     std::uint64_t header_addr = 0, heap_addr = 0, heap_data_addr = 0, heap_bytes = 0, root_tree_addr = 0, data_addr = UNDEF;
@@ -149,7 +153,7 @@ struct writer_t::node_t
     bytes_t header;                                                 // dataset object header, built at allocation
 };
 
-writer_t::writer_t(std::string filename) : filename(std::move(filename)), root(new node_t) {}
+writer_t::writer_t(std::string filename, role_t role) : filename(std::move(filename)), root(new node_t), role(role) {}
 writer_t::~writer_t() { if (! closed) { try { close(); } catch (...) {} } }
 
 writer_t::node_t* writer_t::descend(const std::string& path, bool create_last_as_group, std::string* leaf_name)
@@ -183,7 +187,7 @@ writer_t::node_t* writer_t::descend(const std::string& path, bool create_last_as
 
 void writer_t::require_group(const std::string& path) { descend(path, true, nullptr); }
 
-void writer_t::write(const std::string& path, const type_t& type, const std::vector<std::uint64_t>& shape, const void* data, bool copy)
+void writer_t::write(const std::string& path, const type_t& type, const std::vector<std::uint64_t>& shape, const void* data, bool copy, bool mine)
 {
     std::string name;
     node_t* parent = descend(path, false, &name);
@@ -194,7 +198,8 @@ void writer_t::write(const std::string& path, const type_t& type, const std::vec
     d->shape = shape;
     d->nbytes = type.size;
     for (auto n : shape) d->nbytes *= n;
-    if (copy)
+    d->mine = mine;
+    if (copy && data)
     {
         d->owned.assign(static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + d->nbytes);
         d->data = d->owned.data();
@@ -275,13 +280,44 @@ void writer_t::close()
     layout_t::allocate(*root, cursor);
     const std::uint64_t eof = cursor;
 
+    if (role == role_t::part)
+    {
+        // only this process's datasets, at the addresses every process has computed alike
+        const int fd = ::open(filename.c_str(), O_WRONLY);
+        if (fd < 0) throw std::runtime_error("h5lite: cannot open " + filename + " (written by the root process) for writing");
+        struct part_t
+        {
+            static void store(const node_t& n, int fd, const std::string& filename)
+            {
+                if (n.is_group) { for (auto& c : n.children) store(*c.second, fd, filename); return; }
+                if (! n.mine || ! n.data || ! n.nbytes) return;
+                const char* p = static_cast<const char*>(n.data);
+                std::uint64_t done = 0;
+                while (done < n.nbytes)
+                {
+                    const ssize_t k = ::pwrite(fd, p + done, std::size_t(std::min<std::uint64_t>(n.nbytes - done, 1u << 30)), off_t(n.data_addr + done));
+                    if (k <= 0) { ::close(fd); throw std::runtime_error("h5lite: write to " + filename + " failed"); }
+                    done += std::uint64_t(k);
+                }
+            }
+        };
+        part_t::store(*root, fd, filename);
+        if (::close(fd) != 0) throw std::runtime_error("h5lite: closing " + filename + " failed");
+        return;
+    }
+
     // ---- pass 2: stream
     std::FILE* f = std::fopen(filename.c_str(), "wb");
     if (! f) throw std::runtime_error("h5lite: cannot open " + filename + " for writing");
     std::uint64_t written = 0;
     auto emit = [&] (const void* p, std::size_t n)
     {
-        if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("h5lite: write to " + filename + " failed"); }
+        if (n && ! p)
+        {
+            // leave a hole (the file is extended to its full length at the end)
+            if (fseeko(f, off_t(n), SEEK_CUR) != 0) { std::fclose(f); throw std::runtime_error("h5lite: seek in " + filename + " failed"); }
+        }
+        else if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("h5lite: write to " + filename + " failed"); }
         written += n;
     };
     auto emit_bytes = [&] (const bytes_t& b) { emit(b.data(), b.size()); };
@@ -305,9 +341,13 @@ void writer_t::close()
             if (! n.is_group)
             {
                 emit(n.header.data(), n.header.size());
-                emit(n.data, n.nbytes);
-                static const unsigned char zeros[8] = {0};
-                emit(zeros, round8(n.nbytes) - n.nbytes);
+                if (n.data || ! n.nbytes)
+                {
+                    emit(n.data, n.nbytes);
+                    static const unsigned char zeros[8] = {0};
+                    emit(zeros, round8(n.nbytes) - n.nbytes);
+                }
+                else emit(nullptr, round8(n.nbytes));        // a hole: its owner stores the bytes (role root)
                 return;
             }
             bytes_t b;
@@ -372,6 +412,7 @@ void writer_t::close()
     std::function<void(const void*, std::size_t)> emit_fn = emit;
     stream_t::write(*root, emit_fn, written);
     if (written != eof) { std::fclose(f); throw std::logic_error("h5lite: end-of-file address mismatch"); }
+    if (std::fflush(f) != 0 || ::ftruncate(fileno(f), off_t(eof)) != 0) { std::fclose(f); throw std::runtime_error("h5lite: sizing " + filename + " failed"); }
     if (std::fclose(f) != 0) throw std::runtime_error("h5lite: closing " + filename + " failed");
 }
 
@@ -427,14 +468,26 @@ struct reader_t::impl_t
         return out;
     }
 
+    // One read per local heap and one walk per group: a restart file holds one dataset per leaf (65 536 at config 5), and every
+    // rank looks all of its blocks up -- without these two caches each lookup re-read the group's whole symbol table.
+    mutable std::map<std::uint64_t, bytes_t> heap_cache;                                        // heap address -> its data segment
+    mutable std::map<std::uint64_t, std::map<std::string, std::uint64_t>> children_cache;       // group header -> name -> object header
+    mutable std::map<std::uint64_t, std::vector<std::string>> order_cache;                      // group header -> names in file order
+
     std::string heap_name(std::uint64_t heap, std::uint64_t offset) const
     {
-        auto h = at(heap, 32);
-        if (std::memcmp(h.data(), "HEAP", 4)) throw std::runtime_error("h5lite: bad local heap");
-        std::uint64_t size = get(h, 8, 8), data = get(h, 24, 8);
-        if (offset >= size) throw std::runtime_error("h5lite: name offset outside the heap");
-        auto seg = at(data + offset, std::min<std::uint64_t>(size - offset, 4096));
-        return std::string(reinterpret_cast<const char*>(seg.data()), strnlen(reinterpret_cast<const char*>(seg.data()), seg.size()));
+        auto it = heap_cache.find(heap);
+        if (it == heap_cache.end())
+        {
+            auto h = at(heap, 32);
+            if (std::memcmp(h.data(), "HEAP", 4)) throw std::runtime_error("h5lite: bad local heap");
+            std::uint64_t size = get(h, 8, 8), data = get(h, 24, 8);
+            it = heap_cache.emplace(heap, at(data, size)).first;
+        }
+        const bytes_t& seg = it->second;
+        if (offset >= seg.size()) throw std::runtime_error("h5lite: name offset outside the heap");
+        const char* p = reinterpret_cast<const char*>(seg.data()) + offset;
+        return std::string(p, strnlen(p, seg.size() - offset));
     }
 
     void walk(std::uint64_t addr, std::uint64_t heap, std::vector<std::pair<std::string, std::uint64_t>>& out) const
@@ -453,16 +506,31 @@ struct reader_t::impl_t
         for (std::size_t k = 0; k < used; ++k) walk(get(body, 16 * k + 8, 8), heap, out);
     }
 
-    std::vector<std::pair<std::string, std::uint64_t>> children(std::uint64_t header) const
+    /** name -> object header of a group's members (nullptr: not a group); built once per group */
+    const std::map<std::string, std::uint64_t>* members(std::uint64_t header) const
     {
+        auto it = children_cache.find(header);
+        if (it != children_cache.end()) return &it->second;
         for (auto& m : messages(header))
             if (m.type == 0x0011)
             {
                 std::vector<std::pair<std::string, std::uint64_t>> out;
                 walk(get(m.data, 0, 8), get(m.data, 8, 8), out);
-                return out;
+                auto& names = order_cache[header];
+                auto& table = children_cache[header];
+                for (auto& c : out) { names.push_back(c.first); table[c.first] = c.second; }
+                return &table;
             }
-        throw std::runtime_error("h5lite: not a group");
+        return nullptr;
+    }
+
+    std::vector<std::pair<std::string, std::uint64_t>> children(std::uint64_t header) const
+    {
+        const auto* table = members(header);
+        if (! table) throw std::runtime_error("h5lite: not a group");
+        std::vector<std::pair<std::string, std::uint64_t>> out;
+        for (auto& name : order_cache[header]) out.push_back({name, table->at(name)});
+        return out;
     }
 
     bool find(const std::string& path, std::uint64_t& header) const
@@ -476,12 +544,11 @@ struct reader_t::impl_t
             if (q > p)
             {
                 auto part = path.substr(p, q - p);
-                bool found = false;
-                bool group = false;
-                for (auto& m : messages(header)) if (m.type == 0x0011) group = true;
-                if (! group) return false;
-                for (auto& c : children(header)) if (c.first == part) { header = c.second; found = true; break; }
-                if (! found) return false;
+                const auto* table = members(header);
+                if (! table) return false;
+                auto hit = table->find(part);
+                if (hit == table->end()) return false;
+                header = hit->second;
             }
             p = q + 1;
         }

@@ -52,12 +52,22 @@ namespace m3b { namespace h5 {
     class writer_t
     {
     public:
-        explicit writer_t(std::string filename);
+        /**
+         * One file written by several processes (one per GPU), each the bytes of its own datasets:
+         *   whole  one process writes everything (the default);
+         *   root   writes the file's structure and whatever datasets it holds; a dataset given as nullptr is left as a hole
+         *          of the right size for its owner;
+         *   part   describes the SAME groups and datasets in the same order (nullptr for what it does not own), computes the
+         *          same layout, and on close() only stores its own datasets (`mine = true`) at their addresses in the file the
+         *          root has created (call it after the root's close(); pwrite, no truncation).
+         */
+        enum class role_t { whole, root, part };
+        explicit writer_t(std::string filename, role_t role = role_t::whole);
         ~writer_t();
         writer_t(const writer_t&) = delete;
 
         void require_group(const std::string& path);
-        void write(const std::string& path, const type_t& type, const std::vector<std::uint64_t>& shape, const void* data, bool copy = false);
+        void write(const std::string& path, const type_t& type, const std::vector<std::uint64_t>& shape, const void* data, bool copy = false, bool mine = false);
 
         // conveniences mirroring h5::Group::write for the reference's scalar types
         void write_double(const std::string& path, double value);
@@ -71,6 +81,7 @@ namespace m3b { namespace h5 {
         std::string filename;
         std::unique_ptr<node_t> root;
         bool closed = false;
+        role_t role = role_t::whole;
     };
 
     /** Read side for `restart=`: the same subset, from files written by this module or by libhdf5's defaults. */

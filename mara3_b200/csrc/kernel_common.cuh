@@ -89,6 +89,11 @@ namespace m3b { namespace dev
         unsigned long long* halo_flag[MAX_PEERS];       // [src rank]: number of the last exchange `src` has delivered
         stage_result_t* results[MAX_PEERS];             // [src rank][num_slots]
         unsigned long long* result_flag[MAX_PEERS];     // [src rank]: number of the last step whose results `src` has delivered
+        // every wait on another rank is bounded: a rank that has waited `deadline_cycles` for a peer writes
+        // 1 + (waiting rank) + 256 (awaited rank) into the abort word of EVERY mailbox, all spins end, and the host turns the
+        // word into M3B_ERROR naming the stalled peer (device_solver_t::stage_result)
+        unsigned long long* abort_word[MAX_PEERS];
+        long long deadline_cycles;
     };
 
     __device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v)
@@ -103,6 +108,28 @@ namespace m3b { namespace dev
         return v;
     }
 
+
+
+    /** Spin until *flag >= want, the deadline passes, or any rank has called the run off.  false: give up (the abort word is set). */
+    __device__ __forceinline__ bool bounded_wait_sys(const unsigned long long* flag, unsigned long long want, const peer_table_t& peers, int me, int awaited)
+    {
+        if (load_acquire_sys(flag) >= want) return true;
+        const long long t0 = clock64();
+        for (unsigned n = 1; ; ++n)
+        {
+            if (load_acquire_sys(flag) >= want) return true;
+            if ((n & 255u) == 0)
+            {
+                if (load_acquire_sys(peers.abort_word[me]) != 0) return false;
+                if (clock64() - t0 > peers.deadline_cycles)
+                {
+                    const unsigned long long code = 1ull + unsigned(me) + 256ull * unsigned(awaited);
+                    for (int p = 0; p < MAX_PEERS; ++p) if (peers.abort_word[p]) store_release_sys(peers.abort_word[p], code);
+                    return false;
+                }
+            }
+        }
+    }
 
     struct halo_entry_dev_t
     {

@@ -843,7 +843,7 @@ namespace
         if (threadIdx.x < nranks)
         {
             if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
-            if (threadIdx.x != me) while (load_acquire_sys(peers.result_flag[me] + threadIdx.x) < counter) { }
+            if (threadIdx.x != me) bounded_wait_sys(peers.result_flag[me] + threadIdx.x, counter, peers, me, threadIdx.x);
         }
         __syncthreads();
         if (threadIdx.x == 0 && clock_words)
@@ -870,6 +870,7 @@ namespace
                 r.dt_min = dmin(r.dt_min, __ldcg(q + 18));
                 r.num_negative += __ldcg(reinterpret_cast<const unsigned int*>(q + 19));
             }
+            r.pad = static_cast<unsigned int>(load_acquire_sys(peers.abort_word[me]));     // non-zero: some rank gave up waiting (bounded_wait_sys)
             host_results[slot] = r;
             if (k == 1) dt_min_b = r.dt_min;
         }
@@ -1265,14 +1266,12 @@ namespace
 
     /** Receive side: wait for the source rank's flag (entry.pad = source rank), then scatter its strip into the ghost block. */
     __global__ void __launch_bounds__(128) halo_wait_unpack(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
-        const double* __restrict__ landing, const unsigned long long* flags, unsigned long long counter, int* ticket, unsigned long long* ready)
+        const double* __restrict__ landing, const unsigned long long* flags, unsigned long long counter, int* ticket, unsigned long long* ready,
+        peer_table_t peers, int me)
     {
         __shared__ int is_last;
         const halo_entry_dev_t e = entries[blockIdx.x];
-        if (threadIdx.x == 0)
-        {
-            while (load_acquire_sys(flags + e.pad) < counter) { }
-        }
+        if (threadIdx.x == 0) bounded_wait_sys(flags + e.pad, counter, peers, me, e.pad);
         __syncthreads();
         const int cells = e.ni * e.nj;
 
@@ -1404,6 +1403,8 @@ device_field_t::~device_field_t()
 // ===========================================================================
 // device_solver_t
 // ===========================================================================
+static void throw_if_called_off(unsigned int word);
+
 struct device_solver_t::impl_t
 {
     mesh_dev_t mesh {};
@@ -2502,7 +2503,9 @@ void device_solver_t::wait_step(int parity)
 
 stage_result_t device_solver_t::async_result(int parity, int stage) const
 {
-    return host_results[first_async_slot + 2 * parity + stage];     // already folded over ranks by prepare_next
+    const auto& r = host_results[first_async_slot + 2 * parity + stage];     // already folded over ranks by prepare_next
+    if (num_ranks > 1 && impl->peer_transport) throw_if_called_off(r.pad);
+    return r;
 }
 
 int device_solver_t::async_slot(int parity, int stage) const
@@ -2589,6 +2592,7 @@ void device_solver_t::set_communicator(communicator_t* comm)
         // second buffer starts where rank p says -- which this rank learns from p's own layout words
         impl->peers.halo_flag[p]   = reinterpret_cast<unsigned long long*>(base);
         impl->peers.result_flag[p] = reinterpret_cast<unsigned long long*>(base + 512);
+        impl->peers.abort_word[p]  = reinterpret_cast<unsigned long long*>(base + 256);
         impl->peers.results[p]     = reinterpret_cast<stage_result_t*>(base + flags_bytes);
         impl->peers.recv[p][0]     = reinterpret_cast<double*>(base + flags_bytes + results_bytes);
         impl->peers.recv[p][1]     = nullptr;       // set below from rank p's landing size
@@ -2612,6 +2616,13 @@ void device_solver_t::set_communicator(communicator_t* comm)
     {
         M3B_CUDA(cudaMalloc(&impl->d_push_entries, push.size() * sizeof(halo_entry_dev_t)));
         M3B_CUDA(cudaMemcpy(impl->d_push_entries, push.data(), push.size() * sizeof(halo_entry_dev_t), cudaMemcpyHostToDevice));
+    }
+    {
+        // how long a rank waits for a peer before it calls the run off (M3B_SPIN_DEADLINE_MS; default 30 s of SM clocks)
+        const char* e = std::getenv("M3B_SPIN_DEADLINE_MS");
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
+        impl->peers.deadline_cycles = static_cast<long long>((e ? std::atof(e) : 30000.0) * khz);
     }
     impl->peer_transport = true;
 
@@ -2668,7 +2679,7 @@ void device_solver_t::exchange_on(void* cuda_stream, device_field_t& field)
         if (impl->num_recv_entries)
         {
             halo_wait_unpack<<<impl->num_recv_entries, 128, 0, u>>>(impl->d_recv_entries, field.data, cells, N, impl->peers.recv[rank_][parity],
-                impl->peers.halo_flag[rank_], counter, impl->d_push_ticket + 1, impl->d_ready);
+                impl->peers.halo_flag[rank_], counter, impl->d_push_ticket + 1, impl->d_ready, impl->peers, rank_);
             ++launches;
         }
         if (u != s) M3B_CUDA(cudaEventRecord(impl->halo_ready, u));
@@ -2712,9 +2723,19 @@ void device_solver_t::gather_results()
     M3B_CUDA(cudaMemcpyAsync(impl->h_results_all, impl->d_results_all, size_t(num_ranks) * num_slots * sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
 }
 
+/** Some rank gave up waiting for a peer (bounded_wait_sys): name both in an exception, which the C ABI turns into M3B_ERROR. */
+static void throw_if_called_off(unsigned int word)
+{
+    if (word == 0) return;
+    const unsigned waiting = (word - 1) & 255u, awaited = (word - 1) >> 8;
+    throw std::runtime_error("mara3_b200: rank " + std::to_string(waiting) + " waited longer than the deadline (M3B_SPIN_DEADLINE_MS) for rank "
+        + std::to_string(awaited) + " to deliver its guard zones or stage results; the run was called off on every rank");
+}
+
 stage_result_t device_solver_t::stage_result(int slot) const
 {
     if (num_ranks == 1) return host_results[slot];
+    if (impl->peer_transport) throw_if_called_off(host_results[slot].pad);
 
     // fold the ranks in rank order: every rank computes the same bits
     auto r = stage_result_t();

@@ -246,7 +246,12 @@ namespace
             if (threadIdx.x == 0)
             {
                 unsigned long long v;
-                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); } while (v < mesh.ready_value);
+                // (bounded: the unpack kernel that publishes the flag is itself bounded by the peers' deadline, bounded_wait_sys;
+                // if it never became resident beside this kernel -- a profiler serialising kernels, a foreign stream -- give up
+                // after ~70 s of SM clocks rather than hang: the step then fails its parity, it does not block the GPU)
+                const long long t0 = clock64();
+                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mesh.ready_flag) : "memory"); }
+                while (v < mesh.ready_value && clock64() - t0 < (1ll << 37));
             }
             __syncthreads();
         }

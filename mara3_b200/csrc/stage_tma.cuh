@@ -163,7 +163,7 @@ namespace m3b { namespace dev { namespace
             __syncthreads();
             if (n >= X.n_recv) break;
             const halo_entry_dev_t e = X.recv[n];
-            if (threadIdx.x == 0) while (load_acquire_sys(flags + e.pad) < X.counter) { }
+            if (threadIdx.x == 0) bounded_wait_sys(flags + e.pad, X.counter, X.peers, X.me, e.pad);      // (gives up only when the run is called off)
             __syncthreads();
             const int cells = e.ni * e.nj;
             for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
@@ -179,7 +179,12 @@ namespace m3b { namespace dev { namespace
         if (threadIdx.x == 0)
         {
             int done;
-            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(cnt + 2) : "memory"); } while (done < X.n_recv);
+            unsigned n = 0;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(cnt + 2) : "memory");
+                if ((++n & 1023u) == 0 && load_acquire_sys(X.peers.abort_word[X.me]) != 0) break;       // a CTA that holds strips gave up on its peer
+            } while (done < X.n_recv);
             if (X.clock_words)
             {
                 unsigned long long t1;

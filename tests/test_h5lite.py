@@ -98,3 +98,19 @@ def test_leaf_dataset_names_match_the_reference_known_answers():
     assert name(5, 1, 16) == "5:01-16"
     assert name(8, 1, 2) == "8:001-002"
     assert name(4, 15, 0) == "4:15-00" and name(10, 1023, 7) == "10:1023-0007"
+
+
+def test_a_file_shared_between_ranks_is_the_file_one_rank_writes(tmp_path):
+    """Multi-GPU product writers: rank 0 writes the structure and its own blocks and leaves holes, every other rank stores its
+    blocks at the addresses it has computed itself (h5lite roles root / part).  Byte for byte the single-writer file."""
+    lib = m3.load_library()
+    lib.m3b_h5_selftest_shared.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    for parts in (2, 3, 8):
+        whole, shared = tmp_path / f"whole{parts}.h5", tmp_path / f"shared{parts}.h5"
+        assert lib.m3b_h5_selftest_shared(str(whole).encode(), str(shared).encode(), parts) == 0
+        a, b = whole.read_bytes(), shared.read_bytes()
+        assert len(a) == len(b) and a == b
+    f = H5File(str(tmp_path / "shared8.h5"))
+    assert len(f.keys("/solution/conserved_u")) == 37
+    block = f.read("/solution/conserved_u/6:36-01")
+    assert block.shape == (5, 5, 3) and block[0, 0, 0] == 1.0 / (36 * 75 + 1)
