@@ -20,9 +20,21 @@ def test_two_ranks_match_one():
     assert "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_a_stalled_peer_is_reported_not_waited_for_forever():
+    """Every wait on another rank is bounded (bounded_wait_sys): a rank whose peer stops stepping gets M3B_ERROR naming the peer
+    after the deadline, instead of spinning on a flag for ever (tools/stalled_peer_check.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tools", "stalled_peer_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert "STALLED_PEER_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_two_rank_subprogram_writes_the_same_products(tmp_path):
-    """`binary` on two GPUs (tools/run_binary.py under torchrun) against the single-GPU executable: rank 0 writes the
-    gathered checkpoint / diagnostics; fields bit-identical, time-series sums to rounding (per-rank partial sums)."""
+    """`binary` on two GPUs (tools/run_binary.py under torchrun) against the single-GPU executable: both ranks write
+    their own blocks into the one checkpoint / diagnostics file; fields bit-identical, time-series sums to rounding (per-rank partial sums)."""
     import numpy as np
     import torch
     if torch.cuda.device_count() < 2:
