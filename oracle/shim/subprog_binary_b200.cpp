@@ -16,6 +16,8 @@
  * solution_t <-> flat arrays always goes through mara::get<I> (the std::tuple memory image is reversed under libstdc++).
  */
 #include <cstdio>
+#include <map>
+#include <tuple>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -78,23 +80,34 @@ namespace
         return f;
     }
 
-    /** a tree with the topology and block shapes of `like`, its cells taken from the flat array */
+    /**
+     * A tree with the topology of `like` (square blocks of one size), its cells taken from the flat array.  The position of a
+     * block in the flat array is its ordinal in the tree's traversal (sink) order; tree.map() must not be trusted to visit the
+     * children in that order (core_sequence.hpp:436-439 expands them as function arguments), so the ordinal is looked up by index.
+     */
     template<typename Tree>
     Tree tree_from_flat(const Tree& like, const std::vector<double>& u)
     {
-        auto at = std::size_t(0);
-        return like.map([&u, &at] (auto block)
+        using key_type = std::tuple<std::size_t, std::size_t, std::size_t>;
+        auto key = [] (const mara::tree_index_t<2>& i) { return key_type(i.level, i.coordinates[0], i.coordinates[1]); };
+        auto ordinal = std::map<key_type, std::size_t>();
+        like.indexes().sink([&] (auto index) { const auto n = ordinal.size(); ordinal[key(index)] = n; });
+        const std::size_t nn = u.size() / (3 * ordinal.size());
+        auto n1 = std::size_t(0);
+        while (n1 * n1 < nn) ++n1;
+
+        return like.indexes().map([&u, &ordinal, key, nn, n1] (auto index)
         {
-            using cell_type = std::decay_t<decltype(block(0, 0))>;
-            using T0 = std::decay_t<decltype(mara::get<0>(block(0, 0)))>;
-            using T1 = std::decay_t<decltype(mara::get<1>(block(0, 0)))>;
-            using T2 = std::decay_t<decltype(mara::get<2>(block(0, 0)))>;
-            const std::size_t ni = block.shape(0), nj = block.shape(1), nn = ni * nj;
-            auto out = nd::make_unique_array<cell_type>(ni, nj);
-            for (std::size_t i = 0; i < ni; ++i)
-                for (std::size_t j = 0; j < nj; ++j)
-                    out(i, j) = mara::make_arithmetic_tuple(T0{u[at + i * nj + j]}, T1{u[at + nn + i * nj + j]}, T2{u[at + 2 * nn + i * nj + j]});
-            at += 3 * nn;
+            using block_type = std::decay_t<decltype(like.at(index))>;
+            using cell_type = typename block_type::value_type;
+            using T0 = std::decay_t<decltype(mara::get<0>(std::declval<cell_type>()))>;
+            using T1 = std::decay_t<decltype(mara::get<1>(std::declval<cell_type>()))>;
+            using T2 = std::decay_t<decltype(mara::get<2>(std::declval<cell_type>()))>;
+            const std::size_t at = ordinal.at(key(index)) * 3 * nn;
+            auto out = nd::make_unique_array<cell_type>(n1, n1);
+            for (std::size_t i = 0; i < n1; ++i)
+                for (std::size_t j = 0; j < n1; ++j)
+                    out(i, j) = mara::make_arithmetic_tuple(T0{u[at + i * n1 + j]}, T1{u[at + nn + i * n1 + j]}, T2{u[at + 2 * nn + i * n1 + j]});
             return std::move(out).shared();
         });
     }
