@@ -51,9 +51,9 @@ ALGORITHMIC_BYTES_PER_CELL_LAUNCH = 60.0    # mean over the two stage launches o
 
 
 def ncu_traffic(workload, local_cells):
-    """DRAM bytes per stage launch from the committed ncu --set full capture (profiles/r01_traffic.json), if it is of this workload."""
+    """DRAM bytes per stage launch from the committed ncu --set full capture (profiles/r02_traffic.json), if it is of this workload."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
         if t["workload"] == workload and t["algorithmic_bytes_per_launch"] == local_cells * ALGORITHMIC_BYTES_PER_CELL_LAUNCH:
             return t["traffic_bytes_per_launch"]

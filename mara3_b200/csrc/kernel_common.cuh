@@ -179,7 +179,8 @@ namespace m3b { namespace dev
         int N;              // block size
         bool fast;          // branch-free equation of state
         int stage_mode;     // 0: flags from stage_t, 1 / 2: first / last stage of an adaptive RK2 step
-        int grid;           // resident CTAs
+        int grid;           // CTAs asked for (clamped to what is resident at once)
+        int ctas_per_sm;    // 3: two tile buffers, 168 registers; 4: one buffer, 128 registers
         fused_exchange_t exchange;
     };
     void stage_tma_configure();

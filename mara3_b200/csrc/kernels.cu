@@ -1419,7 +1419,7 @@ struct device_solver_t::impl_t
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     bool tma = false;                       // regular blocks through stage_tma (persistent, cp.async.bulk staging); M3B_STAGE=strip: stage_strip
     bool tma_fast = false;                  // stage_tma's branch-free equation of state (fast_eos and alpha > 0)
-    int tma_ctas_per_sm = 3;                // M3B_TMA_CTAS
+    int tma_ctas_per_sm = 0;                // M3B_TMA_CTAS: 3 (two tile buffers, 168 registers) or 4 (one buffer, 128 registers); 0: per launch, see launch_fused
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
@@ -1869,7 +1869,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         // stage_tma: linear-momentum variables only (conserved_q keeps stage_strip<.., QMODE>)
         impl->tma = sd.conserve_linear_p;
         if (const char* e = std::getenv("M3B_STAGE")) impl->tma = impl->tma && std::string(e) != "strip";
-        if (const char* e = std::getenv("M3B_TMA_CTAS")) impl->tma_ctas_per_sm = std::max(1, std::min(3, std::atoi(e)));
+        if (const char* e = std::getenv("M3B_TMA_CTAS")) impl->tma_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
         impl->tma_fast = impl->fast_eos && sd.alpha > 0.0;
         stage_tma_configure();      // stage_tma.cu
     }
@@ -2208,7 +2208,17 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             a.model = impl->model; a.stage = st; a.tile_info = impl->d_tile_info + size_t(first) * tpb; a.num_tiles = ctas;
             a.Uin = in.data; a.Un = un_data; a.Uout = out.data; a.partials = tiles; a.fail = impl->d_fail + slot;
             a.N = N; a.fast = impl->tma_fast; a.stage_mode = stage_mode;
-            a.grid = std::min(ctas, impl->sm_count * impl->tma_ctas_per_sm);       // persistent: every CTA walks the tile list with stride `grid`
+            // Persistent CTAs take the tiles in rounds of (SMs x CTAs per SM).  A tile costs a 4-per-SM CTA (one buffer, its load
+            // exposed) 1.36 x what it costs a 3-per-SM CTA (measured on 4096^2: 10.6 against 7.8 us), so 4 per SM only pays
+            // where it saves a whole round -- short tile lists, as on 8 GPUs (4096 tiles: 7 rounds instead of 10).
+            int per_sm = impl->tma_ctas_per_sm;
+            if (per_sm == 0)
+            {
+                const int r3 = (ctas + 3 * impl->sm_count - 1) / (3 * impl->sm_count), r4 = (ctas + 4 * impl->sm_count - 1) / (4 * impl->sm_count);
+                per_sm = 1.36 * r4 < double(r3) ? 4 : 3;
+            }
+            a.ctas_per_sm = per_sm;
+            a.grid = std::min(ctas, impl->sm_count * per_sm);       // persistent: every CTA walks the tile list with stride `grid`
             stage_tma_launch(a, s);
         }
         else if (impl->strip)

@@ -32,9 +32,10 @@
 
 namespace m3b { namespace dev { namespace
 {
+    template<int NBUF>
     struct tma_smem_t
     {
-        double P[2][3][SX + 4][SY + 4];     // raw conserved rows as the bulk copies deliver them, then primitives (in place); two tiles
+        double P[NBUF][3][SX + 4][SY + 4];     // raw conserved rows as the bulk copies deliver them, then primitives (in place); two tiles
         double G[6][SX + 2][SY + 2];        // 2 x un-divided PLM differences d/dx (3), d/dy (3) on tile + 1 halo
         double XB[3][4][SY];                // x-face fluxes at rows 4, 8, 12 (strip starts) and 16 (tile boundary): the high-x flux of strip w is XB[.][w]
         double YB[3][SX];                   // y-face fluxes at the tile's high-y boundary
@@ -49,7 +50,6 @@ namespace m3b { namespace dev { namespace
         double red[STRIP_THREADS / 32][NUM_SUMS + 1];
         double sinks[STRIP_THREADS / 32][8];
         tile_info_t info[3];                // records of the tiles k, k + 1, k + 2 (slot = ordinal % 3)
-        double negbuf[STRIP_THREADS / 32][STRIP][32];     // new densities that came out negative, until the strip is done
         int near_sink;
         int unpack_slot;                    // exchange_unpack: the strip this CTA has taken off the list
     };
@@ -69,7 +69,8 @@ namespace m3b { namespace dev { namespace
      * m = 0, 1, 2, of the (SX + 4) x (SY + 4) region = 20 rows of 18 sixteen-byte chunks (two cells in y; columns j0 - 2 and N
      * are even, so a chunk never straddles two blocks), all three fields -- into half `buf`.
      */
-    __device__ __forceinline__ void stage_tile_async(tma_smem_t& T, const tile_info_t& ti, const double* __restrict__ Uin, size_t FS,
+    template<bool PREFETCH_ONLY = false, typename SMEM>
+    __device__ __forceinline__ void stage_tile_async(SMEM& T, const tile_info_t& ti, const double* __restrict__ Uin, size_t FS,
         int t, int buf, int N, int tiles_y)
     {
         const int rr = threadIdx.x / 18, cc = threadIdx.x - 18 * rr;
@@ -90,13 +91,23 @@ namespace m3b { namespace dev { namespace
                     const int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
                     const int nb = di < 0 ? nlo : (di > 0 ? nhi : nmid);
                     const double* src = Uin + (long(nb) * N + (gi - di * N)) * N + col;
-                    cp_async_16(&T.P[buf][0][row][2 * cc], src);
-                    cp_async_16(&T.P[buf][1][row][2 * cc], src + FS);
-                    cp_async_16(&T.P[buf][2][row][2 * cc], src + 2 * FS);
+                    if (PREFETCH_ONLY)
+                    {
+                        // one buffer only (4 CTAs per SM): the tile cannot land yet, but its lines can already come from HBM into L2
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(src));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(src + FS));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 2 * FS));
+                    }
+                    else
+                    {
+                        cp_async_16(&T.P[buf][0][row][2 * cc], src);
+                        cp_async_16(&T.P[buf][1][row][2 * cc], src + FS);
+                        cp_async_16(&T.P[buf][2][row][2 * cc], src + 2 * FS);
+                    }
                 }
             }
         }
-        cp_async_commit();
+        if (! PREFETCH_ONLY) cp_async_commit();
     }
 
     /**
@@ -201,8 +212,8 @@ namespace m3b { namespace dev { namespace
     struct face_cell_t { double p[3], g[3], d1, d2; };
 
     /** cell (li, lj) of the tile as the x-faces see it (AXIS 0: differences along x) or as the y-faces see it (AXIS 1) */
-    template<int AXIS>
-    __device__ __forceinline__ face_cell_t load_face_cell(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], int li, int lj)
+    template<int AXIS, typename SMEM>
+    __device__ __forceinline__ face_cell_t load_face_cell(const SMEM& T, const double (*P)[SX + 4][SY + 4], int li, int lj)
     {
         face_cell_t c;
         #pragma unroll
@@ -234,8 +245,8 @@ namespace m3b { namespace dev { namespace
     }
 
     /** x-face between tile cells (li - 1, lj) and (li, lj), 0 <= li <= SX; yd[k] = T.y2c[k][lj] (tile-boundary faces: nothing to reuse) */
-    template<bool FAST>
-    __device__ __forceinline__ void tma_x_face(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
+    template<bool FAST, typename SMEM>
+    __device__ __forceinline__ void tma_x_face(const SMEM& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
         const strip_consts_t& C, double cvis, const double yd[3], int li, int lj, double F[3])
     {
         const eos_face_t e = tma_eos<FAST>(model, S, C, cvis, T.x2v[0][li] + yd[0], T.x2v[1][li] + yd[1], T.x2v[2][li] + yd[2]);
@@ -243,8 +254,8 @@ namespace m3b { namespace dev { namespace
     }
 
     /** y-face between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= SY; yd[k] = T.y2v[k][lj] */
-    template<bool FAST>
-    __device__ __forceinline__ void tma_y_face(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
+    template<bool FAST, typename SMEM>
+    __device__ __forceinline__ void tma_y_face(const SMEM& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
         const strip_consts_t& C, double cvis, const double yd[3], int li, int lj, double F[3])
     {
         const eos_face_t e = tma_eos<FAST>(model, S, C, cvis, T.x2c[0][li] + yd[0], T.x2c[1][li] + yd[1], T.x2c[2][li] + yd[2]);
@@ -255,8 +266,8 @@ namespace m3b { namespace dev { namespace
      * Both low faces of cell (li, lj): the cell itself is read once for the two of them, and the cell above comes from the
      * row before in registers (`up` in, this cell out) -- 17 shared-memory loads per cell instead of 32.
      */
-    template<bool FAST>
-    __device__ __forceinline__ void tma_cell_faces(const tma_smem_t& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
+    template<bool FAST, typename SMEM>
+    __device__ __forceinline__ void tma_cell_faces(const SMEM& T, const double (*P)[SX + 4][SY + 4], const model_t& model, const stage_t& S,
         const strip_consts_t& C, double cvis, const double ydc[3], const double ydv[3], int li, int lj, face_cell_t& up, double Fx[3], double Fy[3])
     {
         const eos_face_t ex = tma_eos<FAST>(model, S, C, cvis, T.x2v[0][li] + ydc[0], T.x2v[1][li] + ydc[1], T.x2v[2][li] + ydc[2]);
@@ -275,7 +286,7 @@ namespace m3b { namespace dev { namespace
     /** what tma_rows needs to know about the tile */
     struct rows_args_t
     {
-        const double (*P)[SX + 4][SY + 4];
+        double (*P)[SX + 4][SY + 4];
         double dt_over_h, cvis, yc, dy1, dy2;
         int b, i0, j0, N;
         size_t FS;
@@ -289,8 +300,8 @@ namespace m3b { namespace dev { namespace
      * scheme.cpp:568-587), software-pipelined down the strip.  SINK: some cell of the tile lies within the sinks' reach
      * (warp-uniform, decided per tile); has_buffer: the buffer-zone rate is non-zero somewhere in the tile (else its inputs are not loaded).  Contains ONE __syncthreads.
      */
-    template<bool FAST, int MODE, bool SINK>
-    __device__ __forceinline__ void tma_rows(tma_smem_t& T, const model_t& model, const stage_t& S, const strip_consts_t& C, const rows_args_t& A,
+    template<bool FAST, int MODE, bool SINK, typename SMEM>
+    __device__ __forceinline__ void tma_rows(SMEM& T, const model_t& model, const stage_t& S, const strip_consts_t& C, const rows_args_t& A,
         bool has_buffer, bool combine, bool compute_dt, strip_sums_t& sums, double& amax)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -300,7 +311,7 @@ namespace m3b { namespace dev { namespace
         const double ydc[3] = {T.y2c[0][lj], T.y2c[1][lj], T.y2c[2][lj]};      // x-faces and cell centres share the column's y-part
         const double ydv[3] = {T.y2v[0][lj], T.y2v[1][lj], T.y2v[2][lj]};
         const size_t c0 = (size_t(A.b) * N + (A.i0 + li0)) * N + (A.j0 + lj);
-        unsigned negative = 0;          // bit r: the new density of strip row r is negative (its value waits in T.negbuf)
+        unsigned negative = 0;          // bit r: the new density of strip row r is negative (its value waits in the cell's slot of P)
 
         auto update_cell = [&] (int r, const double* u, const double* u0, double br, const double* un,
                                 const double* FxLo, const double* FxHi, const double* FyLo)
@@ -331,7 +342,7 @@ namespace m3b { namespace dev { namespace
 #ifndef M3B_HOT_PATH_ONLY
             // validate_u (scheme.cpp:726-752) without a branch in the strip: remember the value, report after the last row
             const bool neg = __double2hiint(n0) < 0;
-            if (neg) T.negbuf[warp][r][lane] = n0;
+            if (neg) A.P[0][li + 2][lj + 2] = n0;           // (the cell's own sigma slot: nobody reads it any more)
             negative |= neg ? 1u << r : 0u;
 #endif
             if (combine)
@@ -365,11 +376,13 @@ namespace m3b { namespace dev { namespace
             if (combine) { un[0] = ldv(A.Un + c); un[1] = ldv(A.Un + FS + c); un[2] = ldv(A.Un + 2 * FS + c); }
         };
 
-        // the update inputs of row r are asked for BEFORE the faces of row r and used after the faces of row r + 1
-        // (two register sets, alternating): at least a row of face arithmetic lies between every load and its use,
-        // also for the last row of the strip
+        // DEEP (3 CTAs per SM, 168 registers): the update inputs of row r are asked for BEFORE the faces of row r and used after
+        // the faces of row r + 1 (two register sets, alternating): at least a row of face arithmetic lies between every load and
+        // its use, also for the last row of the strip.  Otherwise (4 CTAs per SM, 128 registers): one set, asked for before the
+        // faces of the NEXT row -- a row of faces between load and use -- and the last row's behind its own faces.
+        constexpr bool DEEP = sizeof(T.P) > sizeof(T.P[0]);
         double u[2][3], u0[2][3], un[3], un_last[3], br[2];
-        load_cell(0, u[0], u0[0], br[0]);        // in flight during the prologue
+        if (DEEP) load_cell(0, u[0], u0[0], br[0]);        // in flight during the prologue
 
         // prologue: tile-boundary faces (high-x row by warp 0, high-y column by half of warp 1), then the faces of strip
         // row 0, whose x-flux is also the high-x flux of the strip below
@@ -397,11 +410,14 @@ namespace m3b { namespace dev { namespace
         for (int r = 1; r < STRIP; ++r)
         {
             double FxNew[3], FyNew[3];
-            load_cell(r, u[r & 1], u0[r & 1], br[r & 1]);
+            const int set = DEEP ? ((r - 1) & 1) : 0;
+            if (DEEP) load_cell(r, u[r & 1], u0[r & 1], br[r & 1]); else load_cell(r - 1, u[0], u0[0], br[0]);
             load_un(r - 1, un);
-            if (r == STRIP - 1) load_un(r, un_last);     // (the last row has no faces of a next row to hide behind)
+            if (DEEP && r == STRIP - 1) load_un(r, un_last);     // (the last row has no faces of a next row to hide behind)
+            if (! DEEP) up = load_face_cell<0>(T, A.P, li0 + r - 1, lj);      // (128 registers: re-read the cell above instead of carrying it)
             tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0 + r, lj, up, FxNew, FyNew);
-            update_cell(r - 1, u[(r - 1) & 1], u0[(r - 1) & 1], br[(r - 1) & 1], un, FxLo, FxNew, FyLo);
+            if (! DEEP && r == STRIP - 1) { load_cell(r, u[1], u0[1], br[1]); load_un(r, un_last); }       // behind them: the update of row r - 1
+            update_cell(r - 1, u[set], u0[set], br[set], un, FxLo, FxNew, FyLo);
             #pragma unroll
             for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
         }
@@ -416,21 +432,22 @@ namespace m3b { namespace dev { namespace
             for (int r = 0; r < STRIP; ++r)
                 if (negative >> r & 1)
                 {
-                    const double v = T.negbuf[warp][r][lane];
+                    const double v = A.P[0][li0 + r + 2][lj + 2];
                     if (v < 0.0) report_negative(A.fail, A.b, (A.i0 + li0 + r) * N + A.j0 + lj, v);      // (not -0.0)
                 }
         }
 #endif
     }
 
-    template<int MIN_CTAS, int NB, bool FAST, int MODE>
+    template<int MIN_CTAS, int NB, bool FAST, int MODE, int NBUF = (MIN_CTAS >= 4 ? 1 : 2)>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_tma(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info, int num_tiles,
         const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout, double* partials, fail_dev_t* fail,
         fused_exchange_t X)
     {
         extern __shared__ __align__(128) unsigned char smem_raw[];
-        tma_smem_t& T = *reinterpret_cast<tma_smem_t*>(smem_raw);
+        using SMEM = tma_smem_t<NBUF>;
+        SMEM& T = *reinterpret_cast<SMEM*>(smem_raw);
 
         const stage_t S = *stage_ptr;       // written by the host or by prepare_next of the step before
         // MODE 1 / 2: first / last stage of an RK2 step with adaptive dt, flags known at compile time; 0: read them from S
@@ -471,7 +488,8 @@ namespace m3b { namespace dev { namespace
 
         for (int k = 0; tile < num_tiles; ++k, tile += gridDim.x)
         {
-            const int buf = k & 1;
+            const int buf = NBUF == 2 ? (k & 1) : 0, nbuf = NBUF == 2 ? (buf ^ 1) : 0;       // P half of this tile / of the next; cx, cy, hh alternate either way
+            const int cb = k & 1;
             const int next = tile + int(gridDim.x);
             const bool has_next = next < num_tiles;
             const tile_info_t& tin = T.info[(k + 1) % 3];
@@ -482,7 +500,8 @@ namespace m3b { namespace dev { namespace
             {
                 if (! ghosts_ready && next >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
                 const int tn = next % tpb;
-                stage_tile_async(T, tin, Uin, FS, tn, buf ^ 1, N, tiles_y);
+                if (NBUF == 2) stage_tile_async(T, tin, Uin, FS, tn, nbuf, N, tiles_y);
+                else stage_tile_async<true>(T, tin, Uin, FS, tn, 0, N, tiles_y);
                 if (warp == 0)
                 {
                     const double* xvg = mesh.xv + size_t(tin.b) * (N + 1) + (tn / tiles_y) * SX;
@@ -494,13 +513,13 @@ namespace m3b { namespace dev { namespace
                 else if (warp == 1 && lane < 3 && next + int(gridDim.x) < num_tiles)
                     rec = __ldg(reinterpret_cast<const int4*>(tile_info + next + gridDim.x) + lane);
             }
-            else cp_async_commit();     // (an empty group keeps the wait below uniform)
+            else if (NBUF == 2) cp_async_commit();     // (an empty group keeps the wait below uniform)
 
             const int b = T.info[k % 3].b, flags = T.info[k % 3].flags;
             const int t = tile % tpb;
             const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
             const bool has_buffer = flags & 1;
-            const double h = T.hh[buf][0], inv_h = T.hh[buf][1];
+            const double h = T.hh[cb][0], inv_h = T.hh[cb][1];
             const double cvis = 0.125 * inv_h;      // 0.5 nu x face average 0.5 x (1 / 2h) of the doubled differences
 
             // the update phase's inputs are first touched several us from now: pull their lines into L2 already
@@ -533,13 +552,13 @@ namespace m3b { namespace dev { namespace
                 {
                     if (lane <= SX)
                     {
-                        const double xv = T.cx[buf][lane];
+                        const double xv = T.cx[cb][lane];
                         #pragma unroll
                         for (int q = 0; q < 3; ++q) { const double d = (xv - bx[q]) * (q == 2 ? cf : 1.0); T.x2v[q][lane] = d * d; }
                     }
                     if (lane < SX)
                     {
-                        const double xc = 0.5 * (T.cx[buf][lane] + T.cx[buf][lane + 1]);
+                        const double xc = 0.5 * (T.cx[cb][lane] + T.cx[cb][lane + 1]);
                         T.xc[lane] = xc;
                         T.dxc[0][lane] = xc - bx[0];
                         T.dxc[1][lane] = xc - bx[1];
@@ -549,7 +568,7 @@ namespace m3b { namespace dev { namespace
                 }
                 else if (warp == 2)
                 {
-                    const double yv = T.cy[buf][lane], yc = 0.5 * (yv + T.cy[buf][lane + 1]);
+                    const double yv = T.cy[cb][lane], yc = 0.5 * (yv + T.cy[cb][lane + 1]);
                     #pragma unroll
                     for (int q = 0; q < 3; ++q)
                     {
@@ -560,11 +579,11 @@ namespace m3b { namespace dev { namespace
                 }
                 else if (warp == 3 && lane == 0)
                 {
-                    const double yv = T.cy[buf][SY];
+                    const double yv = T.cy[cb][SY];
                     #pragma unroll
                     for (int q = 0; q < 3; ++q) { const double dv = (yv - by[q]) * (q == 2 ? cf : 1.0); T.y2v[q][SY] = fma(dv, dv, soft[q]); }
                     // does any cell of the tile lie within the sinks' reach (a2 = dr^2 / (2 s^2) < 100)?  distance of each body to the tile's rectangle
-                    const double xlo = T.cx[buf][0], xhi = T.cx[buf][SX], ylo = T.cy[buf][0], yhi = yv;
+                    const double xlo = T.cx[cb][0], xhi = T.cx[cb][SX], ylo = T.cy[cb][0], yhi = yv;
                     bool near = false;
                     #pragma unroll
                     for (int q = 0; q < 2; ++q)
@@ -578,7 +597,7 @@ namespace m3b { namespace dev { namespace
 
             // ------------------------------------------------------------------ phase 0: this thread's chunks of the tile, primitives in place
             // (all but the newest group: the chunks asked for during tile k - 1)
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
             double (*P)[SX + 4][SY + 4] = T.P[buf];
             {
                 // 20 rows of 18 sixteen-byte chunks (two cells in y): thread <-> (row rr + 7 m, chunk cc), m = 0, 1, 2
@@ -646,10 +665,10 @@ namespace m3b { namespace dev { namespace
                 // the next tile's vertex coordinates have arrived long ago
                 if (warp == 0 && has_next)
                 {
-                    if (lane <= SX) T.cx[buf ^ 1][lane] = nx;
-                    T.cy[buf ^ 1][lane] = ny;
-                    if (lane == 0) T.cy[buf ^ 1][SY] = ny32;
-                    if (lane == 1 || lane == 2) T.hh[buf ^ 1][lane - 1] = ny32;
+                    if (lane <= SX) T.cx[cb ^ 1][lane] = nx;
+                    T.cy[cb ^ 1][lane] = ny;
+                    if (lane == 0) T.cy[cb ^ 1][SY] = ny32;
+                    if (lane == 1 || lane == 2) T.hh[cb ^ 1][lane - 1] = ny32;
                 }
                 else if (warp == 1 && lane < 3 && has_next && next + int(gridDim.x) < num_tiles)
                     reinterpret_cast<int4*>(&T.info[(k + 2) % 3])[lane] = rec;
@@ -659,7 +678,7 @@ namespace m3b { namespace dev { namespace
             // ------------------------------------------------------------------ phases 2 + 3: faces, update
             strip_sums_t sums = {{0.0, 0.0}, {0.0, 0.0}, 0.0, 0.0, 0.0};
             double amax = 0.0;                              // largest signal speed of the updated cells
-            const double yc = 0.5 * (T.cy[buf][lane] + T.cy[buf][lane + 1]);
+            const double yc = 0.5 * (T.cy[cb][lane] + T.cy[cb][lane + 1]);
             const double dy1 = yc - S.y1, dy2 = yc - S.y2;
             {
                 const rows_args_t A = {P, S.dt * inv_h, cvis, yc, dy1, dy2, b, i0, j0, N, FS, Uin, Un, Uout, U0, BR, fail};
@@ -718,6 +737,8 @@ namespace m3b { namespace dev { namespace
                 // min over cells of h / wavespeed = h / max wavespeed: one division per tile
                 row[q] = q == NUM_SUMS ? (compute_dt ? h / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (h * h);
             }
+            // one buffer: only now is P free for the next tile (its lines were pulled into L2 a tile ago)
+            if (NBUF == 1 && has_next) stage_tile_async(T, tin, Uin, FS, next % tpb, 0, N, tiles_y);
         }
     }
 }}}
