@@ -93,7 +93,8 @@ uint64_t    m3b_halo_bytes_per_exchange(const m3b_solver_t* s);
 /* guard-zone transport in use: 0 none (one rank), 1 NCCL send / recv, 2 peer memory over NVLink (CUDA IPC mailboxes) */
 int         m3b_exchange_transport(const m3b_solver_t* s);
 /* ---- HDF5 products and the subprogram itself (no libhdf5 needed: mara3_b200/csrc/h5lite.cpp) ----
- * (with several ranks the writers are collective calls: every rank hands its blocks to rank 0, which writes the file)
+ * (with several ranks the writers are collective calls: rank 0 writes the file's structure and its own blocks, every other rank
+ *  stores its blocks at their addresses in that file; if any rank fails, every rank returns M3B_ERROR)
  * m3b_write_checkpoint   replaces mara::write<state_t> into chkpt.NNNN.h5 (subprog_binary_io.cpp:131-158) for a solution
  *                        with the initial schedule and an empty time series; the run loop below stores its full state
  * m3b_write_diagnostics  replaces mara::write<diagnostic_fields_t> (subprog_binary_io.cpp:160-172, subprog_binary_diagnostics.cpp:48-82)
