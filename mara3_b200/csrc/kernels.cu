@@ -32,12 +32,11 @@
 #include "device_solver.hpp"
 #include "iso2d_device.cuh"
 #include "kernel_common.cuh"
+#include "device_solver_impl.cuh"
 
 using namespace m3b;
 using namespace m3b::dev;
 
-#define M3B_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-    throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
 
 namespace
 {
@@ -769,14 +768,6 @@ namespace
         }
     }
 
-    /** What prepare_next needs to set up the following step without the host (constant while the binary is not live). */
-    struct step_config_t
-    {
-        elements_t elements;
-        double cfl_number, recommended_time_step, theta;
-        int fixed_dt;
-    };
-
     __device__ void fill_stage(stage_t& st, double time, double dt, double theta, const two_body_t& b, double rk_b0, int combine, int compute_dt)
     {
         st.time = time; st.dt = dt; st.theta = theta;
@@ -884,23 +875,6 @@ namespace
             else        { next_b->time = t_next + dt_next; next_b->dt = dt_next; }
         }
     }
-
-    /** Optional epilogue of finish_stage (single rank): what prepare_next does, in the last CTA of the step's last stage. */
-    struct prepare_args_t
-    {
-        int enabled;
-        step_config_t cfg;
-        const stage_t* current_a;       // first stage of the step that is ending (its time and dt)
-        stage_t* next_a;
-        stage_t* next_b;
-        // enabled == 2: several ranks, results exchanged through the peer mailboxes (peer_prepare)
-        peer_table_t peers;
-        const stage_result_t* local;
-        stage_result_t* host_results;
-        int me, nranks, slot_stride, slot_a, slot_b;
-        unsigned long long counter;
-        unsigned long long* clock_words;       // stage timing: ns waited for the other ranks' results, calls
-    };
 
     /**
      * Fold the stage kernels' rows in a fixed order (deterministic) and publish the stage result.
@@ -1218,81 +1192,6 @@ namespace
     }
 
     /** One strip / corner of a block in the guard-zone exchange between ranks (partition.hpp). */
-    /** Gather (pack = 1) the listed strips of U into the send buffer, or scatter (pack = 0) the receive
-     *  buffer into the ghost blocks: the device side of extend() across GPUs (scheme.cpp:132-142). */
-    __global__ void __launch_bounds__(128) halo_copy(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
-        double* __restrict__ buffer, int pack)
-    {
-        const halo_entry_dev_t e = entries[blockIdx.x];
-        const int cells = e.ni * e.nj;
-
-        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
-        {
-            int q = k / cells, c = k % cells;
-            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
-            size_t u = q * FS + (size_t(e.block) * N + i) * N + j;
-            if (pack) buffer[e.offset + k] = U[u]; else U[u] = buffer[e.offset + k];
-        }
-    }
-
-    /**
-     * Send side of extend() across GPUs (scheme.cpp:132-142): each CTA copies one strip / corner of an owned
-     * block straight into the destination rank's landing buffer (entry.pad = destination rank, entry.offset =
-     * position in ITS buffer); the last CTA to finish raises this rank's flag on every destination.
-     */
-    __global__ void __launch_bounds__(128) halo_push(const halo_entry_dev_t* __restrict__ entries, const double* __restrict__ U, size_t FS, int N,
-        peer_table_t peers, int parity, int me, unsigned int dest_mask, unsigned long long counter, int* ticket)
-    {
-        __shared__ int is_last;
-        const halo_entry_dev_t e = entries[blockIdx.x];
-        const int cells = e.ni * e.nj;
-        double* __restrict__ dst = peers.recv[e.pad][parity] + e.offset;
-
-        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
-        {
-            int q = k / cells, c = k % cells;
-            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
-            dst[k] = U[q * FS + (size_t(e.block) * N + i) * N + j];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
-        __syncthreads();
-        if (! is_last) return;
-        __threadfence_system();
-        if (threadIdx.x < MAX_PEERS && ((dest_mask >> threadIdx.x) & 1u)) store_release_sys(peers.halo_flag[threadIdx.x] + me, counter);
-        if (threadIdx.x == 0) *ticket = 0;
-    }
-
-    /** Receive side: wait for the source rank's flag (entry.pad = source rank), then scatter its strip into the ghost block. */
-    __global__ void __launch_bounds__(128) halo_wait_unpack(const halo_entry_dev_t* __restrict__ entries, double* __restrict__ U, size_t FS, int N,
-        const double* __restrict__ landing, const unsigned long long* flags, unsigned long long counter, int* ticket, unsigned long long* ready,
-        peer_table_t peers, int me)
-    {
-        __shared__ int is_last;
-        const halo_entry_dev_t e = entries[blockIdx.x];
-        if (threadIdx.x == 0) bounded_wait_sys(flags + e.pad, counter, peers, me, e.pad);
-        __syncthreads();
-        const int cells = e.ni * e.nj;
-
-        for (int k = threadIdx.x; k < 3 * cells; k += blockDim.x)
-        {
-            int q = k / cells, c = k % cells;
-            int i = e.i0 + c / e.nj, j = e.j0 + c % e.nj;
-            U[q * FS + (size_t(e.block) * N + i) * N + j] = __ldcg(landing + e.offset + k);     // written by a peer: not through L1
-        }
-        // the last CTA tells the stage kernel's boundary tiles that every ghost block is in place
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
-        __syncthreads();
-        if (is_last && threadIdx.x == 0)
-        {
-            *ticket = 0;
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(ready), "l"(counter) : "memory");
-        }
-    }
-
     /**
      * disk_mass and disk_angular_momentum of the time series (subprog_binary_diagnostics.cpp:19-41): per block the
      * sums of sigma dA and (x py - y px) dA, folded in a fixed order; the host adds the blocks in tree order.
@@ -1403,117 +1302,6 @@ device_field_t::~device_field_t()
 // ===========================================================================
 // device_solver_t
 // ===========================================================================
-static void throw_if_called_off(unsigned int word);
-
-struct device_solver_t::impl_t
-{
-    mesh_dev_t mesh {};
-    model_t model {};
-    int tile_x = 0, tile_y = 0;
-    int num_global_blocks = 0;
-    int num_interior = 0;                   // leading entries of `regular` that touch no ghost block
-    bool overlap_exchange = false;          // M3B_OVERLAP_EXCHANGE=1: exchange on its own stream beside the interior update
-    cudaStream_t comm_stream = nullptr;     // guard-zone exchange runs here, beside the interior update
-    cudaEvent_t input_ready = nullptr, halo_ready = nullptr;
-    bool fast_eos = false;                  // default equation of state / viscosity: branch-free kernel variant
-    bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
-    bool tma = false;                       // regular blocks through stage_tma (persistent, cp.async.bulk staging); M3B_STAGE=strip: stage_strip
-    bool tma_fast = false;                  // stage_tma's branch-free equation of state (fast_eos and alpha > 0)
-    int tma_ctas_per_sm = 0;                // M3B_TMA_CTAS: 3 (two tile buffers, 168 registers) or 4 (one buffer, 128 registers); 0: per launch, see launch_fused
-    unsigned char* d_tile_flags = nullptr;
-    tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
-    tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
-    cudaStream_t jump_stream = nullptr;     // stage_strip<.., JUMP> runs here, beside the regular blocks' launch
-    cudaEvent_t gradients_done = nullptr, jump_done = nullptr;   // fork (stage input ready on the compute stream) and join
-    bool jump_mode0 = false;                // M3B_JUMP_MODE0=1: run-time stage flags in the JUMP variant (experiment)
-    bool serial_jump = false;               // M3B_SERIAL_JUMP=1: the jump blocks' launch follows the regular blocks' on the compute stream
-    bool jump_strip = false;                // blocks at jumps take stage_strip<.., JUMP> (M3B_JUMP_STRIP=0: the 16 x 16 any-tree kernels)
-    std::vector<int> regular, irregular, gradient_blocks;
-    int* d_regular = nullptr;
-    int* d_irregular = nullptr;
-    int* d_gradient_blocks = nullptr;
-    double* d_gradients = nullptr;
-    double* d_partials = nullptr;
-    double* d_staging = nullptr;            // [B][3][NN] for layout changes
-    fail_dev_t* d_fail = nullptr;           // [num_slots]
-    stage_result_t* d_results = nullptr;    // [num_slots]
-    std::vector<void*> owned;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
-    // stage timing on several ranks: [input ready -> ghosts unpacked] on the exchange stream, and what of it the compute stream
-    // sees: [interior blocks done -> blocks with ghost neighbours may start]
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exchange_events, gap_events;
-    unsigned long long* d_exchange_clock = nullptr;     // [0] ns spent in peer_prepare's wait for the other ranks, [1] calls, [2] ns CTAs of stage_tma spent in exchange_unpack, [3] calls
-    int* d_fused_counters = nullptr;                    // fused_exchange_t::counters
-    unsigned long long fused_launches = 0;
-    bool fused_exchange = true;                         // M3B_FUSED_EXCHANGE=0: halo_push / halo_wait_unpack kernels beside a split stage launch
-    std::vector<cudaEvent_t> event_pool;
-    size_t fused_smem = 0;
-    int sm_count = 148;
-
-    // stage inputs live in device memory (one per result slot): uploaded by the host, or written by prepare_next
-    stage_t* d_stage = nullptr;                 // [num_slots]
-    stage_t* h_stage_ring = nullptr;            // pinned staging ring for the uploads
-    int ring_next = 0;
-    double* d_partials2 = nullptr;              // second row buffer: the two stages of a step stay separate
-    double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
-    double* d_general_tile_rows[2] = {nullptr, nullptr};    // general_update_tiled: one row per tile of a block at a refinement jump
-    bool multi_cta_finish = false;              // M3B_MULTI_CTA_FINISH=1: never use finish_stage_cluster
-    bool untiled_general = false;               // M3B_UNTILED_GENERAL=1: the one-CTA-per-block any-tree update (reference for the tiled one)
-    double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows, one set per slot parity
-    size_t cta_rows_stride = 0;
-    cudaStream_t finish_stream = nullptr;       // finish_stage of a step's first stage runs here, beside the second stage
-    cudaEvent_t stage_done = nullptr, side_finish_done = nullptr;
-    prepare_args_t pending_prepare = prepare_args_t();
-    cudaEvent_t fast_prepare_done = nullptr, positions_done[2] = {nullptr, nullptr};
-    bool fresh_pipeline = false;                // the host uploaded this step's inputs: nobody has prepared the next step's positions
-    int* d_counters = nullptr;                  // per-block tile tickets, then the finish ticket
-    size_t partial_rows = 0;
-    cudaEvent_t step_done[2] = {nullptr, nullptr};
-
-    // multi-GPU: guard-zone exchange plan and cross-rank reduction of the stage results
-    communicator_t* comm = nullptr;
-    int num_send_entries = 0, num_recv_entries = 0;
-    halo_entry_dev_t* d_send_entries = nullptr;
-    halo_entry_dev_t* d_recv_entries = nullptr;
-    double* d_send_buffer = nullptr;
-    double* d_recv_buffer = nullptr;
-    // M3B_TRACE=1: CUDA events at the marks of launch_step_async, averaged and printed by the destructor
-    bool trace = false;
-    std::vector<std::vector<cudaEvent_t>> trace_steps;
-    std::vector<cudaEvent_t> trace_current;
-    std::vector<const char*> trace_names;
-    void mark(cudaStream_t s, const char* name)
-    {
-        if (! trace || trace_steps.size() >= 400) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
-        if (trace_steps.empty()) trace_names.push_back(name);
-        trace_current.push_back(e);
-    }
-    void end_step() { if (trace && ! trace_current.empty()) { trace_steps.push_back(trace_current); trace_current.clear(); } }
-    // peer-memory transport (set up in set_communicator; falls back to NCCL send / recv if CUDA IPC is unavailable)
-    bool peer_transport = false;
-    void* mailbox = nullptr;                        // this rank's mailbox: flags, results of all ranks, two landing buffers
-    std::vector<void*> peer_mailbox;                // cudaIpcOpenMemHandle mappings (null for this rank)
-    peer_table_t peers = peer_table_t();
-    halo_entry_dev_t* d_push_entries = nullptr;     // send entries addressed into the destination's landing buffer
-    std::vector<halo_entry_dev_t> send_entries_host;
-    std::vector<size_t> send_starts_host, recv_starts_host;
-    size_t recv_total = 0;
-    unsigned int dest_mask = 0;
-    unsigned long long exchange_counter = 0, step_counter = 0;
-    int* d_push_ticket = nullptr;                   // [0] halo_push, [1] halo_wait_unpack
-    unsigned long long* d_ready = nullptr;          // number of the last exchange whose ghost blocks are complete
-    bool defer_unpack = false;                      // set around the exchange of a stage launched with in-kernel waiting
-    bool in_kernel_wait = false;                    // boundary tiles wait inside the stage kernel (enough interior work to hide the exchange)
-    std::vector<const double*> send_ptr;
-    std::vector<double*> recv_ptr;
-    std::vector<size_t> send_count, recv_count;
-    stage_result_t* d_results_local = nullptr;      // [num_slots] device copy that NCCL can read
-    stage_result_t* d_results_all = nullptr;        // [nranks][num_slots]
-    stage_result_t* h_results_all = nullptr;        // pinned
-    std::uint64_t halo_bytes_per_exchange = 0;
-};
-
 device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool general_only, bool tiled_kernel) : impl(new impl_t), device_id(device), force_general(general_only)
 {
     int count = 0;
@@ -1956,46 +1744,8 @@ void device_solver_t::download(const device_field_t& src, double* host)
     M3B_CUDA(cudaStreamSynchronize(s));
 }
 
-/** Collective over the ranks: the owned blocks' data (`d_local`: [owned block][doubles_per_block], device memory) of every
- *  rank, concatenated in rank (= global Morton) order into `host_all` on rank 0.  One rank: a plain download. */
-void device_solver_t::gather_blocks(const double* d_local, std::size_t doubles_per_block, double* host_all)
-{
-    M3B_CUDA(cudaSetDevice(device_id));
-    auto s = cudaStream_t(stream_);
-    if (num_ranks == 1)
-    {
-        M3B_CUDA(cudaMemcpyAsync(host_all, d_local, size_t(BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
-        M3B_CUDA(cudaStreamSynchronize(s));
-        return;
-    }
-    const int total = impl->num_global_blocks;
-    auto offsets = std::vector<size_t>(num_ranks + 1);
-    for (int r = 0; r <= num_ranks; ++r) offsets[r] = size_t((long(total) * r) / num_ranks);       // partition_offsets
-    auto send = std::vector<const double*>(num_ranks, nullptr);
-    auto recv = std::vector<double*>(num_ranks, nullptr);
-    auto send_count = std::vector<size_t>(num_ranks, 0), recv_count = std::vector<size_t>(num_ranks, 0);
-    double* d_all = nullptr;
 
-    if (rank_ == 0)
-    {
-        M3B_CUDA(cudaMalloc(&d_all, std::max<size_t>(1, size_t(total - BO)) * doubles_per_block * sizeof(double)));
-        for (int p = 1; p < num_ranks; ++p)
-        {
-            recv[p] = d_all + (offsets[p] - offsets[1]) * doubles_per_block;
-            recv_count[p] = (offsets[p + 1] - offsets[p]) * doubles_per_block;
-        }
-    }
-    else { send[0] = d_local; send_count[0] = size_t(BO) * doubles_per_block; }
-    impl->comm->exchange(send, send_count, recv, recv_count, stream_);
 
-    if (rank_ == 0)
-    {
-        M3B_CUDA(cudaMemcpyAsync(host_all, d_local, size_t(BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
-        M3B_CUDA(cudaMemcpyAsync(host_all + size_t(BO) * doubles_per_block, d_all, size_t(total - BO) * doubles_per_block * sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
-    M3B_CUDA(cudaStreamSynchronize(s));
-    if (d_all) M3B_CUDA(cudaFree(d_all));
-}
 
 /** [block][3][N][N] of every rank's owned blocks on rank 0 (the layout of download()). */
 void device_solver_t::gather_state(const device_field_t& src, double* host_all)
@@ -2539,202 +2289,15 @@ void device_solver_t::launch_max_timestep(const device_field_t& in, double time,
     launch_finish(nullptr, 0, 1, block_rows, 1, BO, slot, 0);
 }
 
-void device_solver_t::set_communicator(communicator_t* comm)
-{
-    impl->comm = comm;
-    if (! comm || num_ranks == 1) return;
-    const char* transport = std::getenv("M3B_TRANSPORT");
-    if (transport && std::string(transport) == "nccl") return;
-    if (num_ranks > MAX_PEERS) return;
 
-    // ---- peer-memory transport: every rank maps every other rank's mailbox (CUDA IPC over NVLink); the handles and
-    // the landing-buffer layouts travel once through NCCL.  Any failure leaves the NCCL send / recv path in place.
-    M3B_CUDA(cudaSetDevice(device_id));
-    auto s = cudaStream_t(stream_);
-    const size_t flags_bytes = 1024, results_bytes = (size_t(num_ranks) * num_slots * sizeof(stage_result_t) + 255) / 256 * 256;
-    const size_t landing = (std::max<size_t>(1, impl->recv_total) * sizeof(double) + 255) / 256 * 256;
-    const size_t bytes = flags_bytes + results_bytes + 2 * landing;
-    M3B_CUDA(cudaMalloc(&impl->mailbox, bytes));
-    M3B_CUDA(cudaMemset(impl->mailbox, 0, bytes));
-    M3B_CUDA(cudaMalloc(&impl->d_push_ticket, 2 * sizeof(int)));
-    M3B_CUDA(cudaMemset(impl->d_push_ticket, 0, 2 * sizeof(int)));
-    M3B_CUDA(cudaMalloc(&impl->d_ready, sizeof(unsigned long long)));
-    M3B_CUDA(cudaMemset(impl->d_ready, 0, sizeof(unsigned long long)));
 
-    cudaIpcMemHandle_t mine;
-    bool ok = cudaIpcGetMemHandle(&mine, impl->mailbox) == cudaSuccess;
-    if (! ok) cudaGetLastError();
 
-    // per rank: [ok flag][64-byte handle as 8 doubles][recv_starts of every source rank]
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
-    const size_t words = 1 + 8 + size_t(num_ranks);
-    auto send = std::vector<double>(words, 0.0);
-    send[0] = ok ? 1.0 : 0.0;
-    std::memcpy(&send[1], &mine, sizeof(mine));
-    for (int p = 0; p < num_ranks; ++p) send[9 + p] = double(impl->recv_starts_host[p]);
-    double* d = nullptr;
-    M3B_CUDA(cudaMalloc(&d, (1 + size_t(num_ranks)) * words * sizeof(double)));
-    M3B_CUDA(cudaMemcpyAsync(d, send.data(), words * sizeof(double), cudaMemcpyHostToDevice, s));
-    comm->all_gather(d, d + words, words, stream_);
-    auto all = std::vector<double>(size_t(num_ranks) * words);
-    M3B_CUDA(cudaMemcpyAsync(all.data(), d + words, all.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    M3B_CUDA(cudaStreamSynchronize(s));
-    M3B_CUDA(cudaFree(d));
 
-    for (int p = 0; p < num_ranks; ++p) ok = ok && all[size_t(p) * words] == 1.0;
-    impl->peer_mailbox.assign(num_ranks, nullptr);
-    for (int p = 0; p < num_ranks && ok; ++p)
-    {
-        if (p == rank_) continue;
-        cudaIpcMemHandle_t h;
-        std::memcpy(&h, &all[size_t(p) * words + 1], sizeof(h));
-        if (cudaIpcOpenMemHandle(&impl->peer_mailbox[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
-    }
-    // everybody must agree, or the ranks would wait for each other on different transports
-    auto agree = all_gather_scalar(ok ? 1.0 : 0.0);
-    for (double a : agree) ok = ok && a == 1.0;
-    if (! ok) return;
 
-    for (int p = 0; p < num_ranks; ++p)
-    {
-        char* base = static_cast<char*>(p == rank_ ? impl->mailbox : impl->peer_mailbox[p]);
-        // the landing buffers of rank p have ITS size: only offsets below its recv_total are ever addressed, and the
-        // second buffer starts where rank p says -- which this rank learns from p's own layout words
-        impl->peers.halo_flag[p]   = reinterpret_cast<unsigned long long*>(base);
-        impl->peers.result_flag[p] = reinterpret_cast<unsigned long long*>(base + 512);
-        impl->peers.abort_word[p]  = reinterpret_cast<unsigned long long*>(base + 256);
-        impl->peers.results[p]     = reinterpret_cast<stage_result_t*>(base + flags_bytes);
-        impl->peers.recv[p][0]     = reinterpret_cast<double*>(base + flags_bytes + results_bytes);
-        impl->peers.recv[p][1]     = nullptr;       // set below from rank p's landing size
-    }
-    // landing size of every rank: second all-gather (one double per rank)
-    auto sizes = all_gather_scalar(double(landing));
-    for (int p = 0; p < num_ranks; ++p)
-        impl->peers.recv[p][1] = reinterpret_cast<double*>(reinterpret_cast<char*>(impl->peers.recv[p][0]) + size_t(sizes[p]));
 
-    // send entries re-addressed into the destination's landing buffer: destination p expects this rank's strips at its recv_starts[me]
-    auto push = impl->send_entries_host;
-    impl->dest_mask = 0;
-    for (auto& e : push)
-    {
-        const int p = e.pad;
-        const size_t remote_start = size_t(all[size_t(p) * words + 9 + rank_]);
-        e.offset = remote_start + (e.offset - impl->send_starts_host[p]);
-        impl->dest_mask |= 1u << p;
-    }
-    if (! push.empty())
-    {
-        M3B_CUDA(cudaMalloc(&impl->d_push_entries, push.size() * sizeof(halo_entry_dev_t)));
-        M3B_CUDA(cudaMemcpy(impl->d_push_entries, push.data(), push.size() * sizeof(halo_entry_dev_t), cudaMemcpyHostToDevice));
-    }
-    {
-        // how long a rank waits for a peer before it calls the run off (M3B_SPIN_DEADLINE_MS; default 30 s of SM clocks)
-        const char* e = std::getenv("M3B_SPIN_DEADLINE_MS");
-        int khz = 1965000;
-        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
-        impl->peers.deadline_cycles = static_cast<long long>((e ? std::atof(e) : 30000.0) * khz);
-    }
-    impl->peer_transport = true;
-
-    // With at least two full generations of interior tiles ahead of them, the boundary tiles can wait for their guard zones
-    // inside the stage kernel while the unpack runs beside it: the exchange latency disappears behind the interior update.
-    // (With less interior work the stage kernel could fill every SM with waiting CTAs before the unpack is resident.)
-    const int tpb = impl->tile_x ? (N / impl->tile_x) * (N / impl->tile_y) : 0;
-    impl->in_kernel_wait = impl->strip && impl->irregular.empty() && impl->num_interior * tpb >= 2 * impl->sm_count * 4;
-    if (const char* e = std::getenv("M3B_IN_KERNEL_WAIT")) impl->in_kernel_wait = impl->in_kernel_wait && std::atoi(e) != 0;
-}
-
-int device_solver_t::exchange_transport() const
-{
-    return num_ranks <= 1 ? 0 : (impl->peer_transport ? 2 : 1);
-}
-
-std::uint64_t device_solver_t::halo_bytes_per_exchange() const
-{
-    return impl->halo_bytes_per_exchange;
-}
-
-void device_solver_t::exchange_halos(device_field_t& field)
-{
-    if (num_ranks == 1) return;
-    exchange_on(stream_, field);
-}
-
-void device_solver_t::exchange_on(void* cuda_stream, device_field_t& field)
-{
-    if (! impl->comm) throw std::logic_error("exchange_halos: no communicator set");
-    auto s = cudaStream_t(cuda_stream);
-    M3B_CUDA(cudaSetDevice(device_id));
-
-    if (impl->peer_transport)
-    {
-        // strips go straight into the neighbours' landing buffers over NVLink; the receive kernel waits on their flags.
-        // With in-kernel waiting both kernels run on the exchange stream, beside the stage kernel that follows on `s`
-        // (its boundary tiles poll d_ready), so none of the exchange sits on the compute stream.
-        const unsigned long long counter = ++impl->exchange_counter;
-        const int parity = int(counter & 1);
-        auto u = s;
-        if (impl->in_kernel_wait && impl->defer_unpack)
-        {
-            M3B_CUDA(cudaEventRecord(impl->input_ready, s));
-            M3B_CUDA(cudaStreamWaitEvent(impl->comm_stream, impl->input_ready, 0));
-            u = impl->comm_stream;
-        }
-        if (impl->num_send_entries)
-        {
-            halo_push<<<impl->num_send_entries, 128, 0, u>>>(impl->d_push_entries, field.data, cells, N, impl->peers, parity, rank_,
-                impl->dest_mask, counter, impl->d_push_ticket);
-            ++launches;
-        }
-        if (impl->num_recv_entries)
-        {
-            halo_wait_unpack<<<impl->num_recv_entries, 128, 0, u>>>(impl->d_recv_entries, field.data, cells, N, impl->peers.recv[rank_][parity],
-                impl->peers.halo_flag[rank_], counter, impl->d_push_ticket + 1, impl->d_ready, impl->peers, rank_);
-            ++launches;
-        }
-        if (u != s) M3B_CUDA(cudaEventRecord(impl->halo_ready, u));
-        M3B_CUDA(cudaGetLastError());
-        return;
-    }
-    if (impl->num_send_entries)
-    {
-        halo_copy<<<impl->num_send_entries, 128, 0, s>>>(impl->d_send_entries, field.data, cells, N, impl->d_send_buffer, 1);
-        ++launches;
-    }
-    impl->comm->exchange(impl->send_ptr, impl->send_count, impl->recv_ptr, impl->recv_count, cuda_stream);
-
-    if (impl->num_recv_entries)
-    {
-        halo_copy<<<impl->num_recv_entries, 128, 0, s>>>(impl->d_recv_entries, field.data, cells, N, impl->d_recv_buffer, 0);
-        ++launches;
-    }
-    M3B_CUDA(cudaGetLastError());
-}
-
-std::vector<double> device_solver_t::all_gather_scalar(double value)
-{
-    auto out = std::vector<double>(num_ranks, value);
-    if (num_ranks == 1) return out;
-    auto s = cudaStream_t(stream_);
-    double* d = reinterpret_cast<double*>(impl->d_results_all);     // scratch: large enough, idle between steps
-    M3B_CUDA(cudaMemcpyAsync(d + num_ranks, &value, sizeof(double), cudaMemcpyHostToDevice, s));
-    impl->comm->all_gather(d + num_ranks, d, 1, stream_);
-    M3B_CUDA(cudaMemcpyAsync(out.data(), d, num_ranks * sizeof(double), cudaMemcpyDeviceToHost, s));
-    M3B_CUDA(cudaStreamSynchronize(s));
-    return out;
-}
-
-void device_solver_t::gather_results()
-{
-    if (num_ranks == 1) return;
-    auto s = cudaStream_t(stream_);
-    const size_t doubles = num_slots * sizeof(stage_result_t) / sizeof(double);
-    impl->comm->all_gather(reinterpret_cast<const double*>(impl->d_results_local), reinterpret_cast<double*>(impl->d_results_all), doubles, stream_);
-    M3B_CUDA(cudaMemcpyAsync(impl->h_results_all, impl->d_results_all, size_t(num_ranks) * num_slots * sizeof(stage_result_t), cudaMemcpyDeviceToHost, s));
-}
 
 /** Some rank gave up waiting for a peer (bounded_wait_sys): name both in an exception, which the C ABI turns into M3B_ERROR. */
-static void throw_if_called_off(unsigned int word)
+void m3b::throw_if_called_off(unsigned int word)
 {
     if (word == 0) return;
     const unsigned waiting = (word - 1) & 255u, awaited = (word - 1) >> 8;
