@@ -105,6 +105,7 @@ struct device_solver_t::impl_t
     double* d_block_rows[2] = {nullptr, nullptr};   // one row per block, folded by the last tile CTA of the block
     double* d_general_tile_rows[2] = {nullptr, nullptr};    // general_update_tiled: one row per tile of a block at a refinement jump
     bool multi_cta_finish = false;              // M3B_MULTI_CTA_FINISH=1: never use finish_stage_cluster
+    int gtile = 0;                              // tile of general_gradients_tiled / general_update_tiled (16, 12, 8; 0: none divides the block)
     bool untiled_general = false;               // M3B_UNTILED_GENERAL=1: the one-CTA-per-block any-tree update (reference for the tiled one)
     double* d_cta_rows = nullptr;               // finish_stage's per-CTA rows, one set per slot parity
     size_t cta_rows_stride = 0;

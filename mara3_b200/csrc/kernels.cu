@@ -1511,10 +1511,16 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaMalloc(&impl->d_partials, max_rows * ROW * sizeof(double)));
     M3B_CUDA(cudaMalloc(&impl->d_partials2, max_rows * ROW * sizeof(double)));
     for (auto& p : impl->d_block_rows) M3B_CUDA(cudaMalloc(&p, size_t(BO + 1) * ROW * sizeof(double)));
-    if (N % 16 == 0)
+    // tile of the tiled any-tree kernels: 16 x 16 where it divides the block, else 12 x 12 (the reference's default block size 24),
+    // else 8 x 8; block sizes none of them divides keep one CTA per block
+    impl->gtile = N % 16 == 0 ? 16 : (N % 12 == 0 ? 12 : (N % 8 == 0 ? 8 : 0));
+    if (impl->gtile)
     {
-        for (auto& p : impl->d_general_tile_rows) M3B_CUDA(cudaMalloc(&p, std::max<size_t>(1, size_t(BO) * (N / 16) * (N / 16)) * ROW * sizeof(double)));
+        const int g = impl->gtile;
+        for (auto& p : impl->d_general_tile_rows) M3B_CUDA(cudaMalloc(&p, std::max<size_t>(1, size_t(BO) * (N / g) * (N / g)) * ROW * sizeof(double)));
         M3B_CUDA(cudaFuncSetAttribute(general_update_tiled<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(tile_t<16, 16>))));
+        M3B_CUDA(cudaFuncSetAttribute(general_update_tiled<12, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(tile_t<12, 12>))));
+        M3B_CUDA(cudaFuncSetAttribute(general_update_tiled<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(tile_t<8, 8>))));
     }
     if (const char* e = std::getenv("M3B_UNTILED_GENERAL")) impl->untiled_general = std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_MULTI_CTA_FINISH")) impl->multi_cta_finish = std::atoi(e) != 0;
@@ -1901,7 +1907,8 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     int fused_ctas = num_fused * tpb;
     // the any-tree path in 16 x 16 tiles where the block size allows (one row per tile), else one CTA and one row per block
     const bool jump_strip = impl->jump_strip && impl->strip && ! impl->untiled_general;
-    const int ggtpb = N % 16 == 0 && ! impl->untiled_general ? (N / 16) * (N / 16) : 1;     // tiles of general_gradients_tiled
+    const int gt = impl->untiled_general ? 0 : impl->gtile;
+    const int ggtpb = gt ? (N / gt) * (N / gt) : 1;     // tiles of general_gradients_tiled
     const int gtpb = jump_strip ? tpb : ggtpb;
     double* general_rows = gtpb > 1 ? impl->d_general_tile_rows[slot & 1] : block_rows;
     exchange = exchange && num_ranks > 1;
@@ -2087,14 +2094,21 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
     else if (num_general > 0)
     {
         // gradients are needed for the general blocks and every block they can fetch from
-        if (ggtpb > 1) general_gradients_tiled<16, 16><<<ng * ggtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        else general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
-        if (gtpb > 1)
-            general_update_tiled<16, 16><<<num_general * gtpb, THREADS, sizeof(tile_t<16, 16>), s>>>(impl->mesh, impl->model, st, d_general,
-                in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
+        #define M3B_GENERAL_TILED(G_) do { \
+            general_gradients_tiled<G_, G_><<<ng * ggtpb, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients); \
+            general_update_tiled<G_, G_><<<num_general * gtpb, THREADS, sizeof(tile_t<G_, G_>), s>>>(impl->mesh, impl->model, st, d_general, \
+                in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot); } while (0)
+        if (ggtpb > 1 && gtpb > 1)
+        {
+            if (gt == 16) M3B_GENERAL_TILED(16); else if (gt == 12) M3B_GENERAL_TILED(12); else M3B_GENERAL_TILED(8);
+        }
         else
+        {
+            general_gradients<<<ng, THREADS, 0, s>>>(impl->mesh, st, impl->d_gradient_blocks, in.data, impl->d_gradients);
             general_update<<<num_general, THREADS, 0, s>>>(impl->mesh, impl->model, st, d_general,
                 in.data, impl->d_gradients, un_data, out.data, general_rows, impl->d_fail + slot);
+        }
+        #undef M3B_GENERAL_TILED
         launches += 2;
         M3B_CUDA(cudaGetLastError());
     }
