@@ -66,7 +66,7 @@ struct device_solver_t::impl_t
     bool strip = false;                     // stage_strip (16 x 32 tiles, warp-organised) instead of stage_fused
     bool tma = false;                       // regular blocks through stage_tma (persistent, cp.async.bulk staging); M3B_STAGE=strip: stage_strip
     bool tma_fast = false;                  // stage_tma's branch-free equation of state (fast_eos and alpha > 0)
-    int tma_ctas_per_sm = 0;                // M3B_TMA_CTAS: 3 (two tile buffers, 168 registers) or 4 (one buffer, 128 registers); 0: per launch, see launch_fused
+    int tma_ctas_per_sm = 0;                // M3B_TMA_CTAS: 3 (two tile buffers, 168 registers) or 4 (one buffer, 128 registers); 0: 3
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
     tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps

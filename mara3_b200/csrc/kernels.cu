@@ -1965,15 +1965,10 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             a.model = impl->model; a.stage = st; a.tile_info = impl->d_tile_info + size_t(first) * tpb; a.num_tiles = ctas;
             a.Uin = in.data; a.Un = un_data; a.Uout = out.data; a.partials = tiles; a.fail = impl->d_fail + slot;
             a.N = N; a.fast = impl->tma_fast; a.stage_mode = stage_mode;
-            // Persistent CTAs take the tiles in rounds of (SMs x CTAs per SM).  A tile costs a 4-per-SM CTA (one buffer, its load
-            // exposed) 1.36 x what it costs a 3-per-SM CTA (measured on 4096^2: 10.6 against 7.8 us), so 4 per SM only pays
-            // where it saves a whole round -- short tile lists, as on 8 GPUs (4096 tiles: 7 rounds instead of 10).
-            int per_sm = impl->tma_ctas_per_sm;
-            if (per_sm == 0)
-            {
-                const int r3 = (ctas + 3 * impl->sm_count - 1) / (3 * impl->sm_count), r4 = (ctas + 4 * impl->sm_count - 1) / (4 * impl->sm_count);
-                per_sm = 1.36 * r4 < double(r3) ? 4 : 3;
-            }
+            // 3 CTAs per SM with two tile buffers unless M3B_TMA_CTAS=4 asks for one buffer and 4: measured on 4096^2, a tile costs a
+            // 4-per-SM CTA 1.36 x what it costs a 3-per-SM CTA (10.6 against 7.8 us, its load is exposed), so 589 against 578 us
+            // on one GPU; on 2 GPUs 0.680 against 0.634 ms per step (the CTAs also spend 19 instead of 5 us in the fused unpack).
+            const int per_sm = impl->tma_ctas_per_sm ? impl->tma_ctas_per_sm : 3;
             a.ctas_per_sm = per_sm;
             a.grid = std::min(ctas, impl->sm_count * per_sm);       // persistent: every CTA walks the tile list with stride `grid`
             stage_tma_launch(a, s);
