@@ -260,8 +260,9 @@ __device__ __forceinline__ void hlle_viscous_core(double cs2, double cs, double 
     // d1, d2: sums over the two cells of D1 = dx ux - dy uy and D2 = dx uy + dy ux (in the scale mu_coef expects)
     double vl = AXIS == 0 ? L.vx : L.vy;
     double vr = AXIS == 0 ? R.vx : R.vy;
-    double ap = dmax0(dmax(vl, vr) + cs);       // max(0, vl + cs, vr + cs)
-    double am = dmin0(dmin(vl, vr) - cs);       // min(0, vl - cs, vr - cs)
+    const bool left_faster = vl > vr;            // one compare serves both extremes
+    double ap = dmax0((left_faster ? vl : vr) + cs);        // max(0, vl + cs, vr + cs)
+    double am = dmin0((left_faster ? vr : vl) - cs);        // min(0, vl - cs, vr - cs)
     double inv = fast_rcp(ap - am);
     double wl = ap * inv, wr = -am * inv;
     double ml = L.s * (wl * (vl - am));
@@ -313,8 +314,9 @@ __device__ __forceinline__ void hlle_viscous_core(double cs2, double cs, double 
 {
     double vl = AXIS == 0 ? L.vx : L.vy;
     double vr = AXIS == 0 ? R.vx : R.vy;
-    double ap = dmax0(dmax(vl, vr) + cs);       // max(0, vl + cs, vr + cs)
-    double am = dmin0(dmin(vl, vr) - cs);       // min(0, vl - cs, vr - cs)
+    const bool left_faster = vl > vr;            // one compare serves both extremes
+    double ap = dmax0((left_faster ? vl : vr) + cs);        // max(0, vl + cs, vr + cs)
+    double am = dmin0((left_faster ? vr : vl) - cs);        // min(0, vl - cs, vr - cs)
     double inv = fast_rcp(ap - am);
     double wl = ap * inv, wr = -am * inv;
     double ml = L.s * (wl * (vl - am));

@@ -399,32 +399,30 @@ namespace m3b { namespace dev { namespace
             tma_y_face<FAST>(T, A.P, model, S, C, cvis, ydhi, lane, SY, F);
             T.YB[0][lane] = F[0]; T.YB[1][lane] = F[1]; T.YB[2][lane] = F[2];
         }
-        double FxLo[3], FyLo[3];
+        // (the fluxes of consecutive rows alternate between two register sets: no copies at the end of a row)
+        double Fx[2][3], Fy[2][3];
         face_cell_t up = load_face_cell<0>(T, A.P, li0 - 1, lj);        // the cell above the strip, then each row's cell for the row below
-        tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0, lj, up, FxLo, FyLo);
+        tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0, lj, up, Fx[0], Fy[0]);
 
-        if (warp > 0) { T.XB[0][warp - 1][lj] = FxLo[0]; T.XB[1][warp - 1][lj] = FxLo[1]; T.XB[2][warp - 1][lj] = FxLo[2]; }
+        if (warp > 0) { T.XB[0][warp - 1][lj] = Fx[0][0]; T.XB[1][warp - 1][lj] = Fx[0][1]; T.XB[2][warp - 1][lj] = Fx[0][2]; }
         __syncthreads();
 
         #pragma unroll
         for (int r = 1; r < STRIP; ++r)
         {
-            double FxNew[3], FyNew[3];
             const int set = DEEP ? ((r - 1) & 1) : 0;
             if (DEEP) load_cell(r, u[r & 1], u0[r & 1], br[r & 1]); else load_cell(r - 1, u[0], u0[0], br[0]);
             load_un(r - 1, un);
             if (DEEP && r == STRIP - 1) load_un(r, un_last);     // (the last row has no faces of a next row to hide behind)
             if (! DEEP) up = load_face_cell<0>(T, A.P, li0 + r - 1, lj);      // (128 registers: re-read the cell above instead of carrying it)
-            tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0 + r, lj, up, FxNew, FyNew);
+            tma_cell_faces<FAST>(T, A.P, model, S, C, cvis, ydc, ydv, li0 + r, lj, up, Fx[r & 1], Fy[r & 1]);
             if (! DEEP && r == STRIP - 1) { load_cell(r, u[1], u0[1], br[1]); load_un(r, un_last); }       // behind them: the update of row r - 1
-            update_cell(r - 1, u[set], u0[set], br[set], un, FxLo, FxNew, FyLo);
-            #pragma unroll
-            for (int q = 0; q < 3; ++q) { FxLo[q] = FxNew[q]; FyLo[q] = FyNew[q]; }
+            update_cell(r - 1, u[set], u0[set], br[set], un, Fx[(r - 1) & 1], Fx[r & 1], Fy[(r - 1) & 1]);
         }
         {
             double FxHi[3];
             FxHi[0] = T.XB[0][warp][lj]; FxHi[1] = T.XB[1][warp][lj]; FxHi[2] = T.XB[2][warp][lj];
-            update_cell(STRIP - 1, u[(STRIP - 1) & 1], u0[(STRIP - 1) & 1], br[(STRIP - 1) & 1], un_last, FxLo, FxHi, FyLo);
+            update_cell(STRIP - 1, u[(STRIP - 1) & 1], u0[(STRIP - 1) & 1], br[(STRIP - 1) & 1], un_last, Fx[(STRIP - 1) & 1], FxHi, Fy[(STRIP - 1) & 1]);
         }
 #ifndef M3B_HOT_PATH_ONLY
         if (negative)
