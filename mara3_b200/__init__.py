@@ -52,7 +52,8 @@ class NegativeDensity(Mara3Error):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmara3_b200.so")
+    """The in-tree library; M3B_LIBRARY names another build of it (development: two builds compared in one visit to the GPU box)."""
+    return os.environ.get("M3B_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmara3_b200.so")
 
 
 _lib = None

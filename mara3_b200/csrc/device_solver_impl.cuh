@@ -69,7 +69,10 @@ struct device_solver_t::impl_t
     int tma_ctas_per_sm = 0;                // M3B_TMA_CTAS: 3 (two tile buffers, 168 registers) or 4 (one buffer, 128 registers); 0: 3
     unsigned char* d_tile_flags = nullptr;
     tile_info_t* d_tile_info = nullptr;     // [regular list position][tile]
-    tile_info_t* d_jump_tile_info = nullptr;    // [any-tree list position][tile]: stage_strip<.., JUMP> for blocks at refinement jumps
+    tile_info_t* d_jump_tile_info = nullptr;    // stage_strip<.., JUMP>: the tiles of blocks at refinement jumps that touch a jump
+    bool jump_after_regular = false;            // M3B_JUMP_AFTER=1: the JUMP tiles' launch on the compute stream behind the regular kernel instead of beside it (measured: c4 equal, c4x 2 % slower)
+    int num_jump_tiles = 0;                     // entries of d_jump_tile_info
+    int num_extra_tiles = 0;                    // tiles of blocks at jumps that touch same-level leaves only: behind the regular blocks' in d_tile_info
     cudaStream_t jump_stream = nullptr;     // stage_strip<.., JUMP> runs here, beside the regular blocks' launch
     cudaEvent_t gradients_done = nullptr, jump_done = nullptr;   // fork (stage input ready on the compute stream) and join
     bool jump_mode0 = false;                // M3B_JUMP_MODE0=1: run-time stage flags in the JUMP variant (experiment)

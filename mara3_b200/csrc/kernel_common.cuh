@@ -54,9 +54,14 @@ namespace m3b { namespace dev
     {
         int b;                          // block
         int n9[9];                      // same-level neighbour ids, (di + 1) * 3 + (dj + 1)
-        int flags;                      // bit 0: the buffer-zone rate is non-zero somewhere in the tile
-        int pad;
+        // bit 0: the buffer-zone rate is non-zero somewhere in the tile; bits 1-4 (stage_strip<.., JUMP>): the block side at the
+        // tile's low-x / high-x / low-y / high-y edge has a finer neighbour; bit 5 (stage_tma): the tile belongs to a block at a
+        // refinement jump but touches same-level leaves only, and its partial row goes to the any-tree rows;
+        // bits 8 and up: position of the tile in its block (row-major over the block's tiles)
+        int flags;
+        int row;                        // the tile's partial row (index into the launch's rows array)
     };
+    constexpr int TILE_POS_SHIFT = 8, TILE_JUMP_ROWS = 32;
 
     struct fail_dev_t
     {
@@ -175,6 +180,7 @@ namespace m3b { namespace dev
         const double* Un;
         double* Uout;
         double* partials;
+        double* jump_partials;      // rows of the tiles flagged TILE_JUMP_ROWS
         fail_dev_t* fail;
         int N;              // block size
         bool fast;          // branch-free equation of state

@@ -1440,6 +1440,7 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         tile_flags_host = flags;
     }
     impl->d_regular = device_upload(impl->regular);
+    auto regular_tile_info = std::vector<tile_info_t>();
     if (impl->tile_x)
     {
         const int tpb = (N / impl->tile_x) * (N / impl->tile_y);
@@ -1450,15 +1451,16 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
                 auto& ti = info[r * tpb + t];
                 ti.b = impl->regular[r];
                 for (int k = 0; k < 9; ++k) ti.n9[k] = nbr9[size_t(ti.b) * 9 + k];
-                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t];
-                ti.pad = 0;
+                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t] | (t << TILE_POS_SHIFT);
+                ti.row = int(r) * tpb + t;
             }
-        impl->d_tile_info = device_upload(info);
+        regular_tile_info = info;       // (uploaded below, with the jump blocks' tiles that touch same-level leaves only behind them)
     }
     // (conserved_q with general_only keeps the any-tree kernels: the reference implementation of that variable set on the device)
     impl->jump_strip = N % 32 == 0 && ! tiled_kernel && (sd.conserve_linear_p || ! general_only);
     if (const char* e = std::getenv("M3B_JUMP_STRIP")) impl->jump_strip = impl->jump_strip && std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_SERIAL_JUMP")) impl->serial_jump = std::atoi(e) != 0;
+    if (const char* e = std::getenv("M3B_JUMP_AFTER")) impl->jump_after_regular = std::atoi(e) != 0;
     if (const char* e = std::getenv("M3B_JUMP_MODE0")) impl->jump_mode0 = std::atoi(e) != 0;
     if (impl->jump_strip)
     {
@@ -1467,23 +1469,51 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
         auto list = std::vector<int>();
         if (general_only) for (int b = 0; b < BO; ++b) list.push_back(b);
         else list = impl->irregular;
-        auto info = std::vector<tile_info_t>(std::max<size_t>(1, list.size() * tpb));
+        // A tile of such a block whose 20 x 36 region (tile + two guard layers) lies in same-level leaves only -- its own block
+        // and the <= 3 neighbours it touches -- sees exactly what a tile of a regular block sees: guard cells are copies, no
+        // prolongation / restriction, no corrected face (mesh_tree_operators.hpp:223-252, scheme.cpp:614-720 touch the block's
+        // sides at the jump only).  With a block of 64^2 in 4 x 2 tiles that is half to three quarters of the tiles of a block
+        // with one side at a jump: they are appended to the persistent regular kernel's list (stage_tma) and leave
+        // stage_strip<.., JUMP>'s, keeping their rows among the block's.  M3B_SPLIT_JUMP=0: every tile of these blocks through JUMP.
+        bool split = ! general_only && sd.conserve_linear_p;        // (stage_tma: linear-momentum variables)
+        if (const char* e = std::getenv("M3B_STAGE")) split = split && std::string(e) != "strip";
+        if (const char* e = std::getenv("M3B_SPLIT_JUMP")) split = split && std::atoi(e) != 0;
+        auto info = std::vector<tile_info_t>();
         for (size_t r = 0; r < list.size(); ++r)
             for (int t = 0; t < tpb; ++t)
             {
-                auto& ti = info[r * tpb + t];
+                tile_info_t ti;
                 const int i0 = (t / tiles_y) * 16, j0 = (t % tiles_y) * 32;
                 ti.b = list[r];
+                ti.row = int(r) * tpb + t;
+                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t] | (t << TILE_POS_SHIFT);
+                bool same_level_only = split;
+                for (int di = -1; di <= 1 && same_level_only; ++di)
+                    for (int dj = -1; dj <= 1; ++dj)
+                    {
+                        const bool touched = (di == 0 || (di < 0 ? i0 == 0 : i0 + 16 == N)) && (dj == 0 || (dj < 0 ? j0 == 0 : j0 + 32 == N));
+                        if (touched && (di | dj) && nbr9[size_t(ti.b) * 9 + (di + 1) * 3 + (dj + 1)] < 0) { same_level_only = false; break; }
+                    }
+                if (same_level_only)
+                {
+                    for (int k = 0; k < 9; ++k) ti.n9[k] = nbr9[size_t(ti.b) * 9 + k];     // (-1 where there is no such leaf: never touched)
+                    ti.flags |= TILE_JUMP_ROWS;
+                    regular_tile_info.push_back(ti);
+                    ++impl->num_extra_tiles;
+                    continue;
+                }
                 for (int k = 0; k < 9; ++k) ti.n9[k] = ti.b;        // cells beyond the block come through resolve_cell
-                ti.flags = tile_flags_host[size_t(ti.b) * tpb + t];
                 if (i0 == 0       && nbr[size_t(ti.b) * 4 + 0].kind == 2) ti.flags |= 2;
                 if (i0 + 16 == N  && nbr[size_t(ti.b) * 4 + 1].kind == 2) ti.flags |= 4;
                 if (j0 == 0       && nbr[size_t(ti.b) * 4 + 2].kind == 2) ti.flags |= 8;
                 if (j0 + 32 == N  && nbr[size_t(ti.b) * 4 + 3].kind == 2) ti.flags |= 16;
-                ti.pad = 0;
+                info.push_back(ti);
             }
+        impl->num_jump_tiles = int(info.size());
+        if (info.empty()) info.push_back(tile_info_t());
         impl->d_jump_tile_info = device_upload(info);
     }
+    if (! regular_tile_info.empty()) impl->d_tile_info = device_upload(regular_tile_info);
     impl->d_irregular = device_upload(impl->irregular);
     impl->d_gradient_blocks = device_upload(impl->gradient_blocks);
 
@@ -1945,11 +1975,15 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         impl->mark(s, "exchange done");
     }
 
-    // blocks [first, first + count) of the regular list: tile rows, block rows and tickets are indexed by list position
-    auto launch_fused = [&] (int first, int count)
+    // blocks [first, first + count) of the regular list: tile rows, block rows and tickets are indexed by list position;
+    // extra_tiles: the jump blocks' tiles that touch same-level leaves only (they follow the regular blocks' tiles in d_tile_info,
+    // so they can only ride with a launch that ends with the last regular block)
+    const int num_extra_tiles = (impl->strip && impl->tma && jump_strip && num_general > 0) ? impl->num_extra_tiles : 0;
+    auto launch_fused = [&] (int first, int count, int extra_tiles = 0)
     {
-        if (count <= 0) return;
-        const int ctas = count * tpb;
+        if (count <= 0 && extra_tiles <= 0) return;
+        if (extra_tiles > 0 && first + count != num_fused) throw std::logic_error("launch_fused: the extra tiles follow the last regular block");
+        const int ctas = count * tpb + extra_tiles;
         const int* list = impl->d_regular + first;
         double* tiles = partials + size_t(first) * tpb * ROW;
         #define M3B_LAUNCH_FUSED(TX, TY) stage_fused<TX, TY><<<ctas, THREADS, sizeof(tile_t<TX, TY>), s>>>( \
@@ -1963,7 +1997,8 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             a.mesh.ready_flag = impl->d_ready;
             a.mesh.ready_value = impl->exchange_counter;
             a.model = impl->model; a.stage = st; a.tile_info = impl->d_tile_info + size_t(first) * tpb; a.num_tiles = ctas;
-            a.Uin = in.data; a.Un = un_data; a.Uout = out.data; a.partials = tiles; a.fail = impl->d_fail + slot;
+            a.Uin = in.data; a.Un = un_data; a.Uout = out.data; a.fail = impl->d_fail + slot;
+            a.partials = partials; a.jump_partials = general_rows;      // (rows are addressed through tile_info_t::row)
             a.N = N; a.fast = impl->tma_fast; a.stage_mode = stage_mode;
             // 3 CTAs per SM with two tile buffers unless M3B_TMA_CTAS=4 asks for one buffer and 4: measured on 4096^2, a tile costs a
             // 4-per-SM CTA 1.36 x what it costs a 3-per-SM CTA (10.6 against 7.8 us, its load is exposed), so 589 against 578 us
@@ -1987,7 +2022,7 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
             mesh.ready_flag = impl->d_ready;
             mesh.ready_value = impl->exchange_counter;
             kernel<<<ctas, STRIP_THREADS, sizeof(strip_smem_t), s>>>(mesh, impl->model, st, impl->d_tile_info + size_t(first) * tpb,
-                in.data, un_data, out.data, tiles, impl->d_fail + slot, nullptr);
+                in.data, un_data, out.data, partials, impl->d_fail + slot, nullptr);
         }
         else if (impl->tile_x == 16 && impl->tile_y == 32) M3B_LAUNCH_FUSED(16, 32);
         else if (impl->tile_x == 12 && impl->tile_y == 24) M3B_LAUNCH_FUSED(12, 24);
@@ -2022,17 +2057,19 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
                              : (impl->fast_eos ? stage_strip<4, 0, true, 0, true, true> : stage_strip<4, 0, false, 0, true, true>);
         mesh_dev_t mesh = impl->mesh;
         mesh.first_wait_cta = 0x7fffffff;
-        kernel<<<num_general * tpb, STRIP_THREADS, sizeof(strip_smem_t), js>>>(mesh, impl->model, st, impl->d_jump_tile_info,
+        const int jump_tiles = force_general ? num_general * tpb : impl->num_jump_tiles;
+        if (jump_tiles == 0) return;
+        kernel<<<jump_tiles, STRIP_THREADS, sizeof(strip_smem_t), js>>>(mesh, impl->model, st, impl->d_jump_tile_info,
             in.data, un_data, out.data, general_rows, impl->d_fail + slot, impl->d_gradients);
         ++launches;
         M3B_CUDA(cudaGetLastError());
     };
     const int ng = int(impl->gradient_blocks.size());
-    bool jump_forked = false, e0_recorded = false;
+    bool jump_forked = false, jump_pending = false, e0_recorded = false;
     if (jump_strip && num_general > 0 && ! exchange)
     {
         // fork: gradients and the jump blocks' update on the side stream, the regular blocks' update on the compute stream
-        const bool fork = num_fused > 0 && ! impl->serial_jump;
+        const bool fork = (num_fused > 0 || num_extra_tiles > 0) && ! impl->serial_jump;
         cudaStream_t js = fork ? impl->jump_stream : s;
         if (e0) { M3B_CUDA(cudaEventRecord(e0, s)); e0_recorded = true; }      // the timed region covers the jump blocks' kernels
         if (fork)
@@ -2044,7 +2081,9 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         ++launches;
         if (fork)
         {
-            launch_jump_strip(js);
+            // jump_after_regular: only the ring gradients run beside the persistent regular kernel (whose CTAs hold their SMs
+            // until its tile list is done); the tiles at the jumps follow on the compute stream once both are through
+            if (impl->jump_after_regular) jump_pending = true; else launch_jump_strip(js);
             M3B_CUDA(cudaEventRecord(impl->jump_done, js));
             jump_forked = true;
         }
@@ -2067,16 +2106,20 @@ void device_solver_t::launch_stage_kernels(const device_field_t& in, const devic
         if (timed) M3B_CUDA(cudaEventRecord(g0, s));
         M3B_CUDA(cudaStreamWaitEvent(s, impl->halo_ready, 0));
         if (timed) M3B_CUDA(cudaEventRecord(g1, s));
-        launch_fused(impl->num_interior, num_fused - impl->num_interior);
+        launch_fused(impl->num_interior, num_fused - impl->num_interior, num_extra_tiles);
         if (timed) { impl->exchange_events.emplace_back(x0, x1); impl->gap_events.emplace_back(g0, g1); }
         if (num_fused == 0) {}      // (general blocks below run after the wait as well)
     }
     else
     {
         if (e0 && ! e0_recorded) M3B_CUDA(cudaEventRecord(e0, s));
-        launch_fused(0, num_fused);
+        launch_fused(0, num_fused, num_extra_tiles);
     }
-    if (jump_forked) M3B_CUDA(cudaStreamWaitEvent(s, impl->jump_done, 0));
+    if (jump_forked)
+    {
+        M3B_CUDA(cudaStreamWaitEvent(s, impl->jump_done, 0));
+        if (jump_pending) launch_jump_strip(s);
+    }
     else if (num_general > 0 && jump_strip)
     {
         if (exchange)       // (overlapped exchange: the guard zones have only just arrived)

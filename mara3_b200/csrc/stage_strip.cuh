@@ -174,7 +174,7 @@ namespace
         const int4 tiA = __ldg(ti4), tiB = __ldg(ti4 + 1), tiC = __ldg(ti4 + 2);
         const int n9[9] = {tiA.y, tiA.z, tiA.w, tiB.x, tiB.y, tiB.z, tiB.w, tiC.x, tiC.y};
         const int b  = tiA.x;
-        const int t  = blockIdx.x % tiles_per_block;
+        const int t  = tiC.z >> TILE_POS_SHIFT;       // position of the tile in its block
         const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
         const size_t FS = mesh.FS;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -213,7 +213,7 @@ namespace
             const int ahead = blockIdx.x + mesh.prefetch_ahead;
             if (mesh.prefetch_ahead > 0 && ahead < gridDim.x && threadIdx.x < 96)
             {
-                const int rb = __ldg(&tile_info[ahead].b), rt = ahead % tiles_per_block;
+                const int rb = __ldg(&tile_info[ahead].b), rt = __ldg(&tile_info[ahead].flags) >> TILE_POS_SHIFT;
                 const int f = threadIdx.x >> 5, row = (threadIdx.x & 31) >> 1, half = threadIdx.x & 1;
                 const size_t c = (size_t(rb) * N + ((rt / tiles_y) * SX + row)) * N + (rt % tiles_y) * SY + 16 * half;
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(Uin + f * FS + c));
@@ -654,7 +654,7 @@ namespace
         if (threadIdx.x <= NUM_SUMS)
         {
             const int k = threadIdx.x;
-            double* row = partials + size_t(blockIdx.x) * ROW;
+            double* row = partials + size_t(tiC.w) * ROW;
             double a = T.red[0][k], bq = T.red[1][k], cq = T.red[2][k], d = T.red[3][k];
             // min over cells of h / wavespeed = h / max wavespeed: one division per tile
             row[k] = k == NUM_SUMS ? (compute_dt ? h / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (h * h);

@@ -51,7 +51,7 @@ template<int CTAS> static void launch(const stage_tma_launch_t& a, cudaStream_t 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, STRIP_THREADS, bytes) != cudaSuccess || per_sm < 1)
         throw std::runtime_error("stage_tma: the kernel does not fit on this device");
     const int grid = std::max(1, std::min(a.grid, std::min(per_sm, a.ctas_per_sm) * sms));
-    kernel<<<grid, STRIP_THREADS, bytes, stream>>>(a.mesh, a.model, a.stage, a.tile_info, a.num_tiles, a.Uin, a.Un, a.Uout, a.partials, a.fail, a.exchange);
+    kernel<<<grid, STRIP_THREADS, bytes, stream>>>(a.mesh, a.model, a.stage, a.tile_info, a.num_tiles, a.Uin, a.Un, a.Uout, a.partials, a.jump_partials, a.fail, a.exchange);
 }
 
 void stage_tma_launch(const stage_tma_launch_t& a, cudaStream_t stream)

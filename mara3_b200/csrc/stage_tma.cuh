@@ -440,8 +440,8 @@ namespace m3b { namespace dev { namespace
     template<int MIN_CTAS, int NB, bool FAST, int MODE, int NBUF = (MIN_CTAS >= 4 ? 1 : 2)>
     __global__ void __launch_bounds__(STRIP_THREADS, MIN_CTAS) stage_tma(
         mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const tile_info_t* __restrict__ tile_info, int num_tiles,
-        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout, double* partials, fail_dev_t* fail,
-        fused_exchange_t X)
+        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout, double* partials, double* jump_partials,
+        fail_dev_t* fail, fused_exchange_t X)
     {
         extern __shared__ __align__(128) unsigned char smem_raw[];
         using SMEM = tma_smem_t<NBUF>;
@@ -451,7 +451,7 @@ namespace m3b { namespace dev { namespace
         // MODE 1 / 2: first / last stage of an RK2 step with adaptive dt, flags known at compile time; 0: read them from S
         const bool combine = MODE == 0 ? S.combine != 0 : MODE == 2, compute_dt = MODE == 0 ? S.compute_dt != 0 : MODE == 2;
         const int N = NB ? NB : mesh.N;
-        const int tiles_y = N / SY, tpb = (N / SX) * tiles_y;
+        const int tiles_y = N / SY;
         const size_t FS = mesh.FS;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const strip_consts_t C = {S.m1 * model.inv_mach2, S.m2 * model.inv_mach2, -S.m1, -S.m2, 2.0 * S.theta, S.dt};
@@ -471,10 +471,10 @@ namespace m3b { namespace dev { namespace
         }
         __syncthreads();
         if (! ghosts_ready && tile >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
-        stage_tile_async(T, T.info[0], Uin, FS, tile % tpb, 0, N, tiles_y);
+        stage_tile_async(T, T.info[0], Uin, FS, T.info[0].flags >> TILE_POS_SHIFT, 0, N, tiles_y);
         if (warp == 0)
         {
-            const int b0 = T.info[0].b, t0 = tile % tpb;
+            const int b0 = T.info[0].b, t0 = T.info[0].flags >> TILE_POS_SHIFT;
             const double* xvg = mesh.xv + size_t(b0) * (N + 1) + (t0 / tiles_y) * SX;
             const double* yvg = mesh.yv + size_t(b0) * (N + 1) + (t0 % tiles_y) * SY;
             if (lane <= SX) T.cx[0][lane] = __ldg(xvg + lane);
@@ -497,7 +497,7 @@ namespace m3b { namespace dev { namespace
             if (has_next)
             {
                 if (! ghosts_ready && next >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
-                const int tn = next % tpb;
+                const int tn = tin.flags >> TILE_POS_SHIFT;
                 if (NBUF == 2) stage_tile_async(T, tin, Uin, FS, tn, nbuf, N, tiles_y);
                 else stage_tile_async<true>(T, tin, Uin, FS, tn, 0, N, tiles_y);
                 if (warp == 0)
@@ -514,7 +514,7 @@ namespace m3b { namespace dev { namespace
             else if (NBUF == 2) cp_async_commit();     // (an empty group keeps the wait below uniform)
 
             const int b = T.info[k % 3].b, flags = T.info[k % 3].flags;
-            const int t = tile % tpb;
+            const int t = flags >> TILE_POS_SHIFT;
             const int i0 = (t / tiles_y) * SX, j0 = (t % tiles_y) * SY;
             const bool has_buffer = flags & 1;
             const double h = T.hh[cb][0], inv_h = T.hh[cb][1];
@@ -730,13 +730,13 @@ namespace m3b { namespace dev { namespace
             if (threadIdx.x <= NUM_SUMS)
             {
                 const int q = threadIdx.x;
-                double* row = partials + size_t(tile) * ROW;
+                double* row = ((flags & TILE_JUMP_ROWS) ? jump_partials : partials) + size_t(T.info[k % 3].row) * ROW;
                 const double a = T.red[0][q], bq = T.red[1][q], cq = T.red[2][q], d = T.red[3][q];
                 // min over cells of h / wavespeed = h / max wavespeed: one division per tile
                 row[q] = q == NUM_SUMS ? (compute_dt ? h / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (h * h);
             }
             // one buffer: only now is P free for the next tile (its lines were pulled into L2 a tile ago)
-            if (NBUF == 1 && has_next) stage_tile_async(T, tin, Uin, FS, next % tpb, 0, N, tiles_y);
+            if (NBUF == 1 && has_next) stage_tile_async(T, tin, Uin, FS, tin.flags >> TILE_POS_SHIFT, 0, N, tiles_y);
         }
     }
 }}}
