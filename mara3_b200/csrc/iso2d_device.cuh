@@ -134,6 +134,28 @@ __device__ __forceinline__ double dmin0(double x)
     return __hiloint2double(hi & m, __double2loint(x) & m);
 }
 
+#ifndef M3B_HOST_EMULATION
+/** Eight sums over the 32 lanes of a warp by recursive halving: at distances 16, 8, 4 a lane keeps half of its values and trades
+ *  the other half, then two butterfly steps finish the one value that is left.  Lane 4 j returns the sum of v8[j]. */
+__device__ __forceinline__ double warp_sum8(const double v8[8], int lane)
+{
+    double v4[4], v2[2], v1;
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+    #pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+        const double lo = v8[q], hi = v8[4 + q];
+        v4[q] = (b16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b16 ? lo : hi, 16);
+    }
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) v2[q] = (b8 ? v4[2 + q] : v4[q]) + __shfl_xor_sync(0xffffffffu, b8 ? v4[q] : v4[2 + q], 8);
+    v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v2[0] : v2[1], 4);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    return v1;
+}
+#endif
+
 /**
  * Un-divided PLM difference: mara::plm_gradient (math_interpolation.hpp:85-94),
  *   0.25 |sgn a + sgn b| (sgn a + sgn c) min(|a|, |b|, |c|),  a = theta dl, b = (dl + dr) / 2, c = theta dr
@@ -196,10 +218,18 @@ static __device__ __noinline__ double viscosity_slow_path(double nu, double alph
     return nu > 0.0 ? profile * nu : profile * alpha * cs * (r * inv_mach);
 }
 
+/**
+ * Reach of a sink in a2 = dr^2 / (2 s^2).  sink_rate_field (scheme.cpp:117-126) is rate exp(-a2) everywhere; beyond a2 = 40 the
+ * factor is below 4.3e-18, so the sink term -u rate exp(-a2) dt (rate dt < 1 for any stable run) is less than a quarter of an
+ * ulp of u -- the updated state has the same bits with or without it -- and the cell adds less than 4.3e-18 of a central
+ * cell's share to the accretion totals.  (Round 1 used 100; 40 takes 60 % of the area, and of the tiles that run the sink code.)
+ */
+constexpr double SINK_REACH_A2 = 40.0;
+
 /** sink_rate_field (scheme.cpp:117-126) where it is not negligible: rare, kept out of line. */
 static __device__ __noinline__ double sink_weight(double rate, double a2)
 {
-    return a2 < 100.0 ? rate * exp(-a2) : 0.0;
+    return a2 < SINK_REACH_A2 ? rate * exp(-a2) : 0.0;
 }
 
 /**
@@ -411,11 +441,10 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
 
     double a0 = 0.0, a1 = (fx1 + fx2) * S.dt, a2 = (fy1 + fy2) * S.dt;
 
-    // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)).  Beyond a2 = 100 the
-    // factor is < 4e-44: no representable effect on the state and < 1e-40 relative on the totals.
+    // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)), nothing representable beyond SINK_REACH_A2
     double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
 
-    const bool near_sink = e1 < 100.0 || e2 < 100.0;
+    const bool near_sink = e1 < SINK_REACH_A2 || e2 < SINK_REACH_A2;
 
     if (WARP_SINKS ? __any_sync(0xffffffffu, near_sink) : near_sink)
     {
@@ -424,18 +453,15 @@ __device__ __forceinline__ void source_terms(const model_t& M, const stage_t& S,
         double lz = fma(x, py, -y * px);
         if (WARP_SINKS)
         {
-            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
-            #pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            }
-            if ((threadIdx.x & 31) == 0)
-            {
-                #pragma unroll
-                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
-            }
+            const double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+#ifdef M3B_HOST_EMULATION
+            for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+#else
+            // recursive halving: 9 exchanges instead of 40; lane 4 j ends with the warp's sum of v[j]
+            const int lane = threadIdx.x & 31;
+            const double v1 = warp_sum8(v, lane);
+            if ((lane & 3) == 0) warp_sinks[lane >> 2] += v1;
+#endif
         }
         else
         {
@@ -524,7 +550,7 @@ __device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& 
     double a2 = tq1 * S.dt + tq2 * S.dt;
 
     double e1 = r1 * M.sink_inv_2s2, e2 = r2 * M.sink_inv_2s2;
-    const bool near_sink = e1 < 100.0 || e2 < 100.0;
+    const bool near_sink = e1 < SINK_REACH_A2 || e2 < SINK_REACH_A2;
     if (WARP_SINKS ? __any_sync(0xffffffffu, near_sink) : near_sink)
     {
         double w1 = sink_weight(M.sink_rate, e1);
@@ -533,18 +559,15 @@ __device__ __forceinline__ void source_terms_q(const model_t& M, const stage_t& 
         angmom_to_linear(x, y, sr, lz, px, py);
         if (WARP_SINKS)
         {
-            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
-            #pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            }
-            if ((threadIdx.x & 31) == 0)
-            {
-                #pragma unroll
-                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
-            }
+            const double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+#ifdef M3B_HOST_EMULATION
+            for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+#else
+            // recursive halving: 9 exchanges instead of 40; lane 4 j ends with the warp's sum of v[j]
+            const int lane = threadIdx.x & 31;
+            const double v1 = warp_sum8(v, lane);
+            if ((lane & 3) == 0) warp_sinks[lane >> 2] += v1;
+#endif
         }
         else
         {
@@ -614,6 +637,7 @@ __device__ __forceinline__ eos_face_t eos_face_fast(const strip_consts_t& C, dou
     return e;
 }
 
+
 /** Running sums of one thread of stage_tma (lane <-> column: y and the y-distances to the bodies are constant, so the six
  *  gravity totals of source_term_total_t follow from  S0_k = sum k_k  and  Sx_k = sum x k_k,  k_k = -G M_k sigma / d_k^(3/2):
  *    force_x = Sx_k - x_k S0_k,  force_y = (y - y_k) S0_k,  torque = x_k y S0_k - y_k Sx_k        (scheme.cpp:390-408)
@@ -650,25 +674,23 @@ __device__ __forceinline__ void source_terms_strip(const model_t& M, const strip
 
     if (near_sink)
     {
-        // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)), nothing representable beyond a2 = 100
+        // sink_rate_field (scheme.cpp:117-126): rate exp(-dr^2 / (2 s^2)), nothing representable beyond SINK_REACH_A2.
+        // The eight accreted quantities of the warp's 32 cells are folded by recursive halving (9 exchanges instead of 40) and
+        // added to the warp's sums in shared memory by the eight lanes that end up with them: no register lives across rows.
         double e1 = fma(dx1, dx1, dy1 * dy1) * M.sink_inv_2s2, e2 = fma(dx2, dx2, dy2 * dy2) * M.sink_inv_2s2;
-        if (__any_sync(0xffffffffu, e1 < 100.0 || e2 < 100.0))
+        if (__any_sync(0xffffffffu, e1 < SINK_REACH_A2 || e2 < SINK_REACH_A2))
         {
             double w1 = sink_weight(M.sink_rate, e1);
             double w2 = sink_weight(M.sink_rate, e2);
             double lz = fma(x, py, -y * px);
-            double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
-            #pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            }
-            if ((threadIdx.x & 31) == 0)
-            {
-                #pragma unroll
-                for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
-            }
+            const double v[8] = {s * w1, s * w2, px * w1, px * w2, py * w1, py * w2, lz * w1, lz * w2};
+#ifdef M3B_HOST_EMULATION
+            for (int k = 0; k < 8; ++k) warp_sinks[k] += v[k];
+#else
+            const int lane = threadIdx.x & 31;
+            const double v1 = warp_sum8(v, lane);
+            if ((lane & 3) == 0) warp_sinks[lane >> 2] += v1;
+#endif
             double w = -(w1 + w2) * C.dt;
             a0 = fma(s, w, a0);  a1 = fma(px, w, a1);  a2 = fma(py, w, a2);
         }
@@ -688,6 +710,7 @@ __device__ __forceinline__ void source_terms_strip(const model_t& M, const strip
     }
     acc[0] = a0; acc[1] = a1; acc[2] = a2;
 }
+
 
 /** max_wavespeed with cs2 from the pre-scaled masses (FAST) */
 __device__ __forceinline__ double max_wavespeed_fast(const strip_consts_t& C, double y1, double y2, double s, double px, double py)

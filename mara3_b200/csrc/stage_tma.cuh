@@ -32,6 +32,11 @@
 
 namespace m3b { namespace dev { namespace
 {
+#ifndef M3B_PLM_UNROLL
+#define M3B_PLM_UNROLL 2
+#endif
+    constexpr int PLM_UNROLL = M3B_PLM_UNROLL;      // rows of the PLM phase per loop body
+
     template<int NBUF>
     struct tma_smem_t
     {
@@ -53,6 +58,19 @@ namespace m3b { namespace dev { namespace
         int near_sink;
         int unpack_slot;                    // exchange_unpack: the strip this CTA has taken off the list
     };
+
+    /** The warp's role in the tile (strip of rows, boundary faces, tables), shifted by the third of the grid the CTA lies in: warp w
+     *  of every CTA sits on scheduler w, warps 0 and 1 carry the tile-boundary faces, and the three CTAs of an SM come one from each
+     *  third of a full grid -- unshifted, one scheduler would hold the three heaviest warps of the SM (measured on 4096^2: 566 ->
+     *  562 us per launch; -DM3B_NO_ROTATE_ROLES for the comparison). */
+    __device__ __forceinline__ int logical_warp()
+    {
+#ifdef M3B_NO_ROTATE_ROLES
+        return threadIdx.x >> 5;
+#else
+        return int((threadIdx.x >> 5) + blockIdx.x * 3u / gridDim.x) & 3;
+#endif
+    }
 
     __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
@@ -304,7 +322,7 @@ namespace m3b { namespace dev { namespace
     __device__ __forceinline__ void tma_rows(SMEM& T, const model_t& model, const stage_t& S, const strip_consts_t& C, const rows_args_t& A,
         bool has_buffer, bool combine, bool compute_dt, strip_sums_t& sums, double& amax)
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int lane = threadIdx.x & 31, warp = logical_warp();
         const int li0 = STRIP * warp, lj = lane, N = A.N;
         const size_t FS = A.FS;
         const double yc = A.yc, dy1 = A.dy1, dy2 = A.dy2, cvis = A.cvis, dt_over_h = A.dt_over_h;
@@ -329,7 +347,11 @@ namespace m3b { namespace dev { namespace
             // The cell's state reaches the source terms through a select on a flux of this row (true for every finite flux):
             // without it ptxas hoists the source terms to just behind the loads that deliver u, u0 and br, where the in-order
             // warp then sits on the long scoreboard with a whole row of independent face arithmetic queued behind it.
+#ifdef M3B_NO_LATE
+            const bool late = true;
+#else
             const bool late = __double2hiint(FxHi[0]) != 0x7ff80001;
+#endif
             const double us = late ? u[0] : 0.0, upx = late ? u[1] : 0.0, upy = late ? u[2] : 0.0;
             double acc[3], y1, y2;
             source_terms_strip<FAST>(model, C, x, yc, T.dxc[0][li], dy1, T.dxc[1][li], dy2, T.x2c[0][li] + ydc[0], T.x2c[1][li] + ydc[1],
@@ -453,7 +475,7 @@ namespace m3b { namespace dev { namespace
         const int N = NB ? NB : mesh.N;
         const int tiles_y = N / SY;
         const size_t FS = mesh.FS;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int lane = threadIdx.x & 31, warp = logical_warp();
         const strip_consts_t C = {S.m1 * model.inv_mach2, S.m2 * model.inv_mach2, -S.m1, -S.m2, 2.0 * S.theta, S.dt};
         const double* __restrict__ U0 = mesh.U0;
         const double* __restrict__ BR = mesh.br;
@@ -580,14 +602,14 @@ namespace m3b { namespace dev { namespace
                     const double yv = T.cy[cb][SY];
                     #pragma unroll
                     for (int q = 0; q < 3; ++q) { const double dv = (yv - by[q]) * (q == 2 ? cf : 1.0); T.y2v[q][SY] = fma(dv, dv, soft[q]); }
-                    // does any cell of the tile lie within the sinks' reach (a2 = dr^2 / (2 s^2) < 100)?  distance of each body to the tile's rectangle
+                    // does any cell of the tile lie within the sinks' reach (a2 = dr^2 / (2 s^2) < SINK_REACH_A2)?  distance of each body to the tile's rectangle
                     const double xlo = T.cx[cb][0], xhi = T.cx[cb][SX], ylo = T.cy[cb][0], yhi = yv;
                     bool near = false;
                     #pragma unroll
                     for (int q = 0; q < 2; ++q)
                     {
                         const double ddx = dmax(dmax(xlo - bx[q], bx[q] - xhi), 0.0), ddy = dmax(dmax(ylo - by[q], by[q] - yhi), 0.0);
-                        near = near || (ddx * ddx + ddy * ddy) * model.sink_inv_2s2 < 100.0;
+                        near = near || (ddx * ddx + ddy * ddy) * model.sink_inv_2s2 < SINK_REACH_A2;
                     }
                     T.near_sink = near;
                 }
@@ -632,7 +654,7 @@ namespace m3b { namespace dev { namespace
                 #pragma unroll
                 for (int q = 0; q < 3; ++q) { pc[q] = P[q][g0 + 1][lane + 1]; dl[q] = pc[q] - P[q][g0][lane + 1]; }
 
-                #pragma unroll 2
+                #pragma unroll (PLM_UNROLL)
                 for (int g = g0; g < g1; ++g)
                 {
                     double pp[3], yl[3], yr[3];
@@ -704,19 +726,7 @@ namespace m3b { namespace dev { namespace
                 static_assert(GRV_FX == 8 && GRV_FY == 10 && GRV_TQ == 12 && BUF_M == 14 && BUF_L == 15 && NUM_SUMS == 16, "layout of the eight values");
                 // Eight sums over 32 lanes by recursive halving: at distances 16, 8, 4 a lane keeps half of its values and trades
                 // the other half, then two butterfly steps finish the one value that is left.  Lane 4 j ends with value j.
-                double v4[4], v2[2], v1;
-                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-                #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                {
-                    const double lo = v8[q], hi = v8[4 + q];
-                    v4[q] = (b16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b16 ? lo : hi, 16);
-                }
-                #pragma unroll
-                for (int q = 0; q < 2; ++q) v2[q] = (b8 ? v4[2 + q] : v4[q]) + __shfl_xor_sync(0xffffffffu, b8 ? v4[q] : v4[2 + q], 8);
-                v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v2[0] : v2[1], 4);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                const double v1 = warp_sum8(v8, lane);
                 if ((lane & 3) == 0) T.red[warp][GRV_FX + (lane >> 2)] = v1;
             }
             if (lane < GRV_FX) T.red[warp][lane] = T.sinks[warp][lane];
