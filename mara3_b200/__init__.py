@@ -411,7 +411,14 @@ class Solver:
             out["unpack_us_per_cta_visit"] = a[6] / a[7]
             out["exposed_wait_us_per_step"] = 2.0 * a[6] / a[7]
             out["how"] = "guard zones pushed and unpacked by the stage kernel itself (stage_tma: exchange_push / exchange_unpack)"
-        if a[4] > 0:
+            if a[4] > 0 and a[3] > 0:
+                # kernel start -> every strip stored in the neighbours' landing buffers and the flags raised there
+                out["push_us_per_exchange"] = a[3] / a[4]
+                out["nvlink_gbs_achieved"] = a[5] / (a[3] * 1e-6) * 1e-9
+                out["nvlink_peak_gbs"] = 900.0
+                out["nvlink_note"] = ("bytes this rank stores into its neighbours' memory per exchange / push time; the messages are a few "
+                                      "hundred KB, so the figure is set by store + fence latency, not by the 900 GB/s per direction of NVLink 5")
+        elif a[4] > 0:
             out["exposed_wait_us_per_step"] = a[1] / steps
             out["push_to_unpacked_us_per_exchange"] = a[3] / a[4]
             out["nvlink_gbs_achieved"] = a[5] / (a[3] * 1e-6) * 1e-9 if a[3] > 0 else None

@@ -92,7 +92,7 @@ struct device_solver_t::impl_t
     // stage timing on several ranks: [input ready -> ghosts unpacked] on the exchange stream, and what of it the compute stream
     // sees: [interior blocks done -> blocks with ghost neighbours may start]
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exchange_events, gap_events;
-    unsigned long long* d_exchange_clock = nullptr;     // [0] ns spent in peer_prepare's wait for the other ranks, [1] calls, [2] ns CTAs of stage_tma spent in exchange_unpack, [3] calls
+    unsigned long long* d_exchange_clock = nullptr;     // [0] ns spent in peer_prepare's wait for the other ranks, [1] calls, [2] ns CTAs of stage_tma spent in exchange_unpack, [3] calls, [4] ns from the start of a fused stage kernel to its flags raised on the neighbours, [5] pushes
     int* d_fused_counters = nullptr;                    // fused_exchange_t::counters
     unsigned long long fused_launches = 0;
     bool fused_exchange = true;                         // M3B_FUSED_EXCHANGE=0: halo_push / halo_wait_unpack kernels beside a split stage launch

@@ -1599,8 +1599,8 @@ device_solver_t::device_solver_t(const solver_data_t& sd, int device, bool gener
     M3B_CUDA(cudaHostGetDevicePointer(&impl->d_results, host_results, 0));
     M3B_CUDA(cudaMemset(impl->d_fail, 0, num_slots * sizeof(fail_dev_t)));
     M3B_CUDA(cudaMalloc(&impl->d_gradients, std::max<size_t>(1, 6 * impl->mesh.GS) * sizeof(double)));
-    M3B_CUDA(cudaMalloc(&impl->d_exchange_clock, 4 * sizeof(unsigned long long)));
-    M3B_CUDA(cudaMemset(impl->d_exchange_clock, 0, 4 * sizeof(unsigned long long)));
+    M3B_CUDA(cudaMalloc(&impl->d_exchange_clock, 6 * sizeof(unsigned long long)));
+    M3B_CUDA(cudaMemset(impl->d_exchange_clock, 0, 6 * sizeof(unsigned long long)));
     M3B_CUDA(cudaMalloc(&impl->d_fused_counters, 8 * sizeof(int)));
     M3B_CUDA(cudaMemset(impl->d_fused_counters, 0, 8 * sizeof(int)));
     if (const char* e = std::getenv("M3B_FUSED_EXCHANGE")) impl->fused_exchange = std::atoi(e) != 0;
@@ -1892,13 +1892,16 @@ void device_solver_t::collect_stage_timing()
     fold(impl->exchange_events, exchange_us_total, exchanges_timed);
     std::uint64_t gaps = 0;
     fold(impl->gap_events, exposed_wait_us_total, gaps);
-    unsigned long long words[4] = {0, 0, 0, 0};
+    unsigned long long words[6] = {0, 0, 0, 0, 0, 0};
     M3B_CUDA(cudaMemcpy(words, impl->d_exchange_clock, sizeof(words), cudaMemcpyDeviceToHost));
     M3B_CUDA(cudaMemset(impl->d_exchange_clock, 0, sizeof(words)));
     result_wait_us_total += words[0] * 1e-3;
     result_waits_timed += words[1];
     unpack_cta_wait_us_total += words[2] * 1e-3;
     unpack_cta_waits += words[3];
+    // fused exchange: kernel start -> all strips stored in the neighbours' landing buffers and the flags raised
+    exchange_us_total += words[4] * 1e-3;
+    exchanges_timed += words[5];
 }
 
 void device_solver_t::upload_stage(const stage_inputs_t& inputs, int slot)
