@@ -516,25 +516,6 @@ namespace m3b { namespace dev { namespace
         }
         __syncthreads();
 
-        // LATE (two tile buffers, -DM3B_THREE_BARRIERS): no barrier at the end of a tile.  What that barrier protected is done behind
-        // the NEXT tile's first barrier instead -- the tile's partial row is published there, the coordinate tables and the sink
-        // sums are re-written there, and the refill of the other half of P is asked for there -- so a tile costs three CTA-wide
-        // barriers instead of four.
-#ifdef M3B_THREE_BARRIERS
-        constexpr bool LATE = NBUF == 2;
-#else
-        constexpr bool LATE = false;
-#endif
-        double* prev_row = nullptr;
-        double prev_h = 0.0;
-        // the tile's row: the four warps' sums, and min over cells of h / wavespeed = h / max wavespeed (one division per tile)
-        auto write_row = [&] (double* row, double hh)
-        {
-            const int q = threadIdx.x;
-            const double a = T.red[0][q], bq = T.red[1][q], cq = T.red[2][q], d = T.red[3][q];
-            row[q] = q == NUM_SUMS ? (compute_dt ? hh / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (hh * hh);
-        };
-
         for (int k = 0; tile < num_tiles; ++k, tile += gridDim.x)
         {
             const int buf = NBUF == 2 ? (k & 1) : 0, nbuf = NBUF == 2 ? (buf ^ 1) : 0;       // P half of this tile / of the next; cx, cy, hh alternate either way
@@ -545,9 +526,6 @@ namespace m3b { namespace dev { namespace
             double nx = 0.0, ny = 0.0, ny32 = 0.0;      // warp 0: vertex coordinates of the next tile, stored when they have arrived
             int4 rec = make_int4(0, 0, 0, 0);           // threads 32-34: the record of the tile after the next
             // the other half of P was released by the barrier that ended tile k - 1: refill it while this tile is computed
-            // (LATE: by this tile's first barrier -- there is none at the end of a tile -- so the refill is asked for behind it)
-            auto issue_next = [&]
-            {
             if (has_next)
             {
                 if (! ghosts_ready && next >= mesh.first_wait_cta) { exchange_unpack(X, FS, N, &T.unpack_slot); ghosts_ready = true; }
@@ -565,9 +543,7 @@ namespace m3b { namespace dev { namespace
                 else if (warp == 1 && lane < 3 && next + int(gridDim.x) < num_tiles)
                     rec = __ldg(reinterpret_cast<const int4*>(tile_info + next + gridDim.x) + lane);
             }
-            else if (NBUF == 2 && ! LATE) cp_async_commit();     // (an empty group keeps the wait below uniform)
-            };
-            if (! LATE) issue_next();
+            else if (NBUF == 2) cp_async_commit();     // (an empty group keeps the wait below uniform)
 
             const int b = T.info[k % 3].b, flags = T.info[k % 3].flags;
             const int t = flags >> TILE_POS_SHIFT;
@@ -594,10 +570,10 @@ namespace m3b { namespace dev { namespace
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(Un + 2 * FS + c));
                 }
             }
+            if (lane < 8) T.sinks[warp][lane] = 0.0;
+
             // coordinate tables (warps 1-3; warp 0 has just issued the next tile)
-            auto tables = [&]
             {
-                if (lane < 8) T.sinks[warp][lane] = 0.0;
                 const double bx[3] = {S.x1, S.x2, 0.0}, by[3] = {S.y1, S.y2, 0.0};
                 const double soft[3] = {model.softening_radius2, model.softening_radius2, 0.0};
                 // FAST: the origin table carries the viscous coefficient c = cvis alpha / Mach: (c x)^2 + (c y)^2 = (c r)^2
@@ -647,12 +623,11 @@ namespace m3b { namespace dev { namespace
                     }
                     T.near_sink = near;
                 }
-            };
-            if (! LATE) tables();
+            }
 
             // ------------------------------------------------------------------ phase 0: this thread's chunks of the tile, primitives in place
             // (all but the newest group: the chunks asked for during tile k - 1)
-            if (NBUF == 2 && ! LATE) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
+            if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
             double (*P)[SX + 4][SY + 4] = T.P[buf];
             {
                 // 20 rows of 18 sixteen-byte chunks (two cells in y): thread <-> (row rr + 7 m, chunk cc), m = 0, 1, 2
@@ -677,13 +652,6 @@ namespace m3b { namespace dev { namespace
                 }
             }
             __syncthreads();
-            if (LATE)
-            {
-                // every warp has left tile k - 1: its sums can be published, the tables, the sink sums and the other half of P re-used
-                if (k > 0 && threadIdx.x <= NUM_SUMS) write_row(prev_row, prev_h);
-                issue_next();
-                tables();
-            }
 
             // ------------------------------------------------------------------ phase 1: PLM differences (doubled)
             {
@@ -778,17 +746,17 @@ namespace m3b { namespace dev { namespace
                 for (int o = 16; o > 0; o >>= 1) m = dmax(m, __shfl_xor_sync(0xffffffffu, m, o));
                 if (lane == 0) T.red[warp][NUM_SUMS] = m;
             }
-            double* row = ((flags & TILE_JUMP_ROWS) ? jump_partials : partials) + size_t(T.info[k % 3].row) * ROW;
-            if (LATE) { prev_row = row; prev_h = h; continue; }     // (published behind the next tile's first barrier, or behind the loop)
             __syncthreads();        // ends the tile: P[buf], G, XB / YB and the tables are free again
-            if (threadIdx.x <= NUM_SUMS) write_row(row, h);
+            if (threadIdx.x <= NUM_SUMS)
+            {
+                const int q = threadIdx.x;
+                double* row = ((flags & TILE_JUMP_ROWS) ? jump_partials : partials) + size_t(T.info[k % 3].row) * ROW;
+                const double a = T.red[0][q], bq = T.red[1][q], cq = T.red[2][q], d = T.red[3][q];
+                // min over cells of h / wavespeed = h / max wavespeed: one division per tile
+                row[q] = q == NUM_SUMS ? (compute_dt ? h / dmax(dmax(a, bq), dmax(cq, d)) : 1e300) : ((a + bq) + (cq + d)) * (h * h);
+            }
             // one buffer: only now is P free for the next tile (its lines were pulled into L2 a tile ago)
             if (NBUF == 1 && has_next) stage_tile_async(T, tin, Uin, FS, tin.flags >> TILE_POS_SHIFT, 0, N, tiles_y);
-        }
-        if (LATE)
-        {
-            __syncthreads();
-            if (threadIdx.x <= NUM_SUMS) write_row(prev_row, prev_h);
         }
     }
 }}}
