@@ -503,8 +503,8 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample_steps = max(1, int(12e6 / cells))
-        mzps, kind, cores, how, done = time_reference(wl["config"], sample_steps, 1, threads, max_seconds=60.0)
+        sample_steps = max(1, int(100e6 / cells))       # ~10-15 s of host work at the reference's ~8 Mzps on 16 cores
+        mzps, kind, cores, how, done = time_reference(wl["config"], sample_steps, 1, threads, max_seconds=40.0)
         cpu_baseline = {"value": mzps, "unit": "Mzps", "cores": cores, "kind": kind,
                         "sample": f"{done} timed steps after 1 warm-up of the same workload; {how}"}
 
