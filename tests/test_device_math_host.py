@@ -159,6 +159,20 @@ def test_source_terms_strip_equals_source_terms(dm):
     assert worst_sum <= 1e-13, worst_sum
 
 
+def test_sink_reach_leaves_the_state_untouched():
+    """iso2d_device.cuh: SINK_REACH_A2 = 40.  The reference applies rate * exp(-a2) everywhere (scheme.cpp:117-126); beyond
+    a2 = 40 the sink term -u * rate * exp(-a2) * dt is less than a quarter of an ulp of u for every stable step (rate * dt < 1),
+    so u + term == u in floating point, and a cell there adds less than 4.3e-18 of a central cell's share to the totals."""
+    header = open(os.path.join(ROOT, "mara3_b200", "csrc", "iso2d_device.cuh")).read()
+    assert "constexpr double SINK_REACH_A2 = 40.0;" in header
+    factor = np.exp(-40.0)
+    assert factor < 4.3e-18 and factor < 0.25 * np.finfo(np.float64).eps
+    rng = np.random.default_rng(11)
+    for u in 10.0 ** rng.uniform(-12, 3, size=200):
+        for rate_dt in (1.0, 0.5, 1e-3):
+            assert u + (-u * rate_dt * factor) == u
+
+
 def test_eos_face_fast(dm):
     # cs2_at_position / nu_at_position (scheme.cpp:160-193) from pre-scaled masses and the pre-scaled r^2 table
     rng = np.random.default_rng(5)

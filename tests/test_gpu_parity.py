@@ -145,6 +145,31 @@ def test_jump_strip_agrees_with_any_tree_kernels(monkeypatch):
     assert_scalars(un.scalars, uo.scalars, 1e-10, un.time)
 
 
+def test_jump_block_tiles_through_the_regular_kernel_agree_with_the_jump_kernel(monkeypatch):
+    """A tile of a block at a refinement jump that touches same-level leaves only rides with the regular blocks' tiles in the
+    persistent kernel (stage_tma) -- the default -- instead of stage_strip<.., JUMP> (M3B_SPLIT_JUMP=0: every tile of such a
+    block through JUMP).  Both see the same cells; two RK2 steps of a nested tree, and one stage against the oracle."""
+    cfg = dict(depth=5, block_size=64)
+    new = m3.Solver(cfg)
+    monkeypatch.setenv("M3B_SPLIT_JUMP", "0")
+    old = m3.Solver(cfg)
+    monkeypatch.delenv("M3B_SPLIT_JUMP")
+    assert new.num_regular_blocks < new.num_blocks          # the tree has jumps
+    un, uo = new.create_solution(), old.create_solution()
+    for _ in range(2):
+        dn, _ = new.next_solution(un)
+        do, _ = old.next_solution(uo)
+        assert abs(dn - do) <= 1e-13 * do
+    assert block_rel_err(un.conserved_u, uo.conserved_u) <= 2 * CELL_TOL
+    assert_scalars(un.scalars, uo.scalars, 1e-10, un.time)
+    # the launch counts differ only if the split is active somewhere: the same kernels run, over different tile lists
+    solver, u, o = make_pair(cfg)
+    dt = solver.maximum_timestep(u)
+    o1, status = o.advance(dt)
+    assert status == 0
+    assert block_rel_err(solver.advance(u, dt).conserved_u, o1.conserved_u) <= CELL_TOL
+
+
 @pytest.mark.parametrize("name", ["nested_d3_n8", "uniform_d2_n16", "live_ecc_d3_n8", "rk1_axisym_d3_n8",
                                   "angmom_nested_d3_n8", "angmom_live_rk1_d2_n16"])
 def test_steps_match_reference_golden_vectors(name):
