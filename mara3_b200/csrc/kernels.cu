@@ -1,23 +1,16 @@
 /**
- * kernels.cu -- CUDA kernels (sm_100a) and launch logic of the iso2d `binary` update.
+ * kernels.cu -- device_solver_t: the launch logic of the iso2d `binary` update (what runs on which stream, in which order, with
+ * which tile lists) and the device-side state it owns.  One translation unit with the kernels it launches directly:
  *
- * Replaces, per RK stage, the reference's phases P1-P8 and P11 of binary::advance_u
- * (Mara3 src/subprog_binary_scheme.cpp:790-904) and binary::maximum_timestep
- * (:1107-1126).  Two paths produce the same update:
+ *   any_tree_kernels.cuh   stage_fused<TX, TY> (regular blocks, block sizes that are not multiples of 32), general_gradients*,
+ *                          general_update* (blocks at refinement jumps outside the strip kernel's JUMP variant)
+ *   stage_strip.cuh        the one-shot strip kernel: blocks at jumps (JUMP), conserved_q (QMODE), M3B_STAGE=strip
+ *   finish_kernels.cuh     max_timestep_kernel, prepare_positions, finish_stage / finish_stage_cluster / peer_prepare /
+ *                          prepare_next, the product and state-layout kernels
  *
- *   stage_fused<TX,TY>   for "regular" blocks (all 8 neighbours are same-level leaves):
- *                        one CTA per TX x TY tile; the tile plus a 2-cell halo is read
- *                        once from HBM, primitives / PLM differences / face fluxes live
- *                        in shared memory, and the updated cells are written once.
- *   general_*            for blocks touching a refinement jump: guard values are
- *                        fetched through per-face neighbour tables with the reference's
- *                        prolongation (injection) / restriction (2x2 mean) rules for
- *                        primitives AND gradients (mesh_tree_operators.hpp:223-252), and
- *                        coarse faces next to finer blocks take the sum of the two fine
- *                        fluxes (scheme.cpp:614-720).
- *
- * Each CTA also reduces the 16 source-term sums, the CFL minimum and the
- * negative-density count; finish_stage folds the per-CTA rows in a fixed order.
+ * The persistent stage kernel (stage_tma.cuh) and the guard-zone transport of the non-fused paths have their own translation
+ * units (stage_tma.cu, transport.cu).  Reference: phases P1-P8 and P11 of binary::advance_u (Mara3
+ * src/subprog_binary_scheme.cpp:790-904), binary::maximum_timestep (:1107-1126), next_solution (subprog_binary.cpp:258-293).
  */
 #include <algorithm>
 #include <cstdio>
@@ -38,1237 +31,11 @@ using namespace m3b;
 using namespace m3b::dev;
 
 
-namespace
-{
-    // =======================================================================
-    // Block-wide reduction of the stage outputs
-    // =======================================================================
-    __device__ __forceinline__ double warp_sum(double v)
-    {
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-
-    __device__ __forceinline__ double warp_min(double v)
-    {
-        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-        return v;
-    }
-
-    /**
-     * Fold the per-thread sums / CFL minimum into one row.  `red` is shared scratch of
-     * (THREADS / 32) * (NUM_SUMS + 1) doubles.  `mask` says which groups of sums can be
-     * non-zero anywhere in the CTA (bit 0: gravity, bit 1: sinks, bit 2: buffer).
-     */
-    __device__ void reduce_and_store(double* red, const double sums[NUM_SUMS], double dtmin, double scale, double* row)
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = THREADS / 32;
-
-        {
-            // sixteen sums over 32 lanes by recursive halving (a lane keeps half of its values and trades the other half at
-            // distances 16, 8, 4, 2; one butterfly step finishes): 16 shuffled doubles per lane instead of 80.
-            // Lane 2 j ends with the total of sum j.
-            static_assert(NUM_SUMS == 16, "the halving below is written for sixteen values");
-            double v8[8], v4[4], v2[2], v1;
-            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) v8[k] = (b16 ? sums[8 + k] : sums[k]) + __shfl_xor_sync(0xffffffffu, b16 ? sums[k] : sums[8 + k], 16);
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) v4[k] = (b8 ? v8[4 + k] : v8[k]) + __shfl_xor_sync(0xffffffffu, b8 ? v8[k] : v8[4 + k], 8);
-            #pragma unroll
-            for (int k = 0; k < 2; ++k) v2[k] = (b4 ? v4[2 + k] : v4[k]) + __shfl_xor_sync(0xffffffffu, b4 ? v4[k] : v4[2 + k], 4);
-            v1 = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? v2[0] : v2[1], 2);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-            if ((lane & 1) == 0) red[warp * (NUM_SUMS + 1) + (lane >> 1)] = v1;
-        }
-        double m = warp_min(dtmin);
-        if (lane == 0) red[warp * (NUM_SUMS + 1) + NUM_SUMS] = m;
-        __syncthreads();
-
-        if (threadIdx.x < NUM_SUMS)
-        {
-            double v = 0.0;
-            for (int w = 0; w < nw; ++w) v += red[w * (NUM_SUMS + 1) + threadIdx.x];
-            row[threadIdx.x] = v * scale;
-        }
-        if (threadIdx.x == NUM_SUMS)
-        {
-            double v = red[NUM_SUMS];
-            for (int w = 1; w < nw; ++w) v = fmin(v, red[w * (NUM_SUMS + 1) + NUM_SUMS]);
-            row[NUM_SUMS] = v;
-        }
-    }
-
-
-
-    // =======================================================================
-    // Fused stage kernel for regular blocks
-    // =======================================================================
-    template<int TX, int TY>
-    struct tile_t
-    {
-        static constexpr int PX = TX + 4, PY = TY + 4;      // primitives: tile + 2 halo
-        static constexpr int GX = TX + 2, GY = TY + 2;      // PLM differences: tile + 1 halo
-        double P[3][PX][PY];
-        double G[6][GX][GY];                                // d/dx (s, vx, vy), d/dy (s, vx, vy), un-divided
-        double Fx[3][TX + 1][TY];
-        double Fy[3][TX][TY + 1];
-        double xv[TX + 1];
-        double yv[TY + 1];
-        double red[(THREADS / 32) * (NUM_SUMS + 1)];
-    };
-
-    template<int TX, int TY>
-    __global__ void __launch_bounds__(THREADS, 2) stage_fused(
-        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ regular_list,
-        const double* __restrict__ Uin, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* partials, fail_dev_t* fail)
-    {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
-
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N;
-        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
-        const int b  = regular_list[blockIdx.x / tiles_per_block];
-        const int t  = blockIdx.x % tiles_per_block;
-        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
-        const size_t FS = mesh.FS;
-        const int tid = threadIdx.x;
-
-        // ---- phase 0: tile + 2-cell halo -> primitives in shared memory (P1 + P2 of advance_u)
-        for (int k = tid; k < T.PX * T.PY; k += THREADS)
-        {
-            int li = k / T.PY, lj = k % T.PY;
-            int gi = i0 - 2 + li, gj = j0 - 2 + lj;
-            int di = gi < 0 ? -1 : (gi >= N ? 1 : 0);
-            int dj = gj < 0 ? -1 : (gj >= N ? 1 : 0);
-            int nb = (di | dj) ? mesh.nbr9[b * 9 + (di + 1) * 3 + (dj + 1)] : b;
-            size_t c = (size_t(nb) * N + (gi - di * N)) * N + (gj - dj * N);
-            prim_t p = cons_to_prim(Uin[c], Uin[FS + c], Uin[2 * FS + c]);
-            T.P[0][li][lj] = p.s;
-            T.P[1][li][lj] = p.vx;
-            T.P[2][li][lj] = p.vy;
-        }
-        if (tid <= TX) T.xv[tid] = mesh.xv[size_t(b) * (N + 1) + i0 + tid];
-        if (tid >= 64 && tid - 64 <= TY) T.yv[tid - 64] = mesh.yv[size_t(b) * (N + 1) + j0 + tid - 64];
-        __syncthreads();
-
-        // ---- phase 1: PLM differences on tile + 1 halo (P3; the guard gradients of P4 are the neighbours' own)
-        for (int k = tid; k < T.GX * T.GY; k += THREADS)
-        {
-            int li = k / T.GY, lj = k % T.GY;       // gradient cell (li, lj) <-> primitive cell (li + 1, lj + 1)
-            #pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                double c = T.P[q][li + 1][lj + 1];
-                T.G[q][li][lj]     = plm_diff(T.P[q][li][lj + 1], c, T.P[q][li + 2][lj + 1], S.theta);
-                T.G[3 + q][li][lj] = plm_diff(T.P[q][li + 1][lj], c, T.P[q][li + 1][lj + 2], S.theta);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: HLLE + viscous fluxes on the (TX+1) x TY x-faces and TX x (TY+1) y-faces (P6)
-        const double h = mesh.spacing[b], inv_h = 1.0 / h;
-
-        auto x_face = [&] (int li, int lj)      // face between tile cells (li - 1, lj) and (li, lj)
-        {
-            eos_t e = eos_at_face(model, S, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]));
-            prim_t pl = {T.P[0][li + 1][lj + 2], T.P[1][li + 1][lj + 2], T.P[2][li + 1][lj + 2]};
-            prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
-            prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]};
-            prim_t gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
-            double F[3];
-            face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5, inv_h, F);
-            T.Fx[0][li][lj] = F[0]; T.Fx[1][li][lj] = F[1]; T.Fx[2][li][lj] = F[2];
-        };
-        auto y_face = [&] (int li, int lj)      // face between tile cells (li, lj - 1) and (li, lj)
-        {
-            eos_t e = eos_at_face(model, S, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj]);
-            prim_t pl = {T.P[0][li + 2][lj + 1], T.P[1][li + 2][lj + 1], T.P[2][li + 2][lj + 1]};
-            prim_t pr = {T.P[0][li + 2][lj + 2], T.P[1][li + 2][lj + 2], T.P[2][li + 2][lj + 2]};
-            prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]};
-            prim_t gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
-            double F[3];
-            face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5, inv_h, F);
-            T.Fy[0][li][lj] = F[0]; T.Fy[1][li][lj] = F[1]; T.Fy[2][li][lj] = F[2];
-        };
-        for (int k = tid; k < TX * TY; k += THREADS)
-        {
-            x_face(k / TY, k % TY);
-            y_face(k / TY, k % TY);
-        }
-        for (int k = tid; k < TX + TY; k += THREADS)
-        {
-            if (k < TY) x_face(TX, k); else y_face(k - TY, TY);
-        }
-        __syncthreads();
-
-        // ---- phase 3: conservative update + source terms (P8), validation (P11), CFL estimate
-        double sums[NUM_SUMS];
-        #pragma unroll
-        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
-        double dtmin = 1e300;
-        const double dt_over_h = S.dt * inv_h;
-
-        for (int k = tid; k < TX * TY; k += THREADS)
-        {
-            int li = k / TY, lj = k % TY;
-            size_t c = (size_t(b) * N + (i0 + li)) * N + (j0 + lj);
-            double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
-            double br = mesh.br[c];
-            double u0s = 0.0, u0x = 0.0, u0y = 0.0;
-            if (br != 0.0) { u0s = mesh.U0[c]; u0x = mesh.U0[FS + c]; u0y = mesh.U0[2 * FS + c]; }
-
-            double x = 0.5 * (T.xv[li] + T.xv[li + 1]), y = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
-            double src[3], y1, y2;
-            source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
-
-            double n0 = s  - ((T.Fx[0][li + 1][lj] - T.Fx[0][li][lj]) + (T.Fy[0][li][lj + 1] - T.Fy[0][li][lj])) * dt_over_h + src[0];
-            double n1 = px - ((T.Fx[1][li + 1][lj] - T.Fx[1][li][lj]) + (T.Fy[1][li][lj + 1] - T.Fy[1][li][lj])) * dt_over_h + src[1];
-            double n2 = py - ((T.Fx[2][li + 1][lj] - T.Fx[2][li][lj]) + (T.Fy[2][li][lj + 1] - T.Fy[2][li][lj])) * dt_over_h + src[2];
-
-            if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
-
-            if (S.combine)
-            {
-                double w = 1.0 - S.rk_b0;
-                n0 = Un[c] * S.rk_b0 + n0 * w;
-                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
-                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
-            }
-            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
-
-            if (S.compute_dt)
-            {
-                double mx = n1, my = n2;
-                if (mesh.qmode) angmom_to_linear(x, y, n1, n2, mx, my);
-                dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, mx, my));
-            }
-        }
-        reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
-    }
-
-
-}
-namespace
-{
-    // =======================================================================
-    // General path: any 2:1 balanced tree
-    // =======================================================================
-
-    /** Location of a (possibly guard) cell of block b: which leaves hold it and how to combine them. */
-    struct cell_ref_t
-    {
-        int kind;           // 0: one cell of `leaf[0]`; 2: mean of 2x2 cells spread over up to 4 leaves
-        int leaf[4];
-        int ci[4], cj[4];
-    };
-
-    /** get_cell_block (mesh_tree_operators.hpp:223-252) resolved for one cell (i, j), -1 <= i, j <= N. */
-    __device__ __forceinline__ cell_ref_t resolve_cell(const mesh_dev_t& m, int b, int i, int j)
-    {
-        const int N = m.N;
-        cell_ref_t r;
-        r.kind = 0;
-
-        if (i >= 0 && i < N && j >= 0 && j < N)
-        {
-            r.leaf[0] = b; r.ci[0] = i; r.cj[0] = j;
-            return r;
-        }
-        int side = i < 0 ? 0 : (i >= N ? 1 : (j < 0 ? 2 : 3));
-        int ii = i < 0 ? N - 1 : (i >= N ? 0 : i);
-        int jj = j < 0 ? N - 1 : (j >= N ? 0 : j);
-        const face_nbr_dev_t nb = m.nbr[b * 4 + side];
-
-        if (nb.kind == 0)           // same level: the neighbour's own cell
-        {
-            r.leaf[0] = nb.leaf[0]; r.ci[0] = ii; r.cj[0] = jj;
-        }
-        else if (nb.kind == 1)      // coarser: piecewise-constant prolongation (mesh_prolong_restrict.hpp:161-196)
-        {
-            r.leaf[0] = nb.leaf[0]; r.ci[0] = (nb.bx * N + ii) / 2; r.cj[0] = (nb.by * N + jj) / 2;
-        }
-        else                        // finer: 2x2 mean over the children (mesh_prolong_restrict.hpp:124-132, 262-272)
-        {
-            r.kind = 2;
-            #pragma unroll
-            for (int q = 0; q < 4; ++q)
-            {
-                int fi = 2 * ii + (q & 1), fj = 2 * jj + (q >> 1);
-                r.leaf[q] = nb.leaf[(fi >= N) + 2 * (fj >= N)];
-                r.ci[q] = fi % N; r.cj[q] = fj % N;
-            }
-        }
-        return r;
-    }
-
-    __device__ __forceinline__ prim_t load_prim(const mesh_dev_t& m, const double* U, int leaf, int i, int j)
-    {
-        size_t c = (size_t(leaf) * m.N + i) * m.N + j;
-        if (m.qmode)
-        {
-            // recover_primitive(Q, x) (physics_iso2d.hpp:376-389) at the centre of the cell in ITS block
-            const double* xv = m.xv + size_t(leaf) * (m.N + 1);
-            const double* yv = m.yv + size_t(leaf) * (m.N + 1);
-            const double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
-            const double s = U[c], sr = U[m.FS + c] / s, lz = U[2 * m.FS + c] / s;
-            double vx, vy;
-            angmom_to_linear(x, y, sr, lz, vx, vy);
-            return {s, vx, vy};
-        }
-        return cons_to_prim(U[c], U[m.FS + c], U[2 * m.FS + c]);
-    }
-
-    /** Primitive at cell (i, j) of block b with guard fill: extend(p0, axis, 1) (scheme.cpp:132-142). */
-    __device__ __forceinline__ prim_t prim_from_ref(const mesh_dev_t& m, const double* U, const cell_ref_t& r)
-    {
-        if (r.kind == 0) return load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
-        prim_t p00 = load_prim(m, U, r.leaf[0], r.ci[0], r.cj[0]);
-        prim_t p10 = load_prim(m, U, r.leaf[1], r.ci[1], r.cj[1]);
-        prim_t p01 = load_prim(m, U, r.leaf[2], r.ci[2], r.cj[2]);
-        prim_t p11 = load_prim(m, U, r.leaf[3], r.ci[3], r.cj[3]);
-        // restrict on axis 0 then on axis 1, each (h0 + h1) / 2
-        return {((p00.s + p10.s) * 0.5 + (p01.s + p11.s) * 0.5) * 0.5,
-                ((p00.vx + p10.vx) * 0.5 + (p01.vx + p11.vx) * 0.5) * 0.5,
-                ((p00.vy + p10.vy) * 0.5 + (p01.vy + p11.vy) * 0.5) * 0.5};
-    }
-
-    __device__ __forceinline__ prim_t prim_at(const mesh_dev_t& m, const double* U, int b, int i, int j)
-    {
-        return prim_from_ref(m, U, resolve_cell(m, b, i, j));
-    }
-
-    __device__ __forceinline__ prim_t load_grad(const mesh_dev_t& m, const double* G, int axis, int leaf, int i, int j)
-    {
-        size_t c = (size_t(m.gslot[leaf]) * m.N + i) * m.N + j;
-        const double* g = G + size_t(3 * axis) * m.GS;
-        return {g[c], g[m.GS + c], g[2 * m.GS + c]};
-    }
-
-    /** Gradient (d/d axis) at cell (i, j) of block b with guard fill: extend(gx, ...) etc. (scheme.cpp:810-813). */
-    __device__ __forceinline__ prim_t grad_from_ref(const mesh_dev_t& m, const double* G, int axis, const cell_ref_t& r)
-    {
-        if (r.kind == 0) return load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
-        prim_t g00 = load_grad(m, G, axis, r.leaf[0], r.ci[0], r.cj[0]);
-        prim_t g10 = load_grad(m, G, axis, r.leaf[1], r.ci[1], r.cj[1]);
-        prim_t g01 = load_grad(m, G, axis, r.leaf[2], r.ci[2], r.cj[2]);
-        prim_t g11 = load_grad(m, G, axis, r.leaf[3], r.ci[3], r.cj[3]);
-        return {((g00.s + g10.s) * 0.5 + (g01.s + g11.s) * 0.5) * 0.5,
-                ((g00.vx + g10.vx) * 0.5 + (g01.vx + g11.vx) * 0.5) * 0.5,
-                ((g00.vy + g10.vy) * 0.5 + (g01.vy + g11.vy) * 0.5) * 0.5};
-    }
-
-    __device__ __forceinline__ prim_t grad_at(const mesh_dev_t& m, const double* G, int axis, int b, int i, int j)
-    {
-        return grad_from_ref(m, G, axis, resolve_cell(m, b, i, j));
-    }
-
-    /** P2 + P3 for the listed blocks: physical PLM gradients at the block's own spacing. */
-    __global__ void __launch_bounds__(THREADS) general_gradients(
-        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
-        const double* __restrict__ Uin, double* __restrict__ G)
-    {
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N, b = list[blockIdx.x];
-        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
-        const size_t base = size_t(mesh.gslot[b]) * N * N;
-
-        for (int k = threadIdx.x; k < N * N; k += THREADS)
-        {
-            int i = k / N, j = k % N;
-            prim_t c  = prim_at(mesh, Uin, b, i, j);
-            prim_t xl = prim_at(mesh, Uin, b, i - 1, j), xr = prim_at(mesh, Uin, b, i + 1, j);
-            prim_t yl = prim_at(mesh, Uin, b, i, j - 1), yr = prim_at(mesh, Uin, b, i, j + 1);
-            G[0 * mesh.GS + base + k] = plm_diff(xl.s,  c.s,  xr.s,  theta) * inv_h;
-            G[1 * mesh.GS + base + k] = plm_diff(xl.vx, c.vx, xr.vx, theta) * inv_h;
-            G[2 * mesh.GS + base + k] = plm_diff(xl.vy, c.vy, xr.vy, theta) * inv_h;
-            G[3 * mesh.GS + base + k] = plm_diff(yl.s,  c.s,  yr.s,  theta) * inv_h;
-            G[4 * mesh.GS + base + k] = plm_diff(yl.vx, c.vx, yr.vx, theta) * inv_h;
-            G[5 * mesh.GS + base + k] = plm_diff(yl.vy, c.vy, yr.vy, theta) * inv_h;
-        }
-    }
-
-    /** The same in TX x TY tiles: the tile's primitives plus one guard layer go through shared memory once. */
-    template<int TX, int TY>
-    __global__ void __launch_bounds__(THREADS) general_gradients_tiled(
-        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
-        const double* __restrict__ Uin, double* __restrict__ G)
-    {
-        __shared__ double P[3][TX + 2][TY + 2];
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N;
-        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
-        const int b = list[blockIdx.x / tiles_per_block], t = blockIdx.x % tiles_per_block;
-        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
-        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
-        const size_t base = size_t(mesh.gslot[b]) * N * N;
-
-        for (int k = threadIdx.x; k < (TX + 2) * (TY + 2); k += THREADS)
-        {
-            const int li = k / (TY + 2), lj = k % (TY + 2);
-            if ((li == 0 || li == TX + 1) && (lj == 0 || lj == TY + 1)) continue;      // corners are not part of the stencil
-            const prim_t p = prim_at(mesh, Uin, b, i0 - 1 + li, j0 - 1 + lj);
-            P[0][li][lj] = p.s; P[1][li][lj] = p.vx; P[2][li][lj] = p.vy;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < TX * TY; k += THREADS)
-        {
-            const int li = k / TY + 1, lj = k % TY + 1;
-            const size_t c = base + size_t(i0 + li - 1) * N + (j0 + lj - 1);
-            #pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                G[q * mesh.GS + c]       = plm_diff(P[q][li - 1][lj], P[q][li][lj], P[q][li + 1][lj], theta) * inv_h;
-                G[(3 + q) * mesh.GS + c] = plm_diff(P[q][li][lj - 1], P[q][li][lj], P[q][li][lj + 1], theta) * inv_h;
-            }
-        }
-    }
-
-    /**
-     * The same for the two outermost cell layers along each side of the listed blocks only, one CTA per (block, side):
-     * all that stage_strip<.., JUMP> reads from a neighbour (guard gradients are injected from / averaged over cells at
-     * most two deep, and the fine faces of the flux correction touch the outermost layer).
-     */
-    __global__ void __launch_bounds__(128, 8) general_gradients_ring(
-        mesh_dev_t mesh, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
-        const double* __restrict__ Uin, double* __restrict__ G)
-    {
-        // Region cell (r, a): r = 0..3 counts layers from the guard layer (r = 0) inwards, a = 0..N+1 runs along the side
-        // from the guard cell before its first cell to the one after its last; primitives go through shared memory once.
-        extern __shared__ double ring_P[];              // [3][4][N + 2]
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N, W = N + 2, b = list[blockIdx.x >> 2], side = blockIdx.x & 3;
-        const bool high = side & 1, along_x = side >= 2;        // along_x: the side runs along i (sides in y)
-        const double theta = S.theta, inv_h = 1.0 / mesh.spacing[b];
-        const size_t base = size_t(mesh.gslot[b]) * N * N;
-
-        for (int k = threadIdx.x; k < 4 * W; k += 128)
-        {
-            const int r = k / W, a = k - r * W;
-            const int n = high ? N - r : r - 1, t = a - 1;
-            if (r == 0 && (t < 0 || t >= N)) continue;          // corners are not part of the stencil
-            const prim_t p = along_x ? prim_at(mesh, Uin, b, t, n) : prim_at(mesh, Uin, b, n, t);
-            ring_P[(0 * 4 + r) * W + a] = p.s; ring_P[(1 * 4 + r) * W + a] = p.vx; ring_P[(2 * 4 + r) * W + a] = p.vy;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < 2 * N; k += 128)
-        {
-            const int d = k / N, t = k - d * N, r = d + 1, a = t + 1;
-            const int n = high ? N - r : r - 1;
-            const size_t cell = base + (along_x ? size_t(t) * N + n : size_t(n) * N + t);
-            #pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                const double* Pq = ring_P + size_t(q) * 4 * W;
-                const double c = Pq[r * W + a];
-                const double below = Pq[(high ? r + 1 : r - 1) * W + a], above = Pq[(high ? r - 1 : r + 1) * W + a];
-                const double gn = plm_diff(below, c, above, theta) * inv_h;                         // across the layers
-                const double gt = plm_diff(Pq[r * W + a - 1], c, Pq[r * W + a + 1], theta) * inv_h; // along the side
-                G[(along_x ? 3 + q : q) * mesh.GS + cell] = gn;
-                G[(along_x ? q : 3 + q) * mesh.GS + cell] = gt;
-            }
-        }
-    }
-
-    /**
-     * Flux (times face length) through face f (0..N) of block b along AXIS at transverse index k,
-     * as block b computes it: block_fluxes_u (scheme.cpp:472-516).
-     */
-    template<int AXIS>
-    __device__ void general_face_flux(const mesh_dev_t& m, const model_t& model, const stage_t& S,
-        const double* U, const double* G, int b, int f, int k, double F[3])
-    {
-        const int N = m.N;
-        const double* xv = m.xv + size_t(b) * (N + 1);
-        const double* yv = m.yv + size_t(b) * (N + 1);
-        int li = AXIS == 0 ? f - 1 : k, lj = AXIS == 0 ? k : f - 1;
-        int ri = AXIS == 0 ? f : k,     rj = AXIS == 0 ? k : f;
-        double x   = AXIS == 0 ? xv[f] : 0.5 * (xv[k] + xv[k + 1]);
-        double y   = AXIS == 0 ? 0.5 * (yv[k] + yv[k + 1]) : yv[f];
-        double len = AXIS == 0 ? yv[k + 1] - yv[k] : xv[k + 1] - xv[k];
-
-        prim_t pl = prim_at(m, U, b, li, lj), pr = prim_at(m, U, b, ri, rj);
-        prim_t gl = grad_at(m, G, AXIS, b, li, lj), gr = grad_at(m, G, AXIS, b, ri, rj);
-        prim_t hl = grad_at(m, G, 1 - AXIS, b, li, lj), hr = grad_at(m, G, 1 - AXIS, b, ri, rj);
-        eos_t e = eos_at_face(model, S, x, y);
-        face_flux<AXIS>(e, pl, pr, gl, gr, hl.vx, hl.vy, hr.vx, hr.vy, 0.5 * m.spacing[b], 1.0, F);
-        if (m.qmode) to_angmom_fluxes<AXIS>(model, x, y, F);
-        F[0] *= len; F[1] *= len; F[2] *= len;
-    }
-
-    /** The same with correct_fluxes_{x,y} applied (scheme.cpp:614-720). */
-    template<int AXIS>
-    __device__ void general_face_flux_corrected(const mesh_dev_t& m, const model_t& model, const stage_t& S,
-        const double* U, const double* G, int b, int f, int k, double F[3])
-    {
-        const int N = m.N;
-        int side = f == 0 ? 2 * AXIS : (f == N ? 2 * AXIS + 1 : -1);
-
-        if (side >= 0 && m.nbr[b * 4 + side].kind == 2)
-        {
-            // the neighbour region is refined: sum of the two fine faces, computed as the fine blocks do
-            const face_nbr_dev_t nb = m.nbr[b * 4 + side];
-            int near = side % 2 ? 0 : 1;                    // children adjacent to this face
-            int fine_face = side % 2 ? 0 : N;
-            double A[3], C[3];
-            int k0 = 2 * k, k1 = 2 * k + 1;
-            int c0 = AXIS == 0 ? nb.leaf[near + 2 * (k0 >= N)] : nb.leaf[(k0 >= N) + 2 * near];
-            int c1 = AXIS == 0 ? nb.leaf[near + 2 * (k1 >= N)] : nb.leaf[(k1 >= N) + 2 * near];
-            general_face_flux<AXIS>(m, model, S, U, G, c0, fine_face, k0 % N, A);
-            general_face_flux<AXIS>(m, model, S, U, G, c1, fine_face, k1 % N, C);
-            F[0] = A[0] + C[0]; F[1] = A[1] + C[1]; F[2] = A[2] + C[2];
-            return;
-        }
-        general_face_flux<AXIS>(m, model, S, U, G, b, f, k, F);
-    }
-
-    /** P6-P8 + P11 for the listed blocks, one CTA per block. */
-    __global__ void __launch_bounds__(THREADS) general_update(
-        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
-        const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* __restrict__ partials, fail_dev_t* fail)
-    {
-        __shared__ double red[(THREADS / 32) * (NUM_SUMS + 1)];
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N, b = list[blockIdx.x];
-        const size_t FS = mesh.FS;
-        const double* xv = mesh.xv + size_t(b) * (N + 1);
-        const double* yv = mesh.yv + size_t(b) * (N + 1);
-        const double h = mesh.spacing[b];
-
-        double sums[NUM_SUMS];
-        #pragma unroll
-        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
-        double dtmin = 1e300;
-
-        for (int k = threadIdx.x; k < N * N; k += THREADS)
-        {
-            int i = k / N, j = k % N;
-            size_t c = size_t(b) * N * N + k;
-            double Fl[3], Fr[3], Fb[3], Ft[3];
-            general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i, j, Fl);
-            general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i + 1, j, Fr);
-            general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j, i, Fb);
-            general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j + 1, i, Ft);
-
-            double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
-            double br = mesh.br[c];
-            double u0s = mesh.U0[c], u0x = mesh.U0[FS + c], u0y = mesh.U0[2 * FS + c];
-            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
-            double dt_over_dA = S.dt / ((xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]));
-            double src[3], y1, y2;
-            if (mesh.qmode)
-            {
-                const prim_t p = load_prim(mesh, Uin, b, i, j);
-                source_terms_q(model, S, x, y, s, px, py, p.vx, p.vy, u0s, u0x, u0y, br, src, sums, y1, y2);
-            }
-            else source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
-
-            double n0 = s  - ((Fr[0] - Fl[0]) + (Ft[0] - Fb[0])) * dt_over_dA + src[0];
-            double n1 = px - ((Fr[1] - Fl[1]) + (Ft[1] - Fb[1])) * dt_over_dA + src[1];
-            double n2 = py - ((Fr[2] - Fl[2]) + (Ft[2] - Fb[2])) * dt_over_dA + src[2];
-
-            if (n0 < 0.0) report_negative(fail, b, k, n0);
-
-            if (S.combine)
-            {
-                double w = 1.0 - S.rk_b0;
-                n0 = Un[c] * S.rk_b0 + n0 * w;
-                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
-                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
-            }
-            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
-
-            if (S.compute_dt)
-            {
-                double mx = n1, my = n2;
-                if (mesh.qmode) angmom_to_linear(x, y, n1, n2, mx, my);
-                dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, mx, my));
-            }
-        }
-        reduce_and_store(red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
-    }
-
-
-    /**
-     * P6-P8 + P11 for blocks at refinement jumps, one CTA per TX x TY tile: the same update as general_update, but the
-     * tile's primitives (guard cells through prolongation / restriction, mesh_tree_operators.hpp:223-252) and the
-     * gradients of general_gradients are staged in shared memory once, every face flux is computed once, and only the
-     * faces on a block side whose neighbour is finer take the slow path (sum of the two fine fluxes, scheme.cpp:614-720).
-     * Rows: one per tile, folded per block by finish_stage like the fused kernels' rows.
-     */
-    template<int TX, int TY>
-    __global__ void __launch_bounds__(THREADS, 3) general_update_tiled(
-        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const int* __restrict__ list,
-        const double* __restrict__ Uin, const double* __restrict__ G, const double* __restrict__ Un, double* __restrict__ Uout,
-        double* __restrict__ partials, fail_dev_t* fail)
-    {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        tile_t<TX, TY>& T = *reinterpret_cast<tile_t<TX, TY>*>(smem_raw);
-
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N;
-        const int tiles_y = N / TY, tiles_per_block = (N / TX) * tiles_y;
-        const int b  = list[blockIdx.x / tiles_per_block];
-        const int t  = blockIdx.x % tiles_per_block;
-        const int i0 = (t / tiles_y) * TX, j0 = (t % tiles_y) * TY;
-        const size_t FS = mesh.FS;
-        const int tid = threadIdx.x;
-        const double h = mesh.spacing[b];
-
-        // which block sides border a finer neighbour (their faces take the flux-correction path): loaded now, used after the barrier
-        const bool finer_lo_x = i0 == 0 && mesh.nbr[b * 4 + 0].kind == 2, finer_hi_x = i0 + TX == N && mesh.nbr[b * 4 + 1].kind == 2;
-        const bool finer_lo_y = j0 == 0 && mesh.nbr[b * 4 + 2].kind == 2, finer_hi_y = j0 + TY == N && mesh.nbr[b * 4 + 3].kind == 2;
-
-        // ---- tile + 1 guard layer (no corners: a face only needs its two cells): primitives and physical gradients
-        for (int k = tid; k < (TX + 2) * (TY + 2); k += THREADS)
-        {
-            const int li = k / (TY + 2), lj = k % (TY + 2);         // region cell <-> block cell (i0 - 1 + li, j0 - 1 + lj)
-            const bool edge_i = li == 0 || li == TX + 1, edge_j = lj == 0 || lj == TY + 1;
-            if (edge_i && edge_j) continue;
-            const int gi = i0 - 1 + li, gj = j0 - 1 + lj;
-            const cell_ref_t ref = resolve_cell(mesh, b, gi, gj);       // once for the primitive and both gradients
-            const prim_t p = prim_from_ref(mesh, Uin, ref);
-            const prim_t gx = grad_from_ref(mesh, G, 0, ref), gy = grad_from_ref(mesh, G, 1, ref);
-            T.P[0][li][lj] = p.s;  T.P[1][li][lj] = p.vx;  T.P[2][li][lj] = p.vy;
-            T.G[0][li][lj] = gx.s; T.G[1][li][lj] = gx.vx; T.G[2][li][lj] = gx.vy;
-            T.G[3][li][lj] = gy.s; T.G[4][li][lj] = gy.vx; T.G[5][li][lj] = gy.vy;
-        }
-        if (tid <= TX) T.xv[tid] = mesh.xv[size_t(b) * (N + 1) + i0 + tid];
-        if (tid >= 64 && tid - 64 <= TY) T.yv[tid - 64] = mesh.yv[size_t(b) * (N + 1) + j0 + tid - 64];
-        __syncthreads();
-
-        // ---- fluxes (times face length, as block_fluxes_u, scheme.cpp:472-516)
-
-        auto x_face = [&] (int li, int lj)      // between tile cells (li - 1, lj) and (li, lj), 0 <= li <= TX
-        {
-            double F[3];
-            if ((li == 0 && finer_lo_x) || (li == TX && finer_hi_x)) general_face_flux_corrected<0>(mesh, model, S, Uin, G, b, i0 + li, j0 + lj, F);
-            else
-            {
-                const eos_t e = eos_at_face(model, S, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]));
-                const prim_t pl = {T.P[0][li][lj + 1], T.P[1][li][lj + 1], T.P[2][li][lj + 1]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
-                const prim_t gl = {T.G[0][li][lj + 1], T.G[1][li][lj + 1], T.G[2][li][lj + 1]}, gr = {T.G[0][li + 1][lj + 1], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1]};
-                face_flux<0>(e, pl, pr, gl, gr, T.G[4][li][lj + 1], T.G[5][li][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1], 0.5 * h, 1.0, F);
-                if (mesh.qmode) to_angmom_fluxes<0>(model, T.xv[li], 0.5 * (T.yv[lj] + T.yv[lj + 1]), F);
-                const double len = T.yv[lj + 1] - T.yv[lj];
-                F[0] *= len; F[1] *= len; F[2] *= len;
-            }
-            T.Fx[0][li][lj] = F[0]; T.Fx[1][li][lj] = F[1]; T.Fx[2][li][lj] = F[2];
-        };
-        auto y_face = [&] (int li, int lj)      // between tile cells (li, lj - 1) and (li, lj), 0 <= lj <= TY
-        {
-            double F[3];
-            if ((lj == 0 && finer_lo_y) || (lj == TY && finer_hi_y)) general_face_flux_corrected<1>(mesh, model, S, Uin, G, b, j0 + lj, i0 + li, F);
-            else
-            {
-                const eos_t e = eos_at_face(model, S, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj]);
-                const prim_t pl = {T.P[0][li + 1][lj], T.P[1][li + 1][lj], T.P[2][li + 1][lj]}, pr = {T.P[0][li + 1][lj + 1], T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1]};
-                const prim_t gl = {T.G[3][li + 1][lj], T.G[4][li + 1][lj], T.G[5][li + 1][lj]}, gr = {T.G[3][li + 1][lj + 1], T.G[4][li + 1][lj + 1], T.G[5][li + 1][lj + 1]};
-                face_flux<1>(e, pl, pr, gl, gr, T.G[1][li + 1][lj], T.G[2][li + 1][lj], T.G[1][li + 1][lj + 1], T.G[2][li + 1][lj + 1], 0.5 * h, 1.0, F);
-                if (mesh.qmode) to_angmom_fluxes<1>(model, 0.5 * (T.xv[li] + T.xv[li + 1]), T.yv[lj], F);
-                const double len = T.xv[li + 1] - T.xv[li];
-                F[0] *= len; F[1] *= len; F[2] *= len;
-            }
-            T.Fy[0][li][lj] = F[0]; T.Fy[1][li][lj] = F[1]; T.Fy[2][li][lj] = F[2];
-        };
-        for (int k = tid; k < TX * TY; k += THREADS)
-        {
-            x_face(k / TY, k % TY);
-            y_face(k / TY, k % TY);
-        }
-        for (int k = tid; k < TX + TY; k += THREADS)
-        {
-            if (k < TY) x_face(TX, k); else y_face(k - TY, TY);
-        }
-        __syncthreads();
-
-        // ---- update (block_update_u, scheme.cpp:568-587), validation, CFL estimate
-        double sums[NUM_SUMS];
-        #pragma unroll
-        for (int k = 0; k < NUM_SUMS; ++k) sums[k] = 0.0;
-        double dtmin = 1e300;
-
-        for (int k = tid; k < TX * TY; k += THREADS)
-        {
-            const int li = k / TY, lj = k % TY;
-            const size_t c = (size_t(b) * N + (i0 + li)) * N + (j0 + lj);
-            const double s = Uin[c], px = Uin[FS + c], py = Uin[2 * FS + c];
-            const double br = mesh.br[c];
-            const double u0s = mesh.U0[c], u0x = mesh.U0[FS + c], u0y = mesh.U0[2 * FS + c];
-            const double x = 0.5 * (T.xv[li] + T.xv[li + 1]), y = 0.5 * (T.yv[lj] + T.yv[lj + 1]);
-            const double dt_over_dA = S.dt / ((T.xv[li + 1] - T.xv[li]) * (T.yv[lj + 1] - T.yv[lj]));
-            double src[3], y1, y2;
-            if (mesh.qmode) source_terms_q(model, S, x, y, s, px, py, T.P[1][li + 1][lj + 1], T.P[2][li + 1][lj + 1], u0s, u0x, u0y, br, src, sums, y1, y2);
-            else source_terms(model, S, x, y, s, px, py, u0s, u0x, u0y, br, src, sums, y1, y2);
-
-            double n0 = s  - ((T.Fx[0][li + 1][lj] - T.Fx[0][li][lj]) + (T.Fy[0][li][lj + 1] - T.Fy[0][li][lj])) * dt_over_dA + src[0];
-            double n1 = px - ((T.Fx[1][li + 1][lj] - T.Fx[1][li][lj]) + (T.Fy[1][li][lj + 1] - T.Fy[1][li][lj])) * dt_over_dA + src[1];
-            double n2 = py - ((T.Fx[2][li + 1][lj] - T.Fx[2][li][lj]) + (T.Fy[2][li][lj + 1] - T.Fy[2][li][lj])) * dt_over_dA + src[2];
-
-            if (n0 < 0.0) report_negative(fail, b, (i0 + li) * N + j0 + lj, n0);
-
-            if (S.combine)
-            {
-                const double w = 1.0 - S.rk_b0;
-                n0 = Un[c] * S.rk_b0 + n0 * w;
-                n1 = Un[FS + c] * S.rk_b0 + n1 * w;
-                n2 = Un[2 * FS + c] * S.rk_b0 + n2 * w;
-            }
-            Uout[c] = n0; Uout[FS + c] = n1; Uout[2 * FS + c] = n2;
-
-            if (S.compute_dt) dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, n0, n1, n2));
-        }
-        reduce_and_store(T.red, sums, dtmin, h * h, partials + size_t(blockIdx.x) * ROW);
-    }
-
-
-}
+#include "any_tree_kernels.cuh"     // reductions, stage_fused, general_gradients*, general_update*
 #include "stage_strip.cuh"      // after the any-tree helpers: its JUMP variant fetches guard cells through them
+#include "finish_kernels.cuh"       // max_timestep_kernel, prepare_positions, finish_stage*, prepare_next, product kernels
 namespace
 {
-    // =======================================================================
-    // Stand-alone CFL pass, row folding, layout changes
-    // =======================================================================
-
-    /** maximum_timestep (scheme.cpp:1107-1126): per-CTA min of spacing / max wavespeed. */
-    __global__ void __launch_bounds__(THREADS) max_timestep_kernel(
-        mesh_dev_t mesh, model_t model, const stage_t* __restrict__ stage_ptr, const double* __restrict__ U, double* __restrict__ partials)
-    {
-        __shared__ double red[THREADS / 32];
-        const stage_t S = *stage_ptr;
-        const int N = mesh.N, b = blockIdx.x;
-        const double* xv = mesh.xv + size_t(b) * (N + 1);
-        const double* yv = mesh.yv + size_t(b) * (N + 1);
-        const double h = mesh.spacing[b];
-        double dtmin = 1e300;
-
-        for (int k = threadIdx.x; k < N * N; k += THREADS)
-        {
-            int i = k / N, j = k % N;
-            size_t c = size_t(b) * N * N + k;
-            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
-            double y1, y2;
-            sound_speed_squared(model, S, x, y, y1, y2);
-            double mx = U[mesh.FS + c], my = U[2 * mesh.FS + c];
-            if (mesh.qmode) angmom_to_linear(x, y, mx, my, mx, my);      // (the reference itself needs fixed_dt = 1 with conserved_q)
-            dtmin = fmin(dtmin, h / max_wavespeed(model, S, x, y, y1, y2, U[c], mx, my));
-        }
-        dtmin = warp_min(dtmin);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dtmin;
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            for (int w = 1; w < THREADS / 32; ++w) dtmin = fmin(dtmin, red[w]);
-            double* row = partials + size_t(b) * ROW;
-            for (int k = 0; k < NUM_SUMS; ++k) row[k] = 0.0;
-            row[NUM_SUMS] = dtmin;
-        }
-    }
-
-    __device__ void fill_stage(stage_t& st, double time, double dt, double theta, const two_body_t& b, double rk_b0, int combine, int compute_dt)
-    {
-        st.time = time; st.dt = dt; st.theta = theta;
-        st.x1 = b.body1.x; st.y1 = b.body1.y; st.m1 = b.body1.mass; st.vx1 = b.body1.vx; st.vy1 = b.body1.vy;
-        st.x2 = b.body2.x; st.y2 = b.body2.y; st.m2 = b.body2.mass; st.vx2 = b.body2.vx; st.vy2 = b.body2.vy;
-        st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
-    }
-
-    /** Everything of a stage input except dt (written later, when the CFL reduction is known). */
-    __device__ void fill_stage_but_dt(stage_t& st, double time, double theta, const two_body_t& b, double rk_b0, int combine, int compute_dt)
-    {
-        st.time = time; st.theta = theta;
-        st.x1 = b.body1.x; st.y1 = b.body1.y; st.m1 = b.body1.mass; st.vx1 = b.body1.vx; st.vy1 = b.body1.vy;
-        st.x2 = b.body2.x; st.y2 = b.body2.y; st.m2 = b.body2.mass; st.vx2 = b.body2.vx; st.vy2 = b.body2.vy;
-        st.rk_b0 = rk_b0; st.combine = combine; st.compute_dt = compute_dt;
-    }
-
-    /**
-     * The slow half of prepare_next, off the critical path (side stream): body positions (a Kepler solve and a
-     * handful of divisions, ~9 us for one thread) for stages whose TIME is already known.  `src` is the first
-     * stage of a step with (time, dt) = (t, dt): the step's second stage `second` runs at t + dt and the first
-     * stage of the step after it, `following`, at t/2 + ((t + dt) + dt)/2 (scheme.cpp:1036, 1055).  Either may be null.
-     */
-    __global__ void prepare_positions(step_config_t cfg, const stage_t* __restrict__ src, stage_t* second, stage_t* following)
-    {
-        const double t = src->time, dt = src->dt;
-        if (threadIdx.x == 0 && second)
-        {
-            const double tb = t + dt;
-            fill_stage_but_dt(*second, tb, cfg.theta, two_body_state(cfg.elements, tb), 0.5, 1, ! cfg.fixed_dt);
-        }
-        if (threadIdx.x == 1 && following)
-        {
-            const double tn = t * 0.5 + ((t + dt) + dt) * 0.5;
-            fill_stage_but_dt(*following, tn, cfg.theta, two_body_state(cfg.elements, tn), 0.0, 0, 0);
-        }
-    }
-
-    // =======================================================================
-    // Peer-memory guard-zone exchange (NVLink loads / stores, no NCCL in the step loop)
-    // =======================================================================
-    /**
-     * prepare_next for several ranks without NCCL (called by the >= 128 threads of one CTA): deliver this rank's
-     * two stage results to every rank's mailbox, wait for everybody else's, fold them in rank order (every rank
-     * gets the same bits) and write time and dt of the next step's stages.
-     */
-    __device__ void peer_prepare(const stage_result_t* __restrict__ local, const peer_table_t& peers, int me, int nranks,
-        int slot_stride, int slot_a, int slot_b, unsigned long long counter,
-        const step_config_t& cfg, const stage_t* __restrict__ current_a, stage_t* next_a, stage_t* next_b, stage_result_t* host_results,
-        unsigned long long* clock_words = nullptr)
-    {
-        __shared__ double dt_min_b;
-        constexpr int words = sizeof(stage_result_t) / sizeof(double);
-
-        for (int k = threadIdx.x; k < nranks * 2 * words; k += blockDim.x)
-        {
-            const int p = k / (2 * words), slot = (k / words) % 2 ? slot_b : slot_a, w = k % words;
-            reinterpret_cast<double*>(peers.results[p] + size_t(me) * slot_stride + slot)[w] = __ldcg(reinterpret_cast<const double*>(local + slot) + w);
-        }
-        __threadfence_system();
-        __syncthreads();
-        unsigned long long t_wait = 0;
-        if (threadIdx.x == 0 && clock_words) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait));
-        if (threadIdx.x < nranks)
-        {
-            if (threadIdx.x != me) store_release_sys(peers.result_flag[threadIdx.x] + me, counter);
-            if (threadIdx.x != me) bounded_wait_sys(peers.result_flag[me] + threadIdx.x, counter, peers, me, threadIdx.x);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && clock_words)
-        {
-            // how long this rank waited for the slowest rank's results (bench.py: exchange.result_exchange_us)
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            clock_words[0] += t1 - t_wait;
-            clock_words[1] += 1;
-        }
-
-        const int k = threadIdx.x;
-        if (k < 2)
-        {
-            const int slot = k == 0 ? slot_a : slot_b;
-            stage_result_t r = stage_result_t();
-            r.dt_min = 1e300;
-            for (int p = 0; p < nranks; ++p)
-            {
-                const double* q = reinterpret_cast<const double*>(peers.results[me] + size_t(p) * slot_stride + slot);
-                for (int c = 0; c < 16; ++c) r.sums[c] += __ldcg(q + c);
-                r.work[0] += __ldcg(q + 16);
-                r.work[1] += __ldcg(q + 17);
-                r.dt_min = dmin(r.dt_min, __ldcg(q + 18));
-                r.num_negative += __ldcg(reinterpret_cast<const unsigned int*>(q + 19));
-            }
-            r.pad = static_cast<unsigned int>(load_acquire_sys(peers.abort_word[me]));     // non-zero: some rank gave up waiting (bounded_wait_sys)
-            host_results[slot] = r;
-            if (k == 1) dt_min_b = r.dt_min;
-        }
-        __syncthreads();
-        if (k < 2)
-        {
-            const double t = current_a->time, dt = current_a->dt;
-            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
-            const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
-            if (k == 0) { next_a->time = t_next; next_a->dt = dt_next; }        // positions: prepare_positions, off the critical path
-            else        { next_b->time = t_next + dt_next; next_b->dt = dt_next; }
-        }
-    }
-
-    /**
-     * Fold the stage kernels' rows in a fixed order (deterministic) and publish the stage result.
-     * Rows [0, num_fused) are regular blocks: their `tpb` tile rows (written by stage_strip / stage_fused,
-     * no fences or tickets in those kernels) are first folded, in tile order, into one row per block;
-     * rows [num_fused, num_rows) are the any-tree path's blocks, `gtpb` tile rows each (1: one row per block).
-     * The reference evaluates the work done on each body PER BLOCK from that block's accreted
-     * mass and momentum -- a non-linear function -- and then sums over blocks
-     * (scheme.cpp:407-408, 829-830), so the same is done here from the per-block rows.
-     * CTA c handles FINISH_ROWS_PER_CTA block rows; the last CTA to finish folds the CTA rows in CTA order.
-     */
-    __global__ void __launch_bounds__(FINISH_THREADS) finish_stage(const double* tile_rows, int num_fused, int tpb,
-        const double* general_rows, int gtpb, int num_rows, double* cta_rows, int* ticket, const stage_t* __restrict__ stage_ptr,
-        fail_dev_t* fail, stage_result_t* result, prepare_args_t prep)
-    {
-        __shared__ double dt_min_all;
-        __shared__ double srow[FINISH_ROWS_PER_CTA][ROW];
-        __shared__ double wred[2][FINISH_ROWS_PER_CTA];
-        __shared__ double fin[FINISH_THREADS / 32][32];
-        __shared__ int is_last;
-        const stage_t S = *stage_ptr;
-        const int r0 = blockIdx.x * FINISH_ROWS_PER_CTA, n = min(FINISH_ROWS_PER_CTA, num_rows - r0);
-
-        // (A) one row per block
-        for (int idx = threadIdx.x; idx < n * ROW; idx += FINISH_THREADS)
-        {
-            const int r = idx / ROW, k = idx % ROW, R = r0 + r;
-            if (k > NUM_SUMS) continue;
-            double v;
-            if (R < num_fused)
-            {
-                const double* rows = tile_rows + size_t(R) * tpb * ROW + k;
-                v = k == NUM_SUMS ? 1e300 : 0.0;
-                for (int t = 0; t < tpb; ++t)
-                {
-                    double p = __ldcg(rows + size_t(t) * ROW);
-                    v = k == NUM_SUMS ? dmin(v, p) : v + p;
-                }
-            }
-            else
-            {
-                // blocks of the any-tree path: gtpb tile rows each (general_update_tiled), or one row (general_update)
-                const double* rows = general_rows + size_t(R - num_fused) * gtpb * ROW + k;
-                v = __ldcg(rows);
-                for (int t = 1; t < gtpb; ++t)
-                {
-                    double p = __ldcg(rows + size_t(t) * ROW);
-                    v = k == NUM_SUMS ? dmin(v, p) : v + p;
-                }
-            }
-            srow[r][k] = v;
-        }
-        __syncthreads();
-
-        // (B) fold the CTA's rows in row order; block-wise work integrals
-        double* mine = cta_rows + size_t(blockIdx.x) * ROW;
-        if (threadIdx.x <= NUM_SUMS)
-        {
-            const int k = threadIdx.x;
-            double v = k == NUM_SUMS ? 1e300 : 0.0;
-            for (int r = 0; r < n; ++r) v = k == NUM_SUMS ? dmin(v, srow[r][k]) : v + srow[r][k];
-            mine[k] = v;
-        }
-        else if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * FINISH_ROWS_PER_CTA)
-        {
-            const int r = (threadIdx.x - 32) >> 1, k = threadIdx.x & 1;
-            double w = 0.0;
-            if (r < n)
-            {
-                const double dm = srow[r][ACC_MASS + k], dpx = srow[r][ACC_PX + k], dpy = srow[r][ACC_PY + k];
-                if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
-                {
-                    const double M0 = k ? S.m2 : S.m1, px0 = (k ? S.vx2 : S.vx1) * M0, py0 = (k ? S.vy2 : S.vy1) * M0;
-                    const double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
-                    w = ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
-                }
-            }
-            wred[k][r] = w;
-        }
-        __syncthreads();
-        if (threadIdx.x < 2)
-        {
-            double w = 0.0;
-            for (int r = 0; r < n; ++r) w += wred[threadIdx.x][r];
-            mine[NUM_SUMS + 1 + threadIdx.x] = w;
-        }
-        if (threadIdx.x < 32) __threadfence();      // the writers of `mine` all sit in warp 0
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == int(gridDim.x) - 1;
-        __syncthreads();
-        if (! is_last) return;
-        __threadfence();
-
-        // (C) CTA rows: group g folds rows g, g + 8, ... in order, then the eight groups are folded in order
-        const int col = threadIdx.x % 32, grp = threadIdx.x / 32, ngrp = FINISH_THREADS / 32;
-        const bool is_min = col == NUM_SUMS;
-        double v = is_min ? 1e300 : 0.0;
-        if (col < ROW - 1)
-        {
-            for (int c = grp; c < int(gridDim.x); c += ngrp)
-            {
-                double p = __ldcg(cta_rows + size_t(c) * ROW + col);
-                v = is_min ? dmin(v, p) : v + p;
-            }
-        }
-        fin[grp][col] = v;
-        __syncthreads();
-        if (threadIdx.x < ROW - 1)
-        {
-            const int k = threadIdx.x;
-            double f = fin[0][k];
-            for (int g = 1; g < ngrp; ++g) f = k == NUM_SUMS ? dmin(f, fin[g][k]) : f + fin[g][k];
-            if (k < NUM_SUMS) result->sums[k] = f;
-            else if (k == NUM_SUMS) { result->dt_min = f; dt_min_all = f; }
-            else result->work[k - NUM_SUMS - 1] = f;
-        }
-        if (threadIdx.x == 64)
-        {
-            result->num_negative = fail->count;
-            fail->pad = fail->count;    // how many entries of the list belong to this launch
-            fail->count = 0;            // ready for the next launch that uses this slot
-            *ticket = 0;
-        }
-        if (! prep.enabled) return;
-        if (prep.enabled == 2)
-        {
-            __threadfence();            // this launch's own result (written above) is read back through global memory
-            __syncthreads();
-            peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
-                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results, prep.clock_words);
-            return;
-        }
-
-        // stage inputs of the next step (see prepare_next): one thread per stage
-        __syncthreads();
-        if (threadIdx.x == 96 || threadIdx.x == 97)
-        {
-            const double t = prep.current_a->time, dt = prep.current_a->dt;
-            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
-            const double dt_next = prep.cfg.fixed_dt ? prep.cfg.recommended_time_step : prep.cfg.cfl_number * dt_min_all;
-            // time and dt only: the body positions of next_a were prepared a step ago, those of next_b follow on the
-            // side stream while next_a runs (prepare_positions)
-            if (threadIdx.x == 96) { prep.next_a->time = t_next; prep.next_a->dt = dt_next; }
-            else { prep.next_b->time = t_next + dt_next; prep.next_b->dt = dt_next; }
-        }
-    }
-
-    /**
-     * finish_stage for up to FINISH_CLUSTER_MAX_ROWS blocks as ONE CLUSTER of eight CTAs (thread-block cluster, distributed
-     * shared memory): every CTA folds its share of the blocks -- tile rows -> block row (tile order), block-wise work integral,
-     * column sums by 32 interleaved groups -- then a hardware cluster barrier replaces the __threadfence + ticket of the
-     * multi-CTA version, and CTA 0 folds the eight partial rows through DSMEM in rank order, publishes the result and writes
-     * the next step's time and dt.  This kernel sits on the critical path of every step (stage b -> finish -> next stage a);
-     * eight SMs give it the memory-level parallelism one CTA lacks (the tile rows come from L2, ~2000 cycles away).
-     */
-    constexpr int FINISH_CLUSTER = 8, FINISH_CLUSTER_THREADS = 1024, FINISH_CLUSTER_ROWS = 128;
-    constexpr int FINISH_CLUSTER_MAX_ROWS = FINISH_CLUSTER * FINISH_CLUSTER_ROWS;
-
-    __global__ void __cluster_dims__(FINISH_CLUSTER, 1, 1) __launch_bounds__(FINISH_CLUSTER_THREADS) finish_stage_cluster(
-        const double* tile_rows, int num_fused, int tpb, const double* general_rows, int gtpb, int num_rows,
-        const stage_t* __restrict__ stage_ptr, fail_dev_t* fail, stage_result_t* result, prepare_args_t prep)
-    {
-        namespace cg = cooperative_groups;
-        __shared__ double srows[FINISH_CLUSTER_ROWS][ROW];
-        __shared__ double part[32][ROW];
-        __shared__ double mine[ROW];
-        __shared__ double dt_min_all;
-        auto cluster = cg::this_cluster();
-        const int tid = threadIdx.x, rank = int(cluster.block_rank());
-        const int per = (num_rows + FINISH_CLUSTER - 1) / FINISH_CLUSTER;
-        const int r0 = min(num_rows, rank * per), n = min(num_rows, r0 + per) - r0;
-
-        // (A) one row per block, tiles in tile order, eight loads in flight at a time
-        for (int idx = tid; idx < n * ROW; idx += FINISH_CLUSTER_THREADS)
-        {
-            const int r = idx / ROW, k = idx % ROW, R = r0 + r;
-            if (k > NUM_SUMS) continue;
-            const bool fused = R < num_fused;
-            const int nt = fused ? tpb : gtpb;
-            const double* rows = (fused ? tile_rows + size_t(R) * tpb * ROW : general_rows + size_t(R - num_fused) * gtpb * ROW) + k;
-            double v = k == NUM_SUMS ? 1e300 : 0.0;
-            for (int t0 = 0; t0 < nt; t0 += 8)
-            {
-                double p[8];
-                #pragma unroll
-                for (int t = 0; t < 8; ++t) p[t] = t0 + t < nt ? __ldcg(rows + size_t(t0 + t) * ROW) : (k == NUM_SUMS ? 1e300 : 0.0);
-                #pragma unroll
-                for (int t = 0; t < 8; ++t) v = k == NUM_SUMS ? dmin(v, p[t]) : (t0 + t < nt ? v + p[t] : v);
-            }
-            srows[r][k] = v;
-        }
-        __syncthreads();
-
-        // block-wise work integral (scheme.cpp:363-374, 407-408) into the two spare columns of the block's row
-        const stage_t S = *stage_ptr;
-        for (int idx = tid; idx < 2 * n; idx += FINISH_CLUSTER_THREADS)
-        {
-            const int r = idx >> 1, k = idx & 1;
-            const double dm = srows[r][ACC_MASS + k], dpx = srows[r][ACC_PX + k], dpy = srows[r][ACC_PY + k];
-            double w = 0.0;
-            if (dm != 0.0 || dpx != 0.0 || dpy != 0.0)
-            {
-                const double M0 = k ? S.m2 : S.m1, px0 = (k ? S.vx2 : S.vx1) * M0, py0 = (k ? S.vy2 : S.vy1) * M0;
-                const double M1 = M0 + dm * S.dt, px1 = px0 + dpx * S.dt, py1 = py0 + dpy * S.dt;
-                w = ((px1 * px1 + py1 * py1) / M1 - (px0 * px0 + py0 * py0) / M0) * 0.5;
-            }
-            srows[r][NUM_SUMS + 1 + k] = w;
-        }
-        __syncthreads();
-
-        // (B) this CTA's columns: group g folds rows g, g + 32, ... in order, then the 32 groups are folded in order
-        {
-            const int col = tid % 32, grp = tid / 32;
-            if (col < ROW - 1)
-            {
-                const bool is_min = col == NUM_SUMS;
-                double v = is_min ? 1e300 : 0.0;
-                for (int r = grp; r < n; r += 32)
-                {
-                    double p = srows[r][col];
-                    v = is_min ? dmin(v, p) : v + p;
-                }
-                part[grp][col] = v;
-            }
-        }
-        __syncthreads();
-        if (tid < ROW - 1)
-        {
-            const int k = tid;
-            double f = part[0][k];
-            for (int g = 1; g < 32; ++g) f = k == NUM_SUMS ? dmin(f, part[g][k]) : f + part[g][k];
-            mine[k] = f;
-        }
-        cluster.sync();
-
-        // (C) CTA 0: the eight partial rows through distributed shared memory, in rank order
-        if (rank == 0)
-        {
-            if (tid < ROW - 1)
-            {
-                const int k = tid;
-                double f = mine[k];
-                for (int c = 1; c < FINISH_CLUSTER; ++c)
-                {
-                    const double p = cluster.map_shared_rank(mine, c)[k];
-                    f = k == NUM_SUMS ? dmin(f, p) : f + p;
-                }
-                if (k < NUM_SUMS) result->sums[k] = f;
-                else if (k == NUM_SUMS) { result->dt_min = f; dt_min_all = f; }
-                else result->work[k - NUM_SUMS - 1] = f;
-            }
-            if (tid == 64)
-            {
-                result->num_negative = fail->count;
-                fail->pad = fail->count;
-                fail->count = 0;
-            }
-        }
-        cluster.sync();         // the other CTAs' shared memory stays alive until CTA 0 has read it
-        if (rank != 0 || ! prep.enabled) return;
-        if (prep.enabled == 2)
-        {
-            __threadfence();
-            __syncthreads();
-            peer_prepare(prep.local, prep.peers, prep.me, prep.nranks, prep.slot_stride, prep.slot_a, prep.slot_b, prep.counter,
-                         prep.cfg, prep.current_a, prep.next_a, prep.next_b, prep.host_results, prep.clock_words);
-            return;
-        }
-        if (tid == 96 || tid == 97)
-        {
-            const double t = prep.current_a->time, dt = prep.current_a->dt;
-            const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
-            const double dt_next = prep.cfg.fixed_dt ? prep.cfg.recommended_time_step : prep.cfg.cfl_number * dt_min_all;
-            if (tid == 96) { prep.next_a->time = t_next; prep.next_a->dt = dt_next; }
-            else { prep.next_b->time = t_next + dt_next; prep.next_b->dt = dt_next; }
-        }
-    }
-
-    /**
-     * End of an RK2 step, on the device: fold the two stage results over the ranks (rank order, so every
-     * rank gets the same bits), publish them to the host, and write the stage inputs of the NEXT step --
-     * dt = cfl * min(spacing / wavespeed) (subprog_binary.cpp:281-283), time = t/2 + ((t + dt) + dt)/2
-     * (scheme.cpp:1036, 1055), body positions from compute_two_body_state (scheme.cpp:814) -- so that
-     * the host can queue the next step without waiting for this one.
-     */
-    __global__ void prepare_next(const stage_result_t* __restrict__ gathered, int nranks, int slot_stride, int slot_a, int slot_b,
-        step_config_t cfg, const stage_t* __restrict__ current, stage_t* next_a, stage_t* next_b, stage_result_t* host_results)
-    {
-        // two threads: one per stage result / per stage of the next step
-        __shared__ double dt_min_b;
-        const int k = threadIdx.x;
-        if (k >= 2) return;
-        const int slot = k == 0 ? slot_a : slot_b;
-        stage_result_t r = stage_result_t();
-        r.dt_min = 1e300;
-
-        for (int p = 0; p < nranks; ++p)
-        {
-            const stage_result_t& q = gathered[size_t(p) * slot_stride + slot];
-            for (int c = 0; c < 16; ++c) r.sums[c] += q.sums[c];
-            r.work[0] += q.work[0];
-            r.work[1] += q.work[1];
-            r.dt_min = dmin(r.dt_min, q.dt_min);
-            r.num_negative += q.num_negative;
-        }
-        host_results[slot] = r;
-        if (k == 1) dt_min_b = r.dt_min;
-        __syncwarp(0x3);
-
-        const double t = current[slot_a].time, dt = current[slot_a].dt;
-        const double t_next = t * 0.5 + ((t + dt) + dt) * 0.5;
-        const double dt_next = cfg.fixed_dt ? cfg.recommended_time_step : cfg.cfl_number * dt_min_b;
-        if (k == 0) fill_stage(*next_a, t_next, dt_next, cfg.theta, two_body_state(cfg.elements, t_next), 0.0, 0, 0);
-        else        fill_stage(*next_b, t_next + dt_next, dt_next, cfg.theta, two_body_state(cfg.elements, t_next + dt_next), 0.5, 1, ! cfg.fixed_dt);
-    }
-
-    /** One strip / corner of a block in the guard-zone exchange between ranks (partition.hpp). */
-    /**
-     * disk_mass and disk_angular_momentum of the time series (subprog_binary_diagnostics.cpp:19-41): per block the
-     * sums of sigma dA and (x py - y px) dA, folded in a fixed order; the host adds the blocks in tree order.
-     */
-    __global__ void __launch_bounds__(THREADS) disk_totals_kernel(mesh_dev_t mesh, const double* __restrict__ U, double* __restrict__ out)
-    {
-        __shared__ double red[2][THREADS / 32];
-        const int N = mesh.N, b = blockIdx.x;
-        const double* xv = mesh.xv + size_t(b) * (N + 1);
-        const double* yv = mesh.yv + size_t(b) * (N + 1);
-        double m = 0.0, l = 0.0;
-
-        for (int k = threadIdx.x; k < N * N; k += THREADS)
-        {
-            int i = k / N, j = k % N;
-            size_t c = size_t(b) * N * N + k;
-            double x = 0.5 * (xv[i] + xv[i + 1]), y = 0.5 * (yv[j] + yv[j + 1]);
-            double dA = (xv[i + 1] - xv[i]) * (yv[j + 1] - yv[j]);
-            m += U[c] * dA;
-            l += (mesh.qmode ? U[2 * mesh.FS + c] : x * U[2 * mesh.FS + c] - y * U[mesh.FS + c]) * dA;     // Lz is the third component of conserved_q
-        }
-        m = warp_sum(m); l = warp_sum(l);
-        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m; red[1][threadIdx.x >> 5] = l; }
-        __syncthreads();
-        if (threadIdx.x < 2)
-        {
-            double v = 0.0;
-            for (int w = 0; w < THREADS / 32; ++w) v += red[threadIdx.x][w];
-            out[2 * b + threadIdx.x] = v;
-        }
-    }
-
-    /**
-     * diagnostic_fields (subprog_binary_diagnostics.cpp:48-82): sigma, v_r = v . rhat, v_phi = v . phihat per cell,
-     * block major [B][3][NN] for the writer.
-     */
-    __global__ void diagnostic_fields_kernel(mesh_dev_t mesh, const double* __restrict__ U, double* __restrict__ out, int BO)
-    {
-        const int N = mesh.N;
-        const size_t NN = size_t(N) * N, n = size_t(BO) * NN;
-        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
-        {
-            const size_t b = k / NN, cell = k % NN;
-            const int i = int(cell / N), j = int(cell % N);
-            const double* xv = mesh.xv + b * (N + 1);
-            const double* yv = mesh.yv + b * (N + 1);
-            const double xc = (xv[i] + xv[i + 1]) * 0.5, yc = (yv[j] + yv[j + 1]) * 0.5;
-            const double rc = sqrt(xc * xc + yc * yc);
-            const double sigma = U[k];
-            double vx = U[mesh.FS + k] / sigma, vy = U[2 * mesh.FS + k] / sigma;
-            if (mesh.qmode) angmom_to_linear(xc, yc, vx, vy, vx, vy);
-            out[(b * 3 + 0) * NN + cell] = sigma;
-            out[(b * 3 + 1) * NN + cell] = vx * (xc / rc) + vy * (yc / rc);
-            out[(b * 3 + 2) * NN + cell] = vx * (-yc / rc) + vy * (xc / rc);
-        }
-    }
-
-    /** [B][3][NN] (host, block major) <-> [3][B][NN] (device, field major) */
-    __global__ void permute_state(const double* __restrict__ src, double* __restrict__ dst, int B, int NN, size_t FS, int to_device)
-    {
-        size_t n = size_t(B) * 3 * NN;
-        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
-        {
-            size_t cell = k % NN, q = (k / NN) % 3, b = k / (size_t(3) * NN);
-            size_t field_major = q * FS + b * NN + cell;
-            if (to_device) dst[field_major] = src[k]; else dst[k] = src[field_major];
-        }
-    }
-
-    __global__ void axpby_kernel(const double* __restrict__ a, double wa, const double* __restrict__ b, double wb, double* __restrict__ dst, size_t n)
-    {
-        for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x)
-        {
-            dst[k] = a[k] * wa + b[k] * wb;
-        }
-    }
-
     template<typename T>
     T* device_upload(const std::vector<T>& v)
     {
