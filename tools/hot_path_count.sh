@@ -4,4 +4,4 @@
 set -e
 cd "$(dirname "$0")/../mara3_b200/csrc"
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -DM3B_HOT_PATH_ONLY $EXTRA -cubin -o /tmp/stage_tma_hot.cubin stage_tma.cu
-for v in "${@:-stage_tma<3, 64, true, 1>}" ; do python ../../tools/sass_count.py /tmp/stage_tma_hot.cubin "$v"; done
+for v in "${@:-stage_tma<3, 64, true, 1, 2>}" ; do python ../../tools/sass_count.py /tmp/stage_tma_hot.cubin "$v"; done
